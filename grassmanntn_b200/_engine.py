@@ -1,0 +1,658 @@
+"""Device engine: parity-blocked tensor storage + launch builders for the sm_100a kernels.
+
+Everything numeric happens in libgtn_b200.so (csrc/*.cu) through grassmanntn_b200._cabi; this
+module only does host-side bookkeeping: which parity block goes where, with which scalar sign,
+and which legs carry a sigma vector.  torch is used for device memory and streams only.
+
+Storage (class BT): one contiguous device buffer holding the parity blocks of a Grassmann
+tensor, block (pi_1..pi_n) of the fermionic legs being a row-major array over ALL legs with
+extent e_a (pi_a = 0) or o_a (pi_a = 1) on fermionic leg a.  Element (pi, s) of a fermionic leg
+is parity-preserving index 2s+pi, canonical index encoder(2s+pi) -- the reference's block
+format (reference __init__.py:242-344, :690-729).  A dense canonical tensor with power-of-two
+fermionic dims is the special case e = o = d/2, and is converted both ways by ONE sign-free
+launch of the permute kernel.
+"""
+import ctypes as C
+import itertools
+import math
+
+import numpy as np
+import torch
+
+from . import _cabi
+from ._cabi import AxisEntry, GemmGroup, PermuteJob, SvdOut, SvdProblem, check, count, lib
+from .param import _popcount_vec, canonical_of_block, encoder_array
+
+ENTRY_DT = np.dtype([("in_off", "<i8"), ("out_off", "<i8"), ("P", "<u4"), ("M", "<u4")])
+assert ENTRY_DT.itemsize == C.sizeof(AxisEntry)
+TILE = 32
+FERMI = (1, -1)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def dtype_code(dt):
+    if dt == torch.complex128:
+        return _cabi.GTN_C128
+    if dt == torch.float64:
+        return _cabi.GTN_F64
+    raise TypeError("grassmanntn_b200 computes in float64 / complex128 only, got %s" % dt)
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("grassmanntn_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def _to_dev_bytes(raw):
+    return torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(require_cuda(), non_blocking=True)
+
+
+# ------------------------------------------------------------------------------------------------
+#  generic sign+permute launch builder
+# ------------------------------------------------------------------------------------------------
+class LegTab:
+    """Per-leg tables over the leg's index values: element offsets on both sides and the parity /
+    sigma bits (None = all zero)."""
+    __slots__ = ("n", "in_off", "out_off", "p", "q")
+
+    def __init__(self, n, in_off, out_off, p=None, q=None):
+        self.n = int(n)
+        self.in_off = np.asarray(in_off, dtype=np.int64)
+        self.out_off = np.asarray(out_off, dtype=np.int64)
+        self.p = None if p is None else np.asarray(p, dtype=np.uint32)
+        self.q = None if q is None else np.asarray(q, dtype=np.uint32)
+
+
+def lin_leg(n, in_stride, out_stride, q=None, p=None):
+    r = np.arange(n, dtype=np.int64)
+    return LegTab(n, r * in_stride, r * out_stride, p, q)
+
+
+def _fuse(legs, ids, alpha, beta, Q):
+    """Fuse legs `ids` (slowest first) into one super-axis table."""
+    n = 1
+    in_off = np.zeros(1, dtype=np.int64)
+    out_off = np.zeros(1, dtype=np.int64)
+    P = np.zeros(1, dtype=np.uint32)
+    intra = np.zeros(1, dtype=np.uint32)
+    for a in ids:
+        L = legs[a]
+        in_off = (in_off[:, None] + L.in_off[None, :]).ravel()
+        out_off = (out_off[:, None] + L.out_off[None, :]).ravel()
+        pa = L.p if L.p is not None else np.zeros(L.n, dtype=np.uint32)
+        qa = L.q if L.q is not None else np.zeros(L.n, dtype=np.uint32)
+        ia = np.zeros(L.n, dtype=np.uint32)
+        if alpha[a]:
+            ia ^= pa
+        if beta[a]:
+            ia ^= qa
+        # cross terms with the legs already fused: popcount(P & Qrow[a]) * p_a
+        cross = (_popcount_vec(P & np.uint32(Q[a])) & 1).astype(np.uint32)
+        intra = ((intra[:, None] ^ ia[None, :]) ^ (cross[:, None] & pa[None, :])).ravel()
+        P = (P[:, None] | (pa[None, :] << np.uint32(a))).ravel()
+        n *= L.n
+    M = np.zeros(n, dtype=np.uint32)
+    for a in ids:
+        if Q[a]:
+            M ^= np.where((P >> np.uint32(a)) & 1, np.uint32(Q[a]), np.uint32(0)).astype(np.uint32)
+    tab = np.empty(n, dtype=ENTRY_DT)
+    tab["in_off"] = in_off
+    tab["out_off"] = out_off
+    tab["P"] = P | (intra << np.uint32(31))
+    tab["M"] = M
+    return tab
+
+
+def _choose_groups(dims, in_order, out_order, target=TILE, cap=1 << 16):
+    live_in = [a for a in in_order if dims[a] > 1]
+    live_out = [a for a in out_order if dims[a] > 1]
+    ones = [a for a in range(len(dims)) if dims[a] == 1]
+    if not live_in:
+        return [list(range(len(dims)))], False
+    la, lb = live_in[-1], live_out[-1]
+    if la == lb:
+        A, size = [la], dims[la]
+        k = len(live_in) - 2
+        while k >= 0 and size < target and size * dims[live_in[k]] <= cap:
+            A.insert(0, live_in[k])
+            size *= dims[live_in[k]]
+            k -= 1
+        rem = [a for a in live_in if a not in A]
+        B, size = [], 1
+        while rem and size < 8:
+            B.insert(0, rem.pop())
+            size *= dims[B[0]]
+        transpose = False
+    else:
+        A, B = [la], [lb]
+        sa, sb = dims[la], dims[lb]
+        k = len(live_in) - 2
+        while k >= 0 and sa < target and live_in[k] not in B and sa * dims[live_in[k]] <= cap:
+            A.insert(0, live_in[k])
+            sa *= dims[live_in[k]]
+            k -= 1
+        k = len(live_out) - 2
+        while k >= 0 and sb < target and live_out[k] not in A and sb * dims[live_out[k]] <= cap:
+            B.insert(0, live_out[k])
+            sb *= dims[live_out[k]]
+            k -= 1
+        rem = [a for a in live_in if a not in A and a not in B]
+        transpose = True
+    A = ones + A
+    groups = [A] + ([B] if B else []) + [[a] for a in rem]
+    while len(groups) > _cabi.GTN_MAX_SUPER:
+        g = groups.pop()
+        groups[-1] = groups[-1] + g
+    return groups, transpose
+
+
+def build_job(legs, alpha=None, beta=None, Q=None, const=0, conj=False, in_base=0, out_base=0,
+              in_order=None, out_order=None):
+    """Returns (job_fields, tables list).  Q: list of bitmask rows (symmetric, zero diagonal)."""
+    n = len(legs)
+    if n > 28:
+        raise ValueError("too many legs in one job")
+    alpha = alpha or [0] * n
+    beta = beta or [0] * n
+    Q = Q or [0] * n
+    dims = [L.n for L in legs]
+
+    def stride_of(off):
+        return int(off[1] - off[0]) if len(off) > 1 else 0
+    if in_order is None:
+        in_order = sorted(range(n), key=lambda a: -abs(stride_of(legs[a].in_off)))
+    if out_order is None:
+        out_order = sorted(range(n), key=lambda a: -abs(stride_of(legs[a].out_off)))
+    groups, transpose = _choose_groups(dims, in_order, out_order)
+    tabs = [_fuse(legs, g, alpha, beta, Q) for g in groups]
+    sizes = [len(t) for t in tabs]
+    nA = sizes[0]
+    nB = sizes[1] if len(sizes) > 1 else 1
+    ntiles = ((nA + TILE - 1) // TILE) * ((nB + TILE - 1) // TILE)
+    for s in sizes[2:]:
+        ntiles *= s
+    return dict(in_base=int(in_base), out_base=int(out_base), sizes=sizes, const=int(const) & 1,
+                conj=int(bool(conj)), transpose=int(transpose), ntiles=int(ntiles)), tabs
+
+
+class PermutePlan:
+    """Device-resident job + table arrays for one gtn_sign_permute launch."""
+
+    def __init__(self, jobs):
+        # jobs: list of (fields, tabs)
+        self.njobs = len(jobs)
+        self.max_tiles = 0
+        if self.njobs == 0:
+            return
+        arr = (PermuteJob * self.njobs)()
+        chunks, start = [], 0
+        for k, (f, tabs) in enumerate(jobs):
+            j = arr[k]
+            j.in_base, j.out_base = f["in_base"], f["out_base"]
+            for x in range(_cabi.GTN_MAX_SUPER):
+                j.size[x] = 1
+                j.table_start[x] = 0
+            for x, t in enumerate(tabs):
+                j.size[x] = len(t)
+                j.table_start[x] = start
+                start += len(t)
+                chunks.append(t)
+            j.nsuper = len(tabs)
+            j.const_exp, j.conj, j.transpose, j.ntiles = f["const"], f["conj"], f["transpose"], f["ntiles"]
+            self.max_tiles = max(self.max_tiles, f["ntiles"])
+        self.jobs_dev = _to_dev_bytes(bytes(arr))
+        self.entries_dev = _to_dev_bytes(np.concatenate(chunks).tobytes())
+
+    def run(self, src, dst, scale=1.0):
+        if self.njobs == 0:
+            return
+        code = dtype_code(src.dtype)
+        s = complex(scale)
+        # grid.y is limited to 65535 jobs; far above any block count we generate
+        check(lib.gtn_sign_permute(_ptr(src), _ptr(dst), code, _ptr(self.jobs_dev), _ptr(self.entries_dev),
+                                   self.njobs, self.max_tiles, s.real, s.imag, _stream()), "gtn_sign_permute")
+        count()
+
+
+# ------------------------------------------------------------------------------------------------
+#  block tensor
+# ------------------------------------------------------------------------------------------------
+def sigma_bits(pi, n):
+    """sigma exponent bit of block element (pi, s), s < n: bit 1 of popcount(canonical index)
+    (reference sgn[blck][axis][sub_i] = param.sgn(param.encoder(i)), __init__.py:300-303)."""
+    c = canonical_of_block(pi, np.arange(n, dtype=np.int64))
+    return ((_popcount_vec(c) >> 1) & 1).astype(np.uint32)
+
+
+class BT:
+    """Parity-blocked Grassmann tensor on the device."""
+
+    def __init__(self, stats, edims, odims, dtype, fmt="standard"):
+        self.stats = tuple(stats)
+        self.e = tuple(int(x) for x in edims)
+        self.o = tuple(int(x) if s in FERMI else 0 for x, s in zip(odims, self.stats))
+        self.dtype = dtype
+        self.fmt = fmt
+        self.faxes = tuple(a for a, s in enumerate(self.stats) if s in FERMI)
+        self.off = {}        # pattern -> element offset (stored blocks only)
+        self.zero = set()    # stored blocks known to be identically zero
+        self.buf = None
+
+    # ---- geometry
+    @property
+    def ndim(self):
+        return len(self.stats)
+
+    def patterns(self):
+        return itertools.product((0, 1), repeat=len(self.faxes))
+
+    def block_shape(self, pat):
+        shp = list(self.e)
+        for a, pi in zip(self.faxes, pat):
+            shp[a] = self.e[a] if pi == 0 else self.o[a]
+        return tuple(shp)
+
+    def block_size(self, pat):
+        return int(np.prod(self.block_shape(pat), dtype=np.int64)) if self.ndim else 1
+
+    def alloc(self, pats=None, zero=False):
+        pats = list(self.patterns()) if pats is None else list(pats)
+        total = 0
+        for p in pats:
+            self.off[p] = total
+            total += self.block_size(p)
+        dev = require_cuda()
+        self.buf = (torch.zeros if zero else torch.empty)(max(total, 1), dtype=self.dtype, device=dev)
+        return self
+
+    def live(self):
+        """stored, not-known-zero, non-empty blocks"""
+        return [p for p in self.off if p not in self.zero and self.block_size(p) > 0]
+
+    def is_even(self):
+        return all(sum(p) % 2 == 0 for p in self.live())
+
+    def block_view(self, pat):
+        shp = self.block_shape(pat)
+        n = self.block_size(pat)
+        if pat in self.off:
+            return self.buf[self.off[pat]: self.off[pat] + n].view(shp)
+        return torch.zeros(shp, dtype=self.dtype, device=self.buf.device if self.buf is not None else require_cuda())
+
+    def key(self):
+        return (self.stats, self.e, self.o, str(self.dtype), self.fmt,
+                tuple(sorted((p, o) for p, o in self.off.items())), tuple(sorted(self.zero)))
+
+    def leg(self, a):
+        return (self.stats[a], self.e[a], self.o[a])
+
+    def clone(self):
+        r = BT(self.stats, self.e, self.o, self.dtype, self.fmt)
+        r.off = dict(self.off)
+        r.zero = set(self.zero)
+        r.buf = self.buf.clone()
+        return r
+
+    def sumsq(self, pats=None):
+        acc = torch.zeros(1, dtype=torch.float64, device=self.buf.device)
+        code = dtype_code(self.dtype)
+        covered = sum(self.block_size(p) for p in self.off)
+        if pats is None and len(self.zero) == 0 and covered == self.buf.numel():
+            # the stored blocks tile the buffer exactly: one launch
+            check(lib.gtn_sumsq(_ptr(self.buf), self.buf.numel(), code, _ptr(acc), 0, _stream()), "gtn_sumsq")
+            count()
+        else:
+            for p in (self.live() if pats is None else pats):
+                if p in self.off and self.block_size(p) > 0:
+                    v = self.buf[self.off[p]:]
+                    check(lib.gtn_sumsq(_ptr(v), self.block_size(p), code, _ptr(acc), 0, _stream()), "gtn_sumsq")
+                    count()
+        return acc
+
+    def norm(self):
+        return math.sqrt(float(self.sumsq().item()))
+
+    def scale_(self, s):
+        s = complex(s)
+        check(lib.gtn_scale(_ptr(self.buf), self.buf.numel(), dtype_code(self.dtype), s.real, s.imag, _stream()),
+              "gtn_scale")
+        count()
+        return self
+
+
+def _row_strides(shape):
+    st, acc = [0] * len(shape), 1
+    for a in range(len(shape) - 1, -1, -1):
+        st[a] = acc
+        acc *= shape[a]
+    return st
+
+
+_plan_cache = {}
+
+
+def _cached(key, builder):
+    p = _plan_cache.get(key)
+    if p is None:
+        if len(_plan_cache) > 4096:
+            _plan_cache.clear()
+        p = builder()
+        _plan_cache[key] = p
+    return p
+
+
+# ---- dense <-> BT --------------------------------------------------------------------------
+def _dense_leg_maps(d, stat, encoder):
+    """for storage index i of a dense fermionic leg: (pi, s)."""
+    i = np.arange(d, dtype=np.int64)
+    if stat not in FERMI:
+        return None, i
+    j = i if encoder == "parity-preserving" else encoder_array(d)    # parity-preserving index
+    return (j & 1), (j >> 1)
+
+
+def bt_from_dense(data, stats, encoder="canonical", fmt="standard", check_even=True):
+    """dense (canonical or parity-preserving) torch tensor -> BT; one sign-free launch.
+    Replaces the element-wise Python loop of reference block.__init__ (__init__.py:311-337)."""
+    shape = tuple(data.shape)
+    e = [((d + 1) // 2 if s in FERMI else d) for d, s in zip(shape, stats)]
+    o = [(d // 2 if s in FERMI else 0) for d, s in zip(shape, stats)]
+    bt = BT(stats, e, o, data.dtype, fmt).alloc()
+    if data.numel() == 0:
+        return bt
+    data = data.contiguous()
+
+    def build():
+        in_st = _row_strides(shape)
+        legs = []
+        # out offset of element = off[pattern] + sum s_a * stride_a(pattern); for power-of-two dims all
+        # non-empty blocks have equal shape, so the offset is separable per leg
+        pats = [p for p in bt.patterns() if bt.block_size(p) > 0]
+        ref_shape = bt.block_shape(pats[0])
+        if any(bt.block_shape(p) != ref_shape for p in pats):
+            raise ValueError("Error[dense]: Some of the fermionic tensor shapes are not a power of two.")
+        bstr = _row_strides(ref_shape)
+        bsize = bt.block_size(pats[0])
+        # weight of pi_a in the pattern index (patterns with an empty block never occur)
+        weights, w = {}, 1
+        for a in reversed(bt.faxes):
+            if bt.o[a] > 0:
+                weights[a] = w
+                w *= 2
+            else:
+                weights[a] = 0
+        # recompute offsets to match the separable formula
+        for p in pats:
+            bt.off[p] = sum(weights[a] * pi for a, pi in zip(bt.faxes, p)) * bsize
+        for a, (d, s) in enumerate(zip(shape, stats)):
+            pi, sidx = _dense_leg_maps(d, s, encoder)
+            i = np.arange(d, dtype=np.int64)
+            if pi is None:
+                legs.append(LegTab(d, i * in_st[a], i * bstr[a]))
+            else:
+                legs.append(LegTab(d, i * in_st[a], pi * (weights[a] * bsize) + sidx * bstr[a]))
+        order = list(range(len(shape)))
+        return PermutePlan([build_job(legs, in_order=order, out_order=order)]), dict(bt.off)
+    plan, off = _cached(("d2b", shape, tuple(stats), encoder, str(data.dtype)), build)
+    bt.off = dict(off)
+    for p in list(bt.off):
+        if bt.block_size(p) == 0:
+            del bt.off[p]
+    plan.run(data.view(-1), bt.buf)
+    if check_even and bt.faxes:
+        odd = [p for p in bt.off if sum(p) % 2 == 1]
+        if odd and float(bt.sumsq(odd).item()) == 0.0:
+            bt.zero.update(odd)
+    return bt
+
+
+def _pad_pow2(n):
+    return 1 if n <= 1 else 2 ** int(math.ceil(math.log2(n)))
+
+
+def bt_dense_shape(bt):
+    return tuple((_pad_pow2(bt.e[a] + bt.o[a]) if bt.stats[a] in FERMI else bt.e[a]) for a in range(bt.ndim))
+
+
+def bt_to_dense(bt, encoder="canonical"):
+    """BT -> dense torch tensor (fermionic dims padded to powers of two), one launch.
+    Replaces reference todense (__init__.py:690-729)."""
+    shape = bt_dense_shape(bt)
+    live = bt.live()
+    full = all(bt.e[a] + bt.o[a] == shape[a] for a in bt.faxes) and len(live) == 2 ** len(bt.faxes)
+    dev = require_cuda()
+    out = (torch.empty if full else torch.zeros)(shape, dtype=bt.dtype, device=dev)
+    if out.numel() == 0 or not live:
+        return out
+
+    def build():
+        ost = _row_strides(shape)
+        jobs = []
+        for p in live:
+            bshape = bt.block_shape(p)
+            bstr = _row_strides(bshape)
+            pis = dict(zip(bt.faxes, p))
+            legs = []
+            for a in range(bt.ndim):
+                s = np.arange(bshape[a], dtype=np.int64)
+                if a in pis:
+                    j = 2 * s + pis[a]
+                    if encoder == "canonical":
+                        j = canonical_of_block(pis[a], s)
+                    legs.append(LegTab(bshape[a], s * bstr[a], j * ost[a]))
+                else:
+                    legs.append(LegTab(bshape[a], s * bstr[a], s * ost[a]))
+            order = list(range(bt.ndim))
+            jobs.append(build_job(legs, in_base=bt.off[p], in_order=order, out_order=order))
+        return PermutePlan(jobs)
+    plan = _cached(("b2d", bt.key(), encoder), build)
+    plan.run(bt.buf, out.view(-1))
+    return out
+
+
+# ---- in-place style elementwise sign passes (format switch) -----------------------------------
+def bt_switch_format(bt):
+    """sigma on every conjugated (-1) leg: reference dense.switch_format (__init__.py:1011-1068) /
+    block.switch_format (:537-571).  One launch, new buffer."""
+    out = BT(bt.stats, bt.e, bt.o, bt.dtype, "matrix" if bt.fmt == "standard" else "standard")
+    out.off = dict(bt.off)
+    out.zero = set(bt.zero)
+    out.buf = torch.empty_like(bt.buf)
+    live = bt.live()
+    if bt.zero:
+        out.buf.zero_()
+
+    def build():
+        jobs = []
+        for p in live:
+            bshape = bt.block_shape(p)
+            bstr = _row_strides(bshape)
+            pis = dict(zip(bt.faxes, p))
+            legs, beta = [], []
+            for a in range(bt.ndim):
+                if a in pis and bt.stats[a] == -1:
+                    legs.append(lin_leg(bshape[a], bstr[a], bstr[a], q=sigma_bits(pis[a], bshape[a])))
+                    beta.append(1)
+                else:
+                    legs.append(lin_leg(bshape[a], bstr[a], bstr[a]))
+                    beta.append(0)
+            order = list(range(bt.ndim))
+            jobs.append(build_job(legs, beta=beta, in_base=bt.off[p], out_base=bt.off[p], in_order=order, out_order=order))
+        return PermutePlan(jobs)
+    _cached(("fmt", bt.key()), build).run(bt.buf, out.buf)
+    return out
+
+
+def bt_force_standard(bt):
+    return bt if bt.fmt == "standard" else bt_switch_format(bt)
+
+
+# ------------------------------------------------------------------------------------------------
+#  group layouts (joined index spaces)
+# ------------------------------------------------------------------------------------------------
+class GroupLayout:
+    """Index space of a list of legs joined together.  Patterns (parities of the fermionic
+    members) are ordered with even total parity first; inside a pattern the members form a
+    row-major mixed-radix index."""
+
+    def __init__(self, legs):
+        self.legs = list(legs)                      # (stat, e, o)
+        self.fpos = [k for k, L in enumerate(self.legs) if L[0] in FERMI]
+        pats = list(itertools.product((0, 1), repeat=len(self.fpos)))
+        pats.sort(key=lambda p: (sum(p) % 2, p))
+        self.pats, self.offset, self.size, self.shape = [], {}, {}, {}
+        acc = 0
+        self.even_total = 0
+        for p in pats:
+            shp = [L[1] for L in self.legs]
+            for k, pi in zip(self.fpos, p):
+                shp[k] = self.legs[k][1] if pi == 0 else self.legs[k][2]
+            sz = int(np.prod(shp, dtype=np.int64)) if shp else 1
+            self.pats.append(p)
+            self.offset[p] = acc
+            self.size[p] = sz
+            self.shape[p] = tuple(shp)
+            acc += sz
+            if sum(p) % 2 == 0:
+                self.even_total = acc
+        self.total = acc
+
+    def sector(self, parity):
+        """(start, length) of the rows with total parity `parity`"""
+        return (0, self.even_total) if parity == 0 else (self.even_total, self.total - self.even_total)
+
+    def strides(self, p):
+        return _row_strides(self.shape[p])
+
+
+# ------------------------------------------------------------------------------------------------
+#  grouped GEMM
+# ------------------------------------------------------------------------------------------------
+class GemmPlan:
+    def __init__(self, groups, dtype):
+        self.n = len(groups)
+        self.tiles = 0
+        if self.n == 0:
+            return
+        arr = (GemmGroup * self.n)()
+        for k, g in enumerate(groups):
+            a = arr[k]
+            a.a_off, a.b_off, a.c_off = g["a_off"], g["b_off"], g["c_off"]
+            a.lda, a.ldb, a.ldc = g["lda"], g["ldb"], g["ldc"]
+            a.batch_stride_a = g.get("bsa", 0)
+            a.batch_stride_b = g.get("bsb", 0)
+            a.batch_stride_c = g.get("bsc", 0)
+            a.m, a.n, a.k, a.batch = g["m"], g["n"], g["k"], g.get("batch", 1)
+            a.alpha, a.beta = g.get("alpha", 1.0), g.get("beta", 0.0)
+        self.tiles = int(lib.gtn_gemm_plan_host(arr, self.n, dtype_code(dtype)))
+        self.dev = _to_dev_bytes(bytes(arr))
+
+    def run(self, A, B, Cm):
+        if self.n == 0 or self.tiles == 0:
+            return
+        check(lib.gtn_grouped_gemm(_ptr(A), _ptr(B), _ptr(Cm), dtype_code(A.dtype), _ptr(self.dev), self.n,
+                                   self.tiles, _stream()), "gtn_grouped_gemm")
+        count()
+
+
+def gemm(A, B, m, n, k, lda=None, ldb=None, ldc=None, out=None):
+    """plain C[m,n] = A[m,k] B[k,n] on the DMMA kernel (row-major)."""
+    if out is None:
+        out = torch.empty(m * n, dtype=A.dtype, device=A.device)
+    plan = _cached(("gemm1", m, n, k, lda, ldb, ldc, str(A.dtype)), lambda: GemmPlan(
+        [dict(a_off=0, b_off=0, c_off=0, lda=lda or k, ldb=ldb or n, ldc=ldc or n, m=m, n=n, k=k)], A.dtype))
+    plan.run(A, B, out)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+#  batched Jacobi SVD
+# ------------------------------------------------------------------------------------------------
+JACOBI_TOL = 1e-15
+JACOBI_MAX_SWEEPS = 60
+
+
+def batched_svd(mats):
+    """mats: list of 2-D device tensors (row-major, any shapes).  Returns list of (U, s, Vh) with
+    U (m x r), s (r, host numpy, descending), Vh (r x n), r = min(m, n); all through the Jacobi
+    kernels in csrc/gtn_svd.cu.  Replaces np.linalg.svd of reference SortedSVD (__init__.py:3932)."""
+    if not mats:
+        return []
+    dev = mats[0].device
+    dt = mats[0].dtype
+    code = dtype_code(dt)
+    probs, works, transposed = [], [], []
+    woff = zoff = soff = 0
+    for Mx in mats:
+        m, n = Mx.shape
+        tr = m > n
+        Wm = (Mx.transpose(0, 1) if tr else Mx).contiguous()
+        p, q = Wm.shape
+        probs.append((woff, zoff, p, q, soff))
+        works.append(Wm.reshape(-1))
+        transposed.append(tr)
+        woff += p * q
+        zoff += p * p
+        soff += p
+    nprob = len(mats)
+    maxp = max(pr[2] for pr in probs)
+    maxq = max(pr[3] for pr in probs)
+    W = torch.cat(works) if nprob > 1 else works[0].clone()
+    if W.numel() == 0:
+        W = torch.zeros(1, dtype=dt, device=dev)
+    Z = torch.empty(max(zoff, 1), dtype=dt, device=dev)
+    parr = (SvdProblem * nprob)()
+    oarr = (SvdOut * nprob)()
+    for k, (wo, zo, p, q, so) in enumerate(probs):
+        parr[k].w_off, parr[k].z_off, parr[k].p, parr[k].q = wo, zo, p, q
+        oarr[k].s_off, oarr[k].u_off = so, zo
+    pdev = _to_dev_bytes(bytes(parr))
+    odev = _to_dev_bytes(bytes(oarr))
+    st = _stream()
+    check(lib.gtn_jacobi_init(_ptr(Z), code, _ptr(pdev), nprob, maxp, st), "gtn_jacobi_init")
+    count()
+    offd = torch.zeros(nprob, dtype=torch.float64, device=dev)
+    sweeps = 0
+    if maxp >= 2:
+        while True:
+            check(lib.gtn_jacobi_sweep(_ptr(W), _ptr(Z), code, _ptr(pdev), nprob, maxp, maxq, JACOBI_TOL,
+                                       _ptr(offd), st), "gtn_jacobi_sweep")
+            P = (maxp + 1) & ~1
+            count(P - 1)
+            sweeps += 1
+            if float(offd.max().item()) <= JACOBI_TOL:
+                break
+            if sweeps >= JACOBI_MAX_SWEEPS:
+                raise _cabi.GtnError("Jacobi SVD did not converge in %d sweeps" % sweeps)
+    U = torch.empty_like(Z)
+    Vh = torch.empty_like(W)
+    s = torch.empty(max(soff, 1), dtype=torch.float64, device=dev)
+    order = torch.empty(max(soff, 1), dtype=torch.int32, device=dev)
+    scratch = torch.empty(max(soff, 1), dtype=torch.float64, device=dev)
+    check(lib.gtn_jacobi_finish(_ptr(W), _ptr(Z), _ptr(U), _ptr(Vh), _ptr(s), code, _ptr(pdev), _ptr(odev),
+                                _ptr(order), _ptr(scratch), nprob, maxp, maxq, st), "gtn_jacobi_finish")
+    count(2)
+    s_host = s.cpu().numpy()
+    outs = []
+    for (wo, zo, p, q, so), tr in zip(probs, transposed):
+        Uk = U[zo: zo + p * p].view(p, p)
+        Vk = Vh[wo: wo + p * q].view(p, q)
+        sk = s_host[so: so + p].copy()
+        if tr:
+            # W = A^T = Uk diag(s) Vk  =>  A = Vk^T diag(s) Uk^T
+            outs.append((Vk.transpose(0, 1), sk, Uk.transpose(0, 1)))
+        else:
+            outs.append((Uk, sk, Vk))
+    batched_svd.last_sweeps = sweeps
+    return outs
+
+
+batched_svd.last_sweeps = 0

@@ -1,0 +1,665 @@
+"""Grassmann einsum / decomposition / conjugation on parity-blocked device tensors (BT).
+
+Host logic only decides, per parity block, where the block goes, its scalar sign and which legs
+carry a sigma vector; the data movement and arithmetic are three kernels:
+  pack   (gtn_sign_permute)  operand blocks  -> packed [rows x cols] matrices, rows/cols ordered
+                              by (total parity, parity pattern, offset)
+  gemm   (gtn_grouped_gemm)   one DMMA GEMM per output parity block, K restricted to the parity
+                              sector that can be non-zero for Grassmann-even operands
+  svd    (gtn_jacobi_*)       batched one-sided Jacobi on the even/odd sector matrices
+References: einsum_ds / einsum_block (reference __init__.py:1633-2306, :2346-2941), svd / eig /
+decompose_block (:4033-4308, :4425-4698, :4704-5289), hconjugate(_block) (:5300-5493, :5495-5955).
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import _planner as P
+from ._engine import (BT, FERMI, GemmPlan, GroupLayout, PermutePlan, _cached, _ptr, _row_strides, _stream,
+                      batched_svd, bt_force_standard, bt_switch_format, build_job, dtype_code, gemm, lin_leg,
+                      require_cuda, sigma_bits)
+from ._cabi import check, count, lib
+
+NUMER_CUTOFF = 1.0e-14      # reference __init__.py:30 (module global numer_cutoff)
+
+
+def _err(msg):
+    raise P.GtnValueError(msg)
+
+
+# ------------------------------------------------------------------------------------------------
+#  packing an operand into [batch][rows][cols][t]
+# ------------------------------------------------------------------------------------------------
+def _label_legs(bt, labels):
+    info = {}
+    for a, ch in enumerate(labels):
+        leg = bt.leg(a)
+        if ch in info:
+            if info[ch][1:] != leg[1:]:
+                _err("Error[einsum]: index '%s' has inconsistent dimensions" % ch)
+        else:
+            info[ch] = leg
+    return info
+
+
+def _pack_jobs(bt, labels, info, groups, lays, assigned, out_elems_mult=None):
+    """Jobs that copy every live block of `bt` into the packed buffer.
+    groups: dict name -> list of labels for 'B' (batch), 'R', 'C', 'T'; lays: GroupLayout per name.
+    assigned: (alpha labels, beta labels, Q pairs) evaluated by this operand."""
+    alpha_l, beta_l, q_pairs = assigned
+    tot = {k: lays[k].total for k in lays}
+    mult = {"T": 1, "C": tot["T"], "R": tot["T"] * tot["C"], "B": tot["T"] * tot["C"] * tot["R"]}
+    uniq = list(dict.fromkeys(labels))
+    where = {}
+    for g, lst in groups.items():
+        for pos, ch in enumerate(lst):
+            where[ch] = (g, pos)
+    jobs = []
+    used = set()
+    for pat in bt.live():
+        pis = dict(zip(bt.faxes, pat))
+        par, ok = {}, True
+        for a, ch in enumerate(labels):
+            if a in pis:
+                if ch in par and par[ch] != pis[a]:
+                    ok = False           # traced pair with different parities: off the diagonal
+                    break
+                par[ch] = pis[a]
+        if not ok:
+            continue
+        gp = {g: tuple(par[ch] for ch in lst if info[ch][0] in FERMI) for g, lst in groups.items()}
+        used.add(tuple(gp[g] for g in ("B", "R", "C", "T")))
+        out_base = sum(lays[g].offset[gp[g]] * mult[g] for g in lays)
+        bshape = bt.block_shape(pat)
+        bstr = _row_strides(bshape)
+        legs, beta = [], []
+        for ch in uniq:
+            axes = [a for a, c in enumerate(labels) if c == ch]
+            n = bshape[axes[0]]
+            g, pos = where[ch]
+            ostr = lays[g].strides(gp[g])[pos] * mult[g]
+            q = None
+            if ch in beta_l:
+                q = sigma_bits(par[ch], n)
+            legs.append(lin_leg(n, sum(bstr[a] for a in axes), ostr, q=q))
+            beta.append(1 if ch in beta_l else 0)
+        const = 0
+        for x in alpha_l:
+            const ^= par[x]
+        for pr in q_pairs:
+            x, y = tuple(pr)
+            const ^= par[x] & par[y]
+        jobs.append(build_job(legs, beta=beta, const=const, in_base=bt.off[pat], out_base=out_base))
+    return jobs, used
+
+
+def _pack(bt, labels, info, groups, assigned, restrict_even=None):
+    """returns (buffer [B*R*C] after the t-sum, layouts, set of written (pB,pR,pC,pT))."""
+    lays = {g: GroupLayout([info[ch] for ch in groups[g]]) for g in ("B", "R", "C", "T")}
+    key = ("pack", bt.key(), tuple(labels), tuple((g, tuple(groups[g])) for g in ("B", "R", "C", "T")),
+           tuple(sorted(assigned[0])), tuple(sorted(assigned[1])), tuple(sorted(tuple(sorted(p)) for p in assigned[2])))
+
+    def build():
+        jobs, used = _pack_jobs(bt, labels, info, groups, lays, assigned)
+        return PermutePlan(jobs), used
+    plan, used = _cached(key, build)
+    total = lays["B"].total * lays["R"].total * lays["C"].total * lays["T"].total
+    # which regions will be read?  if the operand is even, consumers only touch parity-matched
+    # sectors; zero-fill whenever some region that may be read is not written.
+    need = 1
+    for g in ("B", "R", "C", "T"):
+        need *= len(lays[g].pats)
+    even = bt.is_even() if restrict_even is None else restrict_even
+    if even:
+        # traced labels are diagonal in parity; parity(pR)+parity(pC) must be even
+        readable = sum(1 for pb in lays["B"].pats for pr in lays["R"].pats for pc in lays["C"].pats
+                       for pt in lays["T"].pats if (sum(pr) + sum(pc)) % 2 == 0)
+        full = len(used) >= readable
+    else:
+        full = len(used) >= need
+    dev = require_cuda()
+    buf = (torch.empty if full else torch.zeros)(max(total, 1), dtype=bt.dtype, device=dev)
+    plan.run(bt.buf, buf)
+    if lays["T"].total > 1 or groups["T"]:
+        rows = lays["B"].total * lays["R"].total * lays["C"].total
+        red = torch.empty(max(rows, 1), dtype=bt.dtype, device=dev)
+        check(lib.gtn_rowsum(_ptr(buf), _ptr(red), rows, lays["T"].total, dtype_code(bt.dtype), _stream()),
+              "gtn_rowsum")
+        count()
+        buf = red
+    return buf, lays, even
+
+
+def _out_bt(info, out_labels, dtype, lays_order, pats_offsets):
+    stats = [info[ch][0] for ch in out_labels]
+    e = [info[ch][1] for ch in out_labels]
+    o = [info[ch][2] for ch in out_labels]
+    bt = BT(stats, e, o, dtype)
+    bt.off = dict(pats_offsets)
+    return bt
+
+
+# ------------------------------------------------------------------------------------------------
+#  einsum
+# ------------------------------------------------------------------------------------------------
+def einsum_bt(subscripts, ops, ignore_anticommutation=False):
+    inputs, output = P.parse_subscripts(subscripts)
+    if len(inputs) != len(ops):
+        _err("Error[einsum]: the number of subscripts does not match the number of operands")
+    ops = [bt_force_standard(o) for o in ops]
+    for sub, o in zip(inputs, ops):
+        if len(sub) != o.ndim:
+            _err("Error[einsum]: subscript '%s' does not match a tensor with %d legs" % (sub, o.ndim))
+    dt = torch.complex128 if any(o.dtype == torch.complex128 for o in ops) else torch.float64
+    ops = [o if o.dtype == dt else _cast(o, dt) for o in ops]
+    if len(ops) > 2:
+        return _einsum_fold(inputs, output, ops, ignore_anticommutation)
+    prog, first_stat, contracted = P.einsum_sign_program(inputs, output, [o.stats for o in ops],
+                                                         ignore_anticommutation)
+    if len(ops) == 1:
+        return _einsum_single(inputs[0], output, ops[0], prog)
+    return _einsum_pair(inputs, output, ops, prog)
+
+
+def _cast(bt, dt):
+    r = BT(bt.stats, bt.e, bt.o, dt, bt.fmt)
+    r.off, r.zero = dict(bt.off), set(bt.zero)
+    r.buf = bt.buf.to(dt)
+    return r
+
+
+def _einsum_fold(inputs, output, ops, ignore):
+    """N >= 3 operands: contract left to right (Grassmann contraction is associative as long as
+    the operands stay in order); every pairwise step is a full Grassmann einsum."""
+    cur_sub, cur = inputs[0], ops[0]
+    for k in range(1, len(ops)):
+        rest = "".join(inputs[k + 1:]) + (output or "")
+        both = cur_sub + inputs[k]
+        keep = []
+        for ch in dict.fromkeys(both):
+            cnt = both.count(ch)
+            st = (cur.stats[cur_sub.index(ch)] if ch in cur_sub else ops[k].stats[inputs[k].index(ch)])
+            if ch in rest:
+                keep.append(ch)
+            elif st == 0 and cnt == 1:
+                pass           # lone bosonic index summed away
+            elif cnt == 1:
+                keep.append(ch)
+        if k == len(ops) - 1:
+            sub = cur_sub + "," + inputs[k] + ("->" + output if output is not None else "")
+        else:
+            sub = cur_sub + "," + inputs[k] + "->" + "".join(keep)
+        cur = einsum_bt(sub, [cur, ops[k]], ignore)
+        cur_sub = "".join(keep)
+    return cur
+
+
+def _scalar(buf):
+    v = buf[:1].cpu().numpy()[0]
+    return v
+
+
+def _einsum_single(labels, output, bt, prog):
+    info = _label_legs(bt, labels)
+    out = output or ""
+    t_labels = [ch for ch in dict.fromkeys(labels) if ch not in out]
+    for ch in dict.fromkeys(labels):
+        if labels.count(ch) == 2 and ch in out:
+            raise NotImplementedError("einsum: a repeated index that is kept in the output is not supported")
+    groups = {"B": [], "R": list(out), "C": [], "T": t_labels}
+    buf, lays, even = _pack(bt, labels, info, groups, (prog.alpha, prog.beta, prog.Q))
+    if output is None:
+        return _scalar(buf)
+    res = _out_bt(info, out, bt.dtype, None, {})
+    for p in lays["R"].pats:
+        if even and sum(p) % 2 == 1:
+            continue
+        if lays["R"].size[p] > 0:
+            res.off[p] = lays["R"].offset[p]
+    # the layout is parity-sorted: for an even tensor the (never written) odd part is the tail
+    res.buf = buf[: max(lays["R"].even_total, 1)] if even else buf
+    return res
+
+
+def _einsum_pair(inputs, output, ops, prog):
+    la, lb = inputs
+    A, B = ops
+    infoA, infoB = _label_legs(A, la), _label_legs(B, lb)
+    info = dict(infoA)
+    for ch, leg in infoB.items():
+        if ch in info and info[ch][1:] != leg[1:]:
+            _err("Error[einsum]: index '%s' has inconsistent dimensions" % ch)
+        info.setdefault(ch, leg)
+    out = output or ""
+    cls = {}
+    for ch in dict.fromkeys(la + lb):
+        cA, cB, co = la.count(ch), lb.count(ch), out.count(ch)
+        if cA == 2 and cB == 0 and co == 0:
+            cls[ch] = "tA"
+        elif cB == 2 and cA == 0 and co == 0:
+            cls[ch] = "tB"
+        elif cA == 1 and cB == 1 and co == 0:
+            cls[ch] = "K"
+        elif cA == 1 and cB == 1 and co == 1:
+            if info[ch][0] != 0:
+                _err("Error[einsum]: Inconsistent index statistics.")
+            cls[ch] = "batch"
+        elif cA == 1 and cB == 0:
+            cls[ch] = "M" if co == 1 else "tA"
+        elif cB == 1 and cA == 0:
+            cls[ch] = "N" if co == 1 else "tB"
+        else:
+            raise NotImplementedError("einsum: unsupported index multiplicity for '%s'" % ch)
+    M = [ch for ch in out if cls[ch] == "M"]
+    N = [ch for ch in out if cls[ch] == "N"]
+    batch = [ch for ch in out if cls[ch] == "batch"]
+    K = [ch for ch in la if cls[ch] == "K"]
+    tA = [ch for ch in dict.fromkeys(la) if cls[ch] == "tA"]
+    tB = [ch for ch in dict.fromkeys(lb) if cls[ch] == "tB"]
+    # left operand = the one whose free legs come first in the output
+    swap = False
+    if M and N and out.index(N[0]) < out.index(M[0]):
+        swap = True
+    if swap:
+        L, R = (B, lb, infoB, N, tB), (A, la, infoA, M, tA)
+    else:
+        L, R = (A, la, infoA, M, tA), (B, lb, infoB, N, tB)
+    Lset, Rset = set(L[1]), set(R[1])
+    asg = {"L": (set(), set(), set()), "R": (set(), set(), set())}
+    cross = set()
+    for x in prog.alpha:
+        asg["L" if x in Lset else "R"][0].add(x)
+    for x in prog.beta:
+        asg["L" if x in Lset else "R"][1].add(x)
+    for pr in prog.Q:
+        x, y = tuple(pr)
+        if x in Lset and y in Lset:
+            asg["L"][2].add(pr)
+        elif x in Rset and y in Rset:
+            asg["R"][2].add(pr)
+        else:
+            cross.add(pr)
+    gL = {"B": batch, "R": L[3], "C": K, "T": L[4]}
+    gR = {"B": batch, "R": K, "C": R[3], "T": R[4]}
+    even = L[0].is_even() and R[0].is_even()
+    bufL, layL, _ = _pack(L[0], L[1], info, gL, asg["L"], restrict_even=even)
+    bufR, layR, _ = _pack(R[0], R[1], info, gR, asg["R"], restrict_even=even)
+    layM, layK, layN, layB = layL["R"], layL["C"], layR["C"], layL["B"]
+    Mtot, Ktot, Ntot, Btot = layM.total, layK.total, layN.total, layB.total
+    tmp_labels = batch + L[3] + R[3]
+    res = _out_bt(info, tmp_labels, A.dtype, None, {})
+    # output blocks: pattern over (M fermions, N fermions) in tmp order
+    groups, acc = [], 0
+    Mferm = [ch for ch in L[3] if info[ch][0] in FERMI]
+    Nferm = [ch for ch in R[3] if info[ch][0] in FERMI]
+    for pM in layM.pats:
+        for pN in layN.pats:
+            m, n = layM.size[pM], layN.size[pN]
+            if even and (sum(pM) + sum(pN)) % 2 == 1:
+                continue
+            if m == 0 or n == 0:
+                continue
+            if even:
+                k0, kl = layK.sector(sum(pM) % 2)
+            else:
+                k0, kl = 0, Ktot
+            par = dict(zip(Mferm, pM))
+            par.update(zip(Nferm, pN))
+            e = 0
+            for pr in cross:
+                x, y = tuple(pr)
+                e ^= par[x] & par[y]
+            pat = tuple(pM) + tuple(pN)
+            res.off[pat] = acc
+            groups.append(dict(a_off=layM.offset[pM] * Ktot + k0, b_off=k0 * Ntot + layN.offset[pN], c_off=acc,
+                               lda=Ktot, ldb=Ntot, ldc=n, m=m, n=n, k=kl, batch=Btot,
+                               bsa=Mtot * Ktot, bsb=Ktot * Ntot, bsc=m * n, alpha=-1.0 if e else 1.0))
+            acc += Btot * m * n
+    dev = require_cuda()
+    res.buf = torch.empty(max(acc, 1), dtype=A.dtype, device=dev)
+    key = ("gemmplan", str(A.dtype), tuple(tuple(sorted(g.items())) for g in groups))
+    plan = _cached(key, lambda: GemmPlan(groups, A.dtype))
+    if Ktot == 0:
+        res.buf.zero_()
+    else:
+        plan.run(bufL, bufR, res.buf)
+    if output is None:
+        return _scalar(res.buf)
+    if "".join(tmp_labels) == out:
+        return res
+    # bring the legs into the requested order (all signs are already applied)
+    return permute_bt(res, "".join(tmp_labels), out)
+
+
+def permute_bt(bt, labels, out_labels):
+    """sign-free leg permutation of a BT (one launch)."""
+    info = _label_legs(bt, labels)
+    groups = {"B": [], "R": list(out_labels), "C": [], "T": []}
+    buf, lays, even = _pack(bt, labels, info, groups, (set(), set(), set()))
+    res = _out_bt(info, out_labels, bt.dtype, None, {})
+    for p in lays["R"].pats:
+        if even and sum(p) % 2 == 1:
+            continue
+        if lays["R"].size[p] > 0:
+            res.off[p] = lays["R"].offset[p]
+    # the layout is parity-sorted: for an even tensor the (never written) odd part is the tail
+    res.buf = buf[: max(lays["R"].even_total, 1)] if even else buf
+    return res
+
+
+# ------------------------------------------------------------------------------------------------
+#  decompositions
+# ------------------------------------------------------------------------------------------------
+def _rank_rule(s, cutoff):
+    """reference SortedSVD (__init__.py:3935-3944)"""
+    if len(s) == 0:
+        return 0
+    nnz = int(np.sum(np.abs(s / (abs(s[0]) + NUMER_CUTOFF)) > NUMER_CUTOFF))
+    if cutoff is not None and cutoff < nnz:
+        nnz = cutoff
+    return nnz
+
+
+def _join_sign_terms(legs_idx, stats, fermionic):
+    """sign program of joining legs into one leg of statistic -1 in matrix format:
+    (-1)^p on the +1 members (get_grouping_sign_factors, __init__.py:3250-3275; join_legs_block
+    :3574-3580) times sigma of the joined index = prod sigma_a * (-1)^{sum_{a<b} p_a p_b}
+    (switch_format on the joined leg, :3036; join_index's sgn_sigma_perm, :3357-3366)."""
+    f = [a for a in legs_idx if fermionic[a]]
+    alpha = {a for a in f if stats[a] == 1}
+    beta = set(f)
+    Q = {frozenset((a, b)) for i, a in enumerate(f) for b in f[i + 1:]}
+    return alpha, beta, Q
+
+
+def _block_jobs(bt, live, alpha, beta, Q, place):
+    """jobs over blocks with leg-level sign terms; place(pat, bshape) -> (out_base, out_strides) or None"""
+    jobs = []
+    for pat in live:
+        pis = dict(zip(bt.faxes, pat))
+        bshape = bt.block_shape(pat)
+        pl = place(pat, bshape)
+        if pl is None:
+            continue
+        out_base, ostr, conj = pl
+        bstr = _row_strides(bshape)
+        legs, bflags = [], []
+        for a in range(bt.ndim):
+            q = sigma_bits(pis[a], bshape[a]) if a in beta else None
+            legs.append(lin_leg(bshape[a], bstr[a], ostr[a], q=q))
+            bflags.append(1 if a in beta else 0)
+        const = 0
+        for a in alpha:
+            const ^= pis[a]
+        for pr in Q:
+            x, y = tuple(pr)
+            const ^= pis[x] & pis[y]
+        jobs.append(build_job(legs, beta=bflags, const=const, conj=conj, in_base=bt.off[pat], out_base=out_base))
+    return jobs
+
+
+def decompose_bt(bt, nl, cutoff, kind, rule):
+    """U, S, V of the (first nl legs | remaining legs) matricisation.
+    rule 'dense': reference BlockSVD/BlockEig rank rule (int(cutoff/2) per sector, pad to a power of
+    two, __init__.py:3998-4015); rule 'block': decompose_block's (ceil/floor, pad to max, :5076-5103)."""
+    this_fmt = bt.fmt
+    bt = bt_force_standard(bt)
+    n = bt.ndim
+    Rl, Cl = list(range(nl)), list(range(nl, n))
+    ferm = [s in FERMI for s in bt.stats]
+    fR, fC = any(ferm[a] for a in Rl), any(ferm[a] for a in Cl)
+    if not bt.is_even():
+        _err("Error[BlockSVD]: This matrix is not constructed from a Grassmann-even tensor.")
+    layR = GroupLayout([bt.leg(a) for a in Rl])
+    layC = GroupLayout([bt.leg(a) for a in Cl])
+    sectors = [0, 1] if (fR and fC) else [0]
+    if fR != fC:
+        # one side purely bosonic: an even tensor then lives entirely in the parity-0 rows/cols
+        pass
+    alpha, beta, Q = (_join_sign_terms(Rl, bt.stats, ferm) if fR else (set(), set(), set()))
+    rows = {s: layR.sector(s) for s in (0, 1)}
+    cols = {s: layC.sector(s) for s in (0, 1)}
+    if not (fR and fC):
+        # one side purely bosonic: an even tensor lives entirely in the parity-0 rows / columns
+        rows = {0: layR.sector(0)}
+        cols = {0: layC.sector(0)}
+    live = bt.live()
+    dev = require_cuda()
+    fpos_R = [a for a in Rl if ferm[a]]
+    fpos_C = [a for a in Cl if ferm[a]]
+
+    def pats_of(pat):
+        pis = dict(zip(bt.faxes, pat))
+        return tuple(pis[a] for a in fpos_R), tuple(pis[a] for a in fpos_C)
+
+    # ---- pack the sector matrices (one launch)
+    sizes = {s: (rows[s][1], cols[s][1]) for s in sectors}
+    offs, acc = {}, 0
+    for s in sectors:
+        offs[s] = acc
+        acc += sizes[s][0] * sizes[s][1]
+    nlive_needed = sum(1 for pr in layR.pats for pc in layC.pats if (sum(pr) + sum(pc)) % 2 == 0)
+
+    def build_pack():
+        def place(pat, bshape):
+            pr, pc = pats_of(pat)
+            s = (sum(pr) % 2) if (fR and fC) else 0
+            ld = sizes[s][1]
+            base = offs[s] + (layR.offset[pr] - rows[s][0]) * ld + (layC.offset[pc] - cols[s][0])
+            sr, sc = layR.strides(pr), layC.strides(pc)
+            return base, [x * ld for x in sr] + list(sc), False
+        return PermutePlan(_block_jobs(bt, live, alpha, beta, Q, place))
+    plan = _cached(("svdpack", bt.key(), nl), build_pack)
+    Mbuf = (torch.empty if len(live) >= nlive_needed else torch.zeros)(max(acc, 1), dtype=bt.dtype, device=dev)
+    plan.run(bt.buf, Mbuf)
+    mats = [Mbuf[offs[s]: offs[s] + sizes[s][0] * sizes[s][1]].view(sizes[s][0], sizes[s][1]) for s in sectors]
+    if kind == "eig":
+        for Mx in mats:
+            if Mx.shape[0] != Mx.shape[1]:
+                _err("Error[SortedEig]: The input matrix is not Hermitian!")
+            nrm2 = torch.zeros(2, dtype=torch.float64, device=dev)
+            # Hermiticity check ||M - M^H|| / ||M|| <= 1e-14 (reference :4316-4321), on device buffers
+            D = (Mx - Mx.conj().transpose(0, 1)).contiguous()
+            check(lib.gtn_sumsq(_ptr(D), D.numel(), dtype_code(D.dtype), _ptr(nrm2[0:]), 0, _stream()), "gtn_sumsq")
+            check(lib.gtn_sumsq(_ptr(Mx), Mx.numel(), dtype_code(Mx.dtype), _ptr(nrm2[1:]), 0, _stream()), "gtn_sumsq")
+            count(2)
+            dn, mn = [math.sqrt(v) for v in nrm2.cpu().tolist()]
+            if mn >= NUMER_CUTOFF and dn / mn > NUMER_CUTOFF:
+                _err("Error[SortedEig]: The input matrix is not Hermitian!")
+    usv = batched_svd(mats)
+
+    # ---- rank rule
+    if len(sectors) == 2:
+        if rule == "dense":
+            cuts = [None, None] if cutoff is None else [int(cutoff / 2)] * 2
+        else:
+            cuts = [None, None] if cutoff is None else [int(math.ceil(cutoff / 2)), int(math.floor(cutoff / 2))]
+    else:
+        cuts = [cutoff]
+    keep = [_rank_rule(usv[i][1], cuts[i]) for i in range(len(sectors))]
+    if len(sectors) == 2:
+        d = max(keep)
+        if rule == "dense":
+            d = int(2 ** math.ceil(np.log2(d))) if d > 0 else 0
+        dims_x = (d, d)
+    else:
+        d = keep[0]
+        dims_x = (d, 0)
+    bond_stat = (1, -1) if len(sectors) == 2 else (0, 0)
+
+    # signed eigenvalues for eig: L_k = sum_ij s_i V_ij U_jk (reference :4340-4341)
+    svals = []
+    for i, s in enumerate(sectors):
+        U, sv, Vh = usv[i]
+        k = keep[i]
+        if kind == "eig" and k > 0:
+            Uk = U[:, :k].contiguous()
+            Vk = Vh[:k, :].contiguous()
+            VU = gemm(Vk.view(-1), Uk.view(-1), k, k, U.shape[0]).view(k, k).cpu().numpy()
+            lam = np.einsum("i,ik->k", sv[:k].astype(VU.dtype), VU)
+            svals.append(lam)
+        else:
+            svals.append(sv[:k])
+
+    # ---- U tensor: legs R + x
+    Ust = tuple(bt.stats[a] for a in Rl) + (bond_stat[0],)
+    Ue = tuple(bt.e[a] for a in Rl) + (dims_x[0],)
+    Uo = tuple(bt.o[a] for a in Rl) + (dims_x[1],)
+    Ubt = BT(Ust, Ue, Uo, bt.dtype)
+    Vst = (bond_stat[1],) + tuple(bt.stats[a] for a in Cl)
+    Ve = (dims_x[0],) + tuple(bt.e[a] for a in Cl)
+    Vo = (dims_x[1],) + tuple(bt.o[a] for a in Cl)
+    Vbt = BT(Vst, Ve, Vo, bt.dtype)
+    two = len(sectors) == 2
+    if two:
+        upats = [tuple(pr) + (sum(pr) % 2,) for pr in layR.pats]
+        vpats = [(sum(pc) % 2,) + tuple(pc) for pc in layC.pats]
+    else:
+        upats = [tuple(pr) for pr in layR.pats if sum(pr) % 2 == 0]
+        vpats = [tuple(pc) for pc in layC.pats if sum(pc) % 2 == 0]
+    Ubt.alloc([p for p in upats if Ubt.block_size(p) > 0], zero=True)
+    Vbt.alloc([p for p in vpats if Vbt.block_size(p) > 0], zero=True)
+    # U: one launch per sector source buffer (different base pointers)
+    for i, s in enumerate(sectors):
+        U, sv, Vh = usv[i]
+        k = keep[i]
+        if k == 0:
+            continue
+        if kind == "eig":
+            Vh = U.conj().transpose(0, 1)
+        Uc = U.contiguous()
+        ldu = Uc.shape[1]
+        Vc = Vh.contiguous()
+        ldv = Vc.shape[1]
+        # -- U blocks of this sector
+        src = BT(tuple(bt.stats[a] for a in Rl) + (0,), tuple(bt.e[a] for a in Rl) + (k,),
+                 tuple(bt.o[a] for a in Rl) + (0,), bt.dtype)
+        src.buf = Uc.view(-1)
+        for pr in layR.pats:
+            if (sum(pr) % 2 if two else 0) != s or layR.size[pr] == 0:
+                continue
+            if not two and sum(pr) % 2 == 1:
+                continue
+            src.off[pr] = (layR.offset[pr] - rows[s][0]) * ldu
+
+        def build_u(src=src, s=s, k=k, ldu=ldu):
+            jobs = []
+            for pr in src.off:
+                shp = layR.shape[pr]
+                pis = dict(zip(fpos_R, pr))
+                upat = tuple(pr) + ((s,) if two else ())
+                ostr = _row_strides(Ubt.block_shape(upat))
+                sr = layR.strides(pr)
+                legs, bflags = [], []
+                for j, a in enumerate(Rl):
+                    q = sigma_bits(pis[a], shp[j]) if a in beta else None
+                    legs.append(lin_leg(shp[j], sr[j] * ldu, ostr[j], q=q))
+                    bflags.append(1 if a in beta else 0)
+                legs.append(lin_leg(k, 1, ostr[len(Rl)]))
+                bflags.append(0)
+                const = 0
+                for a in alpha:
+                    const ^= pis[a]
+                for prr in Q:
+                    x, y = tuple(prr)
+                    const ^= pis[x] & pis[y]
+                jobs.append(build_job(legs, beta=bflags, const=const, in_base=src.off[pr], out_base=Ubt.off[upat]))
+            return PermutePlan(jobs)
+        _cached(("svdU", bt.key(), nl, s, k, ldu, dims_x, kind), build_u).run(src.buf, Ubt.buf)
+
+        # -- V blocks: V_std[x, C] = sigma(x) * Vh[x, C]   (x is the conjugated (-1) leg)
+        def build_v(s=s, k=k, ldv=ldv):
+            jobs = []
+            for pc in layC.pats:
+                if (sum(pc) % 2 if two else 0) != s or layC.size[pc] == 0:
+                    continue
+                if not two and sum(pc) % 2 == 1:
+                    continue
+                shp = layC.shape[pc]
+                vpat = ((s,) if two else ()) + tuple(pc)
+                ostr = _row_strides(Vbt.block_shape(vpat))
+                sc = layC.strides(pc)
+                legs = [lin_leg(k, ldv, ostr[0], q=sigma_bits(s, k) if two else None)]
+                bflags = [1 if two else 0]
+                for j in range(len(Cl)):
+                    legs.append(lin_leg(shp[j], sc[j], ostr[1 + j]))
+                    bflags.append(0)
+                jobs.append(build_job(legs, beta=bflags, in_base=layC.offset[pc] - cols[s][0], out_base=Vbt.off[vpat]))
+            return PermutePlan(jobs)
+        _cached(("svdV", bt.key(), nl, s, k, ldv, dims_x, kind), build_v).run(Vc.view(-1), Vbt.buf)
+
+    # ---- S tensor (tiny): diag(sigma(x) * s) per sector, built on the host
+    Sbt = BT((bond_stat[1], bond_stat[0]), (dims_x[0],) * 2, (dims_x[1],) * 2, bt.dtype)
+    spats = [(0, 0), (1, 1)] if two else [()]
+    Sbt.alloc([p for p in spats if Sbt.block_size(p) > 0], zero=True)
+    host = np.zeros(max(Sbt.buf.numel(), 1), dtype=np.complex128 if bt.dtype == torch.complex128 else np.float64)
+    for i, s in enumerate(sectors):
+        k = keep[i]
+        p = (s, s) if two else ()
+        if k == 0 or p not in Sbt.off:
+            continue
+        dd = dims_x[s] if two else dims_x[0]
+        sg = (1 - 2 * sigma_bits(s, k).astype(np.int64)) if two else np.ones(k, dtype=np.int64)
+        vals = np.asarray(svals[i]) * sg
+        if host.dtype == np.float64:
+            vals = np.real(vals)
+        idx = Sbt.off[p] + np.arange(k) * (dd + 1)
+        host[idx] = vals
+    if Sbt.buf.numel() > 0 and host.size > 0:
+        Sbt.buf.copy_(torch.from_numpy(host[: Sbt.buf.numel()]))
+    outs = [Ubt, Sbt, Vbt]
+    if this_fmt == "matrix":
+        outs = [bt_switch_format(x) for x in outs]
+    return outs[0], outs[1], outs[2], tuple(keep)
+
+
+def hconjugate_bt(bt, nl):
+    """Hermitian conjugate of the (first nl | rest) matricisation, one launch.
+    reference hconjugate (__init__.py:5300-5493) / hconjugate_block (:5495-5955)."""
+    this_fmt = bt.fmt
+    bt = bt_force_standard(bt)
+    n = bt.ndim
+    Rl, Cl = list(range(nl)), list(range(nl, n))
+    ferm = [s in FERMI for s in bt.stats]
+    new_order = Cl + Rl
+    flip = lambda s: -s if s in FERMI else s
+    res = BT([flip(bt.stats[a]) for a in new_order], [bt.e[a] for a in new_order], [bt.o[a] for a in new_order],
+             bt.dtype)
+    # join signs of the old row group (stats as they are) ...
+    a1, b1, q1 = _join_sign_terms(Rl, bt.stats, ferm)
+    # ... and split signs of the new row group = old column group with FLIPPED statistics
+    fl = {a: flip(bt.stats[a]) for a in range(n)}
+    a2, b2, q2 = _join_sign_terms(Cl, fl, ferm)
+    alpha, beta, Q = a1 ^ a2, b1 ^ b2, q1 ^ q2
+    live = bt.live()
+    npat = lambda pat: tuple(dict(zip(bt.faxes, pat))[a] for a in new_order if ferm[a])
+    res.alloc([npat(p) for p in live])
+
+    def build():
+        def place(pat, bshape):
+            op = npat(pat)
+            ostr_new = _row_strides(res.block_shape(op))
+            ostr = [0] * n
+            for newpos, a in enumerate(new_order):
+                ostr[a] = ostr_new[newpos]
+            return res.off[op], ostr, True
+        return PermutePlan(_block_jobs(bt, live, alpha, beta, Q, place))
+    _cached(("hconj", bt.key(), nl), build).run(bt.buf, res.buf)
+    res.zero = set()
+    if this_fmt == "matrix":
+        res = bt_switch_format(res)
+    return res
+
+
+def power_bt(bt, p, rcond=1e-10):
+    """element-wise power in matrix format with the |x| > rcond mask: reference power_ds
+    (__init__.py:6059-6069) and the *fixed* power_block (:6071-6082, see oracle/ref_harness.py)."""
+    this_fmt = bt.fmt
+    m = bt if bt.fmt == "matrix" else bt_switch_format(bt)
+    if m is bt:
+        m = bt.clone()
+    check(lib.gtn_pow_rcond(_ptr(m.buf), m.buf.numel(), dtype_code(m.dtype), float(p), float(rcond), _stream()),
+          "gtn_pow_rcond")
+    count()
+    return m if this_fmt == "matrix" else bt_switch_format(m)

@@ -1,0 +1,162 @@
+"""Coarse-graining drivers of the 2D gauge-theory example on the B200 ops.
+
+Same call signatures and return values as the reference's gauge2d.trg / atrg2dy / atrg2dx / zcap /
+logZ (reference gauge2d.py:1591-1889, and the block twin gauge2d_block.py); one implementation
+serves dense and block tensors because every op underneath works on the parity-blocked device
+storage.  The tensor-network contractions are the algorithm (Levin-Nave TRG; ATRG) and therefore
+use the same index patterns as the reference; everything else (no deep copies, no progress bars,
+normalisation fused into one scale kernel) is new.
+
+The initial-tensor construction (tensor_preparation, get_ABtensors, compress_*) is out of scope
+(SURVEY.md section 8): load the fixture with `load_initial_tensor`.
+"""
+import math
+import os
+
+import numpy as np
+
+import grassmanntn_b200 as gtn
+
+_GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+
+
+def load_initial_tensor(path=None):
+    """Z2, N_f=1, beta=m=q=a=1, mu=0 site tensor produced once by the reference
+    (tests/golden/make_z2_tensor.py): shape (8,8,8,8,2,2), statistics (1,1,-1,-1,0,0)."""
+    path = path or os.path.join(_GOLDEN, "z2_initial_tensor.npz")
+    z = np.load(path)
+    stats = tuple(int(s) for s in z["statistics"])
+    return gtn.dense(z["data"], statistics=stats, encoder=str(z["encoder"]), format=str(z["format"]))
+
+
+def _normalised(T):
+    Tnorm = T.norm
+    return T * (1.0 / Tnorm), Tnorm
+
+
+def zcap(T):
+    """sum over the two bosonic legs (reference gauge2d.py:1591-1597)."""
+    n = T.shape[4]
+    capper = gtn.dense(np.full((n, n), 1.0), statistics=(0, 0))
+    if isinstance(T, gtn.block):
+        capper = capper.toblock()
+    return gtn.einsum("IJKLij,ij->IJKL", T, capper)
+
+
+def logZ(T, boundary_conditions="periodic"):
+    """log of the trace of T with (anti-)periodic boundary in the second direction
+    (reference gauge2d.py:1599-1615).  Like gauge2d_block.py:1608 the anti-periodic sign is NOT
+    applied to block tensors."""
+    if boundary_conditions == "anti-periodic" and not isinstance(T, gtn.block):
+        # (-1)^{p(J)} on leg J == switch_parity restricted to leg 1; as a Grassmann einsum this is
+        # the trace with the sign vector folded into the block signs
+        bt = T._get_bt().clone()
+        for p in bt.live():
+            if dict(zip(bt.faxes, p)).get(1, 0) == 1:
+                bt.buf[bt.off[p]: bt.off[p] + bt.block_size(p)].neg_()
+        T = gtn.dense._from_bt(bt, T.encoder)
+    Z = gtn.einsum("IJIJ", T)
+    return np.log(Z)
+
+
+def trg(T, dcut=64, iternum=None, error_test=False):
+    """One Levin-Nave TRG step (reference gauge2d.py:1647-1755).  T: shape (m,n,m,n), statistics
+    (1,1,-1,-1).  Returns (T', Tnorm[, err])."""
+    if [T.shape[0], T.shape[1]] != [T.shape[2], T.shape[3]]:
+        gtn.error("Error[trg]: The shape must be of the form (m,n,m,n)!")
+    if gtn.make_list(T.statistics) != [1, 1, -1, -1]:
+        gtn.error("Error[trg]: The statistics must be (1,1,-1,-1)!")
+    T1 = gtn.einsum("ijkl->jkli", T)
+    T2 = gtn.einsum("ijkl->klij", T)
+    U1, S1, V1 = T1.svd("ab|cd", dcut)
+    U2, S2, V2 = T2.svd("ab|cd", dcut)
+    sq = gtn.sqrt(S1)
+    U1 = gtn.einsum("abx,xc->abc", U1, sq)
+    V1 = gtn.einsum("ax,xbc->abc", sq, V1)
+    sq = gtn.sqrt(S2)
+    U2 = gtn.einsum("abx,xc->abc", U2, sq)
+    V2 = gtn.einsum("ax,xbc->abc", sq, V2)
+    VV = gtn.einsum("kwz,lxw->lxzk", V1, V2)
+    UU = gtn.einsum("yxi,zyj->jzxi", U1, U2)
+    Tn = gtn.einsum("lxzk,jzxi->ijkl", VV, UU)
+    err = None
+    if error_test:
+        Z1 = gtn.einsum("ijkl,klij", T, T)
+        Z2 = gtn.einsum("ijij", Tn)
+        err = np.abs(1 - Z2 / Z1)
+    Tn, Tnorm = _normalised(Tn)
+    return (Tn, Tnorm, err) if error_test else (Tn, Tnorm)
+
+
+def atrg2dy(T1, T2, dcut=64, intermediate_dcut=None, iternum=None, error_test=False, alignment="y"):
+    """One ATRG step along y (reference gauge2d.py:1761-1869)."""
+    if intermediate_dcut is None:
+        intermediate_dcut = dcut
+    T1o, T2o = T1, T2
+    T1 = gtn.einsum("ijkl->lijk", T1)
+    T2 = gtn.einsum("ijkl->lijk", T2)
+    U1, S1, V1 = T1.svd("li|jk", intermediate_dcut)
+    U2, S2, V2 = T2.svd("li|jk", intermediate_dcut)
+    A = V1
+    B = gtn.einsum("lia,ab->lib", U1, S1)
+    C = gtn.einsum("ab,bjk->ajk", S2, V2)
+    D = U2
+    M = gtn.einsum("ajk,jib->aibk", C, B)
+    U, S, V = M.svd("ai|bk", intermediate_dcut)
+    sq = gtn.sqrt(S)
+    Y = gtn.einsum("abx,xc->abc", U, sq)
+    X = gtn.einsum("ax,xbc->abc", sq, V)
+    Q1 = gtn.einsum("iax,xbj->ijab", D, Y)
+    Q2 = gtn.einsum("kya,ylb->abkl", X, A)
+    Q = gtn.einsum("ijab,abkl->ijkl", Q1, Q2)
+    U, S, V = Q.svd("ij|kl", dcut)
+    sq = gtn.sqrt(S)
+    H = gtn.einsum("abx,xc->abc", U, sq)
+    G = gtn.einsum("ax,xbc->abc", sq, V)
+    H = gtn.einsum("lai->ila", H)
+    G = gtn.einsum("kaj->ajk", G)
+    T = gtn.einsum("ila,ajk->ijkl", H, G)
+    err = None
+    if error_test:
+        Z1 = gtn.einsum("IJIK,iKiJ", T1o, T2o)
+        Z2 = gtn.einsum("IJIJ", T)
+        err = np.abs(1 - Z2 / Z1)
+    T, Tnorm = _normalised(T)
+    return (T, Tnorm, err) if error_test else (T, Tnorm)
+
+
+def _swap_xy(T):
+    return gtn.einsum("jikl->jilk", gtn.einsum("ijkl->jikl", T))
+
+
+def atrg2dx(T1, T2, dcut=64, intermediate_dcut=None, iternum=None, error_test=False):
+    """One ATRG step along x: swap the legs, atrg2dy, swap back (reference gauge2d.py:1871-1889)."""
+    same = T1 is T2
+    T1 = _swap_xy(T1)
+    T2 = T1 if same else _swap_xy(T2)
+    out = atrg2dy(T1, T2, dcut, intermediate_dcut, iternum, error_test, alignment="x")
+    return (_swap_xy(out[0]),) + tuple(out[1:])
+
+
+def coarse_grain(T, cgsteps=5, dcut=32, method="atrg", boundary_conditions="anti-periodic", error_test=False):
+    """The 2D loop of example.py:156-196 (after zcap): returns the list of per-step records
+    (volume, F, Tnorm, err, shape)."""
+    logNorm = 0.0
+    records = []
+    F = logZ(T, boundary_conditions) + logNorm
+    records.append(dict(vol=1, F=complex(F), Tnorm=None, err=None, shape=T.shape[:2]))
+    cgxfirst = T.shape[0] > T.shape[1]
+    for i in range(cgsteps):
+        if method == "trg":
+            out = trg(T, dcut, iternum=i, error_test=error_test)
+        else:
+            use_x = (i % 2 == 0) == cgxfirst
+            fn = atrg2dx if use_x else atrg2dy
+            out = fn(T, T, dcut, iternum=i, error_test=error_test)
+        T, Tnorm = out[0], out[1]
+        vol = 2 ** (i + 1)
+        logNorm = 2 * logNorm + math.log(Tnorm)
+        F = (logZ(T, boundary_conditions) + logNorm) / vol
+        records.append(dict(vol=vol, F=complex(F), Tnorm=float(Tnorm), err=(out[2] if error_test else None),
+                            shape=T.shape[:2]))
+    return T, records

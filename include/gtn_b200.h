@@ -1,0 +1,188 @@
+/*
+ * gtn_b200.h -- C ABI of libgtn_b200.so, the sm_100a kernels behind grassmanntn_b200.
+ *
+ * The reference (ayosprakob/grassmanntn) is pure Python/numpy and has no FFI boundary; its
+ * "operator interface" is the numpy / opt_einsum / LAPACK call sites its Grassmann algebra
+ * bottoms out in (SURVEY.md section 1, table "L0 call").  Each entry point below replaces one
+ * family of those call sites; the citation says which (file:line relative to the reference
+ * repository root).  All pointers are DEVICE pointers unless the name ends in _host, all sizes
+ * are element counts, every call takes the CUDA stream to launch on, returns 0 on success or a
+ * negative gtn_status / positive cudaError_t, never throws and never allocates.
+ *
+ * Data types: GTN_F64 = IEEE double, GTN_C128 = interleaved (re, im) doubles (numpy complex128,
+ * torch.complex128).
+ */
+#ifndef GTN_B200_H
+#define GTN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GTN_F64 0
+#define GTN_C128 1
+
+#define GTN_MAX_SUPER 8 /* super-axes per sign-permute job (see gtn_permute_job) */
+
+typedef enum {
+  GTN_OK = 0,
+  GTN_ERR_BAD_ARG = -1,
+  GTN_ERR_UNSUPPORTED = -2,
+  GTN_ERR_NOT_CONVERGED = -3
+} gtn_status;
+
+/* ------------------------------------------------------------------------------------------
+ * Fused sign + permute (+ encoder gather, + conjugate, + scale).
+ *
+ * Replaces: the sign tensors S1/S3 that einsum_ds materialises element by element and feeds
+ * to opt_einsum (__init__.py:1962-1999, :2088-2126, :2295) whenever they only re-order data;
+ * dense.switch_format / switch_encoder / switch_parity (__init__.py:1011-1154: `dat*v[ss]`,
+ * `dat.take(...)`); join_legs / split_legs (__init__.py:3015, :3027, :3036-3050, :3112-3157);
+ * hconjugate's conj-transpose (__init__.py:5428); block <-> dense conversion
+ * (__init__.py:311-337, :701-725) and join/split_legs_block's element copies (:3582-3586).
+ *
+ *   out[out_base + sum_X out_off_X(i_X)] = scale * (+-1) * maybe_conj( in[in_base + sum_X in_off_X(i_X)] )
+ *
+ * The tensor is presented as <= GTN_MAX_SUPER "super-axes" (one or several fused tensor legs).
+ * Every super-axis X has a table of gtn_axis_entry, one per index value i_X: the element
+ * offsets on both sides (so strides, diagonals, encoder gathers and block interleaves are all
+ * just tables), the Grassmann-parity bits P of the legs it fuses and M = Qsym*P, the GF(2)
+ * image of P under the symmetric pair matrix of the sign program.  The sign exponent is the
+ * quadratic form
+ *     e = const ^ XOR_X intra_X ^ XOR_{X<Y} parity(P_Y & M_X)
+ * i.e. exactly (-1)^{sum_a alpha_a p_a + beta_a q_a + sum_{a<b} Q_ab p_a p_b} over the legs'
+ * parities p_a = popcount(index)&1 and sigma bits q_a = (popcount(index)>>1)&1, which is what
+ * param.gparity / param.sgn (param.py:61-73) and relative_sign (__init__.py:1553-1591) evaluate
+ * element by element in the reference.  Sign tensors are never materialised.
+ *
+ * Super-axis 0 is contiguous on the INPUT side (tile rows are read along it), super-axis 1 is
+ * contiguous on the OUTPUT side (tile rows are written along it); the kernel transposes
+ * 32x32 tiles through shared memory.  If `transpose` is 0 both sides are contiguous along
+ * super-axis 0 and the tile goes straight through registers.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int64_t in_off;  /* element offset contributed on the input side  */
+  int64_t out_off; /* element offset contributed on the output side */
+  uint32_t P;      /* bits 0..27: parity bits of the fused legs; bit 31: intra-axis sign exponent */
+  uint32_t M;      /* bits 0..27: Qsym * P (GF(2)) */
+} gtn_axis_entry;
+
+typedef struct {
+  int64_t in_base;                 /* element offset of this job inside `in`  */
+  int64_t out_base;                /* element offset of this job inside `out` */
+  int64_t table_start[GTN_MAX_SUPER]; /* first entry of super-axis X inside `entries` */
+  int32_t size[GTN_MAX_SUPER];     /* extent of super-axis X (unused ones = 1) */
+  int32_t nsuper;                  /* number of super-axes in use (>= 1) */
+  int32_t const_exp;               /* constant sign exponent (0/1) */
+  int32_t conj;                    /* 1: complex-conjugate the element */
+  int32_t transpose;               /* 1: shared-memory tile transpose between axis 0 and axis 1 */
+  int64_t ntiles;                  /* number of 32x32 tiles (CTAs) of this job */
+} gtn_permute_job;
+
+/* Launch `njobs` jobs in ONE grid (grid.y = job, grid.x = max_tiles). `jobs` and `entries` are
+ * device arrays (built once per plan by the host and cached).  scale_re/scale_im multiply
+ * every element (scale_im ignored for GTN_F64). */
+int gtn_sign_permute(const void* in, void* out, int dtype, const gtn_permute_job* jobs,
+                     const gtn_axis_entry* entries, int njobs, int64_t max_tiles,
+                     double scale_re, double scale_im, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Grouped GEMM on the FP64 tensor cores (DMMA m8n8k4), row-major operands.
+ *
+ * Replaces: oe.contract(..) of the two data operands in einsum_ds (__init__.py:2295) and the
+ * per-parity-block np.einsum of einsum_block (__init__.py:2781, :2928).
+ *
+ *   for every group g:  C_g[M x N] (ldc) = alpha_g * A_g[M x K] (lda) * B_g[K x N] (ldb) + beta_g * C_g
+ *
+ * offsets are in elements from the base pointers; a group may be repeated `batch` times with
+ * strides (batch index is the slowest loop).  GTN_C128 is computed as four real DMMA products
+ * per tile with the complex arithmetic expanded in registers.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int64_t a_off, b_off, c_off;
+  int64_t lda, ldb, ldc;
+  int64_t batch_stride_a, batch_stride_b, batch_stride_c;
+  int32_t m, n, k, batch;
+  double alpha; /* real scalar (block sign S1*S3 = +-1 in einsum_block, __init__.py:2761) */
+  double beta;  /* 0 or 1 */
+  int64_t tile_start; /* prefix sum of CTA tiles (filled by gtn_gemm_plan_host) */
+} gtn_gemm_group;
+
+/* Fills tile_start for all groups on the HOST array and returns the total CTA count. */
+int64_t gtn_gemm_plan_host(gtn_gemm_group* groups_host, int ngroups, int dtype);
+
+int gtn_grouped_gemm(const void* A, const void* B, void* C, int dtype,
+                     const gtn_gemm_group* groups_dev, int ngroups, int64_t total_tiles,
+                     void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Batched one-sided Jacobi SVD (Hestenes) of the parity-sector matrices.
+ *
+ * Replaces: np.linalg.svd(M, full_matrices=False) in SortedSVD (__init__.py:3932) and
+ * SortedEig (__init__.py:4323), i.e. LAPACK gesdd, for the E/O sectors of BlockSVD/BlockEig
+ * (:4002-4003, :4394-4395) and decompose_block (:5083-5088).
+ *
+ * W_b (p_b x q_b row-major, ld = q_b, p_b <= q_b) is overwritten: its rows are rotated until
+ * mutually orthogonal; Z_b (p_b x p_b, initialised to identity by the caller or by
+ * gtn_jacobi_init) accumulates the rotations.  After convergence  W0 = Z^H * diag(s) * Vh with
+ * s_i = ||row_i(W)|| and Vh = rows of W normalised.  gtn_jacobi_finish sorts by descending s,
+ * writes s (double), U = (Z^H permuted) (p x p) and Vh (p x q) into caller buffers.
+ * The sweep loop runs on the host side of the ABI: gtn_jacobi_sweep launches the p-1 rounds of
+ * one sweep for the whole batch and returns; `offdiag` (device double[batch]) receives
+ * max |<w_i,w_j>| / (|w_i||w_j|) seen in that sweep.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int64_t w_off; /* element offset of W_b inside W */
+  int64_t z_off; /* element offset of Z_b inside Z */
+  int32_t p, q;
+} gtn_svd_problem;
+
+int gtn_jacobi_init(void* Z, int dtype, const gtn_svd_problem* probs_dev, int nprob, int max_p,
+                    void* stream);
+int gtn_jacobi_sweep(void* W, void* Z, int dtype, const gtn_svd_problem* probs_dev, int nprob,
+                     int max_p, int max_q, double tol, double* offdiag_dev, void* stream);
+/* s_out: double[sum p_b] at offsets s_off_b (descending); U_out (p x p row-major) at u_off;
+ * Vh_out: rows of W normalised and permuted, at w_off.  order_dev: int32 [sum p_b] receives the
+ * permutation; norm_scratch_dev: double [sum p_b] scratch. */
+typedef struct {
+  int64_t s_off, u_off;
+} gtn_svd_out;
+int gtn_jacobi_finish(const void* W, const void* Z, void* U_out, void* Vh_out, double* s_out,
+                      int dtype, const gtn_svd_problem* probs_dev, const gtn_svd_out* outs_dev,
+                      int32_t* order_dev, double* norm_scratch_dev, int nprob, int max_p,
+                      int max_q, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Small element-wise / reduction helpers.
+ * ------------------------------------------------------------------------------------------ */
+/* out[0] = sum |x_i|^2 (double). Replaces np.linalg.norm in dense.norm / block.norm
+ * (__init__.py:891-893, :432-437).  `out` must be zeroed by the caller (or pass zero_first=1). */
+int gtn_sumsq(const void* x, int64_t n, int dtype, double* out_dev, int zero_first, void* stream);
+
+/* y[r] = sum_c x[r*cols + c]  (row sums; the summed tail of a trace-type einsum such as
+ * 'IJIJ' -- the final reduction of oe.contract at __init__.py:2295 when nothing is left to
+ * multiply).  y has `rows` elements of the same dtype. */
+int gtn_rowsum(const void* x, void* y, int64_t rows, int64_t cols, int dtype, void* stream);
+
+/* x_i <- |x_i| > rcond ? x_i^p : 0   (power_ds, __init__.py:6059-6069; fixed power_block :6071). */
+int gtn_pow_rcond(void* x, int64_t n, int dtype, double p, double rcond, void* stream);
+
+/* x_i <- x_i * (s_re + i s_im)   (T.data/Tnorm at gauge2d.py:1748, :1864). */
+int gtn_scale(void* x, int64_t n, int dtype, double s_re, double s_im, void* stream);
+
+/* out[0] = max |x_i| over the entries whose Grassmann parity is odd, for a packed sector check
+ * (BlockSVD's evenness test __init__.py:3977-3983): x is rows x cols, entry (r,c) counts when
+ * ((r ^ c) & 1). */
+int gtn_odd_checker(const void* x, int64_t rows, int64_t cols, int dtype, double* out_dev,
+                    void* stream);
+
+/* Library / device introspection (no device work). */
+int gtn_version(void);
+const char* gtn_build_arch(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GTN_B200_H */

@@ -1,0 +1,172 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded
+inputs.  Tolerances: element-wise data produced by sign/permute work must be BIT-EXACT (0.0);
+contractions 1e-12 relative (different summation order); singular values / Tnorm / free energy
+1e-10 relative (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+import gtn_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+EINSUM_CASES = [
+    ('ijkl->jkli', [((4, 4, 4, 4), (1, 1, -1, -1))]),
+    ('ijkl->klij', [((4, 2, 8, 4), (1, -1, -1, 1))]),
+    ('ijkl->lijk', [((8, 4, 8, 4), (1, 1, -1, -1))]),
+    ('ijkl->jikl', [((8, 4, 8, 4), (1, 1, -1, -1))]),
+    ('lai->ila', [((8, 4, 8), (1, -1, 1))]),
+    ('ijkl,klmn->ijmn', [((4, 4, 4, 2), (1, 1, 1, 1)), ((4, 2, 4, 8), (-1, -1, 1, -1))]),
+    ('kwz,lxw->lxzk', [((4, 4, 8), (1, -1, 1)), ((4, 2, 4), (-1, 1, 1))]),
+    ('yxi,zyj->jzxi', [((4, 2, 8), (1, -1, 1)), ((4, 4, 2), (1, -1, -1))]),
+    ('lxzk,jzxi->ijkl', [((4, 2, 8, 4), (1, 1, -1, 1)), ((2, 8, 2, 4), (-1, 1, -1, 1))]),
+    ('ijij', [((4, 2, 4, 2), (1, 1, -1, -1))]),
+    ('ijij', [((4, 2, 4, 2), (-1, 1, 1, -1))]),
+    ('ijkl,klij', [((4, 2, 4, 8), (1, 1, -1, -1)), ((4, 8, 4, 2), (1, 1, -1, -1))]),
+    ('IJIK,iKiJ', [((4, 2, 4, 8), (1, 1, -1, -1)), ((2, 8, 2, 2), (1, 1, -1, -1))]),
+    ('IJKLij,ij->IJKL', [((4, 2, 4, 2, 3, 3), (1, 1, -1, -1, 0, 0)), ((3, 3), (0, 0))]),
+    ('i1 i3 a, j1 j3 b -> i1 i3 ab j1 j3', [((4, 2, 3), (1, -1, 0)), ((2, 4, 2), (1, -1, 0))]),
+    ('t s al m , lbm -> t s ab m', [((4, 2, 4, 2, 3), (1, -1, 1, 1, 0)), ((2, 4, 3), (-1, 1, 0))]),
+    ('abx,xc->abc', [((4, 4, 8), (1, 1, 1)), ((8, 8), (-1, 1))]),
+    ('ax,xbc->abc', [((8, 8), (-1, 1)), ((8, 4, 4), (-1, -1, -1))]),
+    ('ajk,jib->aibk', [((4, 2, 8), (-1, -1, -1)), ((2, 4, 4), (1, 1, 1))]),
+    ('iax,xbj->ijab', [((4, 2, 8), (1, 1, 1)), ((8, 4, 2), (-1, 1, -1))]),
+    ('ab,bc,cd->ad', [((4, 8), (1, 1)), ((8, 2), (-1, 1)), ((2, 4), (-1, -1))]),
+    ('abc,dbe,fce->adf', [((4, 8, 2), (1, 1, 1)), ((2, 8, 4), (1, -1, 1)), ((4, 2, 4), (-1, -1, -1))]),
+    ('IJIJmn,KLKLmn->mn', [((4, 2, 4, 2, 3, 2), (1, 1, -1, -1, 0, 0)), ((2, 2, 2, 2, 3, 2), (1, 1, -1, -1, 0, 0))]),
+    ('xa,xb->ab', [((4, 2), (1, 1)), ((4, 8), (-1, -1))]),
+]
+
+
+def _mk(gtn, shape, stats, rng, cplx=True, trim=False):
+    o = O.random_dense(shape, stats, dtype=complex if cplx else float, rng=rng, skip_trimming=not trim)
+    return o, gtn.dense(o.data, statistics=stats)
+
+
+def _relerr(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+@pytest.mark.parametrize("trim", [False, True])
+@pytest.mark.parametrize("case", range(len(EINSUM_CASES)))
+def test_einsum_vs_oracle(gtn, case, trim):
+    sub, ops = EINSUM_CASES[case]
+    rng = np.random.RandomState(1000 + case)
+    pairs = [_mk(gtn, s, st, rng, trim=trim) for s, st in ops]
+    ref = O.einsum(sub, *[p[0] for p in pairs])
+    got = gtn.einsum(sub, *[p[1] for p in pairs])
+    if isinstance(ref, O.Dense):
+        assert tuple(got.statistics) == tuple(ref.statistics)
+        assert got.shape == ref.shape
+        err = _relerr(got.data.cpu().numpy(), ref.data)
+        single = len(ops) == 1 and all(sub.split('->')[0].count(c) == 1 for c in sub.split('->')[0])
+        assert err == 0.0 if single else err < 1e-12, (sub, err)
+    else:
+        assert abs(got - ref) <= 1e-12 * max(abs(ref), 1.0), (sub, got, ref)
+
+
+def test_einsum_real_dtype(gtn):
+    rng = np.random.RandomState(5)
+    a, A = _mk(gtn, (4, 8, 4), (1, 1, -1), rng, cplx=False)
+    b, B = _mk(gtn, (4, 8, 2), (1, -1, -1), rng, cplx=False)
+    ref = O.einsum('abc,cbd->ad', a, b)
+    got = gtn.einsum('abc,cbd->ad', A, B)
+    assert got.data.dtype.is_floating_point
+    assert _relerr(got.data.cpu().numpy(), ref.data) < 1e-12
+
+
+def test_format_encoder_switches_bit_exact(gtn):
+    rng = np.random.RandomState(7)
+    a, A = _mk(gtn, (4, 4, 2, 8), (1, -1, -1, 1), rng)
+    for fn in ("switch_format", "switch_encoder", "switch_parity"):
+        ref = getattr(a, fn)()
+        got = getattr(A, fn)()
+        assert (got.format, got.encoder) == (ref.format, ref.encoder)
+        assert np.array_equal(got.data.cpu().numpy(), ref.data), fn
+    ref = a.switch_format().switch_encoder()
+    got = A.switch_format().switch_encoder()
+    assert np.array_equal(got.data.cpu().numpy(), ref.data)
+    r2 = O.einsum('ijkl->lkji', ref)
+    g2 = gtn.einsum('ijkl->lkji', got)
+    assert (g2.format, g2.encoder) == (r2.format, r2.encoder)
+    assert np.array_equal(g2.data.cpu().numpy(), r2.data)
+
+
+@pytest.mark.parametrize("cut", [None, 8, 6])
+def test_svd_vs_oracle(gtn, cut):
+    rng = np.random.RandomState(11)
+    a, A = _mk(gtn, (4, 4, 4, 4), (1, 1, -1, -1), rng, trim=True)
+    Ur, Sr, Vr = O.svd(a, 'ab|cd', cut)
+    U, S, V = A.svd('ab|cd', cut)
+    assert S.shape == Sr.shape and U.shape == Ur.shape and V.shape == Vr.shape
+    assert tuple(U.statistics) == tuple(Ur.statistics) and tuple(V.statistics) == tuple(Vr.statistics)
+    sr = np.sort(np.abs(np.diag(Sr.data)))[::-1]
+    sg = np.sort(np.abs(np.diag(S.data.cpu().numpy())))[::-1]
+    assert np.abs(sr - sg).max() <= 1e-10 * sr[0]
+    rec_r = O.einsum('abx,xy,ycd->abcd', Ur, Sr, Vr).data
+    rec_g = gtn.einsum('abx,xy,ycd->abcd', U, S, V).data.cpu().numpy()
+    assert _relerr(rec_g, rec_r) < 1e-10
+    if cut is None:
+        assert _relerr(rec_g, a.data) < 1e-12
+
+
+def test_svd_with_bosonic_legs(gtn):
+    rng = np.random.RandomState(12)
+    a, A = _mk(gtn, (4, 2, 3, 4, 2), (1, -1, 0, -1, 1), rng, trim=True)
+    Ur, Sr, Vr = O.svd(a, 'abc|de', None)
+    U, S, V = A.svd('abc|de', None)
+    rec_g = gtn.einsum('abcx,xy,yde->abcde', U, S, V).data.cpu().numpy()
+    assert _relerr(rec_g, a.data) < 1e-12
+    assert tuple(U.statistics) == tuple(Ur.statistics)
+
+
+def test_hconjugate_bit_exact(gtn):
+    rng = np.random.RandomState(13)
+    for shape, stats, s in [((4, 2, 3, 4, 2), (1, -1, 0, -1, 1), 'abc|de'), ((4, 4, 4, 4), (1, 1, -1, -1), 'ab|cd'),
+                            ((4, 8, 2), (-1, 1, 1), 'a|bc')]:
+        a, A = _mk(gtn, shape, stats, rng)
+        ref = O.hconjugate(a, s)
+        got = A.hconjugate(s)
+        assert tuple(got.statistics) == tuple(ref.statistics)
+        assert np.array_equal(got.data.cpu().numpy(), ref.data), s
+
+
+def test_eig_vs_oracle(gtn):
+    rng = np.random.RandomState(14)
+    a, A = _mk(gtn, (4, 4, 4, 4), (1, 1, -1, -1), rng, trim=True)
+    Mr = O.einsum('abcd,cdef->abef', O.hconjugate(a, 'ab|cd'), a)
+    Mg = gtn.einsum('abcd,cdef->abef', A.hconjugate('ab|cd'), A)
+    assert _relerr(Mg.data.cpu().numpy(), Mr.data) < 1e-12
+    Ur, Sr, Vr = O.eig(Mr, 'ab|cd', 8)
+    U, S, V = Mg.eig('ab|cd', 8)
+    sr = np.sort(np.abs(np.diag(Sr.data)))[::-1]
+    sg = np.sort(np.abs(np.diag(S.data.cpu().numpy())))[::-1]
+    assert np.abs(sr - sg).max() <= 1e-10 * sr[0]
+    rec_r = O.einsum('abx,xy,ycd->abcd', Ur, Sr, Vr).data
+    rec_g = gtn.einsum('abx,xy,ycd->abcd', U, S, V).data.cpu().numpy()
+    assert _relerr(rec_g, rec_r) < 1e-10
+
+
+@pytest.mark.parametrize("fmt", ["dense", "block"])
+@pytest.mark.parametrize("algo", ["trg", "atrg2dy", "atrg2dx"])
+def test_cg_step_vs_oracle(gtn, algo, fmt):
+    rng = np.random.RandomState(21)
+    a, A = _mk(gtn, (4, 4, 4, 4), (1, 1, -1, -1), rng, trim=True)
+    cut = 8 if fmt == "dense" else 6
+    rule = fmt
+    if fmt == "block":
+        A = A.toblock()
+    g = gtn.gauge2d
+    if algo == "trg":
+        Tr, nr, er = O.trg(a, cut, rule=rule, error_test=True)
+        Tg, ng, eg = g.trg(A, cut, error_test=True)
+    else:
+        fo = getattr(O, algo)
+        fg = getattr(g, algo)
+        Tr, nr, er = fo(a, a, cut, rule=rule, error_test=True)
+        Tg, ng, eg = fg(A, A, cut, error_test=True)
+    assert abs(ng - nr) <= 1e-10 * nr, (ng, nr)
+    assert abs(eg - er) <= 1e-9 * max(er, 1e-3)
+    Fr = O.logZ(Tr, 'anti-periodic', block_format=(fmt == "block"))
+    Fg = g.logZ(Tg, 'anti-periodic')
+    assert abs(Fg - Fr) <= 1e-10 * max(abs(Fr), 1.0)
