@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py -- TRG coarse-graining steps/sec of the 2D Z2 gauge theory at chi (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--chi 32] [--impl ours|reference]
+
+One "step" = one Levin-Nave TRG coarse-graining step (reference gauge2d_block.trg) of the
+chi-saturated site tensor of the Z2 (K=2), N_f=1, beta=m=q=a=1, mu=0 model in block format at
+chi (default 32 = example_block.py, BASELINE.json configs[1]).  Prints ONE JSON line.
+
+  value      steps/s with the tensor already resident in HBM (CUDA events per step, L2 flushed
+             between steps, max over ranks)
+  e2e        steps/s through the public API from HOST buffers: pinned host T -> H2D -> gtn.block ->
+             trg -> dense -> D2H of T' and Tnorm, every step
+  roofline   the kernel family with the largest share of the timed region (events around every C-ABI
+             launch) against the measured peak in MEASURED_PEAKS.json; extra.microbench holds the
+             sign+permute kernel (HBM) and the DMMA GEMM (FP64 tensor pipe, yard-stick = cuBLAS
+             ZGEMM timed in the same run) at large sizes
+  cpu_baseline  the numpy oracle port (oracle/gtn_oracle.py: trg_block) on the host cores, one
+             bounded sample (rank 0, N=1)
+
+--impl reference runs ONLY the CPU oracle port (the reference is Python and does not travel to
+the GPU box) with all host threads on the same config/metric.
+N > 1 (torchrun): independent replicas, one per GPU -- the TRG step at one chi does not shard in
+this round (DESIGN.md "Multi-GPU"); value = N * K / max-over-ranks time, scaling "weak".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+import numpy as np
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--chi", type=int, default=32)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--no-micro", action="store_true")
+    ap.add_argument("--micro-chi", type=int, default=64)
+    return ap.parse_args()
+
+
+def load_z2():
+    path = os.path.join(ROOT, "tests", "golden", "z2_initial_tensor.npz")
+    if os.path.exists(path):
+        z = np.load(path)
+        return z["data"], tuple(int(s) for s in z["statistics"]), "Z2 gauge initial tensor (reference fixture)"
+    # fixture not generated yet: a random Grassmann-even tensor of the same shape
+    import gtn_oracle as O
+    rng = np.random.RandomState(0)
+    T = O.random_dense((8, 8, 8, 8, 2, 2), (1, 1, -1, -1, 0, 0), dtype=complex, rng=rng)
+    return T.data, T.statistics, "random Grassmann-even tensor (Z2 fixture missing)"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.stop_flag = False
+        self.max_mhz = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                self.samples.append(float(f[0]))
+                self.max_mhz = float(f[1])
+                for n, v in zip(names, f[2:]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def result(self):
+        self.stop_flag = True
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+def best_blas_threads():
+    """OpenBLAS/LAPACK gesdd can be pathologically slow with all threads on a busy or CPU-limited
+    host (seen: 17 s vs 0.24 s for one 512x512 complex SVD).  Give the CPU baseline its best
+    setting: time one SVD with 1 thread and with all threads and keep the faster."""
+    try:
+        from threadpoolctl import threadpool_limits
+    except Exception:
+        return None, os.cpu_count()
+    a = np.random.RandomState(0).rand(256, 256) + 1j
+    best = None
+    for n in (1, os.cpu_count()):
+        with threadpool_limits(limits=n):
+            np.linalg.svd(a)
+            t0 = time.perf_counter()
+            np.linalg.svd(a)
+            dt = time.perf_counter() - t0
+        if best is None or dt < best[1]:
+            best = (n, dt)
+    return threadpool_limits, best[0]
+
+
+def cpu_reference_run(args, data, stats, label):
+    """the oracle port of gauge2d_block.trg on the host cores"""
+    limiter, nthreads = best_blas_threads()
+    if limiter is not None:
+        with limiter(limits=nthreads):
+            return _cpu_reference_run(args, data, stats, label) + (nthreads,)
+    return _cpu_reference_run(args, data, stats, label) + (nthreads,)
+
+
+def _cpu_reference_run(args, data, stats, label):
+    import gtn_oracle as O
+    T = O.zcap(O.Dense(data, stats))
+    B = O.Blocks.from_dense(T)
+    for _ in range(2):                      # saturate chi (untimed)
+        B, _ = O.trg_block(B, args.chi)
+    for _ in range(args.warmup):
+        O.trg_block(B, args.chi)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        Bn, _ = O.trg_block(B, args.chi)
+    dt = time.perf_counter() - t0
+    return args.steps / dt, dt / args.steps * 1e3, B.effective_shape
+
+
+def config_dict(args, label, shape):
+    return {"workload": "TRG step (gauge2d_block.trg), 2D Z2 gauge theory K=2 Nf=1 beta=m=q=a=1 mu=0, block format, "
+                        "chi=%d, site tensor %s complex128" % (args.chi, "x".join(str(int(s)) for s in shape)),
+            "input": label, "chi": args.chi, "parallelism": "replicas x%d" % args.gpus,
+            "l2": "flushed between timed steps (256 MiB write)"}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    data, stats, label = load_z2()
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cores = os.cpu_count()
+        v, ms, shape, nthr = cpu_reference_run(args, data, stats, label)
+        cores = "%d BLAS threads (best of 1/all) on %d logical cores" % (nthr, cores)
+        line = {"impl": "reference", "metric": "TRG coarse-grain steps/sec at chi", "value": v, "unit": "steps/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "complex128",
+                "data": "synthetic", "config": config_dict(args, label, shape),
+                "cpu_baseline": {"value": v, "unit": "steps/s", "cores": cores, "kind": "port",
+                                 "sample": "%d full TRG steps at chi=%d (oracle/gtn_oracle.py trg_block; numpy/LAPACK, "
+                                           "all host threads)" % (args.steps, args.chi)},
+                "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl")
+    import grassmanntn_b200 as gtn
+    from grassmanntn_b200 import _engine as E
+    g = gtn.gauge2d
+    dev = torch.device("cuda", local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    T0 = g.zcap(gtn.dense(data, statistics=stats)).toblock()
+    T = T0
+    for _ in range(2):                       # saturate chi (untimed prologue)
+        T, _ = g.trg(T, args.chi)
+    shape = T.effective_shape
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    # ---- device-resident steps
+    X = T
+    for _ in range(args.warmup):
+        X, _ = g.trg(X, args.chi)
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    n0 = gtn.launch_count()
+    E.PROF.start()
+    evs = []
+    X = T
+    for _ in range(args.steps):
+        flush.fill_(1)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        X, Tn = g.trg(X, args.chi)
+        e.record()
+        evs.append((s, e))
+    barrier()
+    prof = E.PROF.stop()
+    launches = gtn.launch_count() - n0
+    t_dev = sum(s.elapsed_time(e) for s, e in evs) * 1e-3
+    clocks = sampler.result()
+
+    # ---- end to end from host buffers
+    host_in = torch.from_numpy(np.ascontiguousarray(T.todense().data.cpu().numpy())).pin_memory()
+    tstats = T.statistics
+
+    def e2e_step():
+        d = host_in.to(dev, non_blocking=True)
+        Xb = gtn.dense(d, statistics=tstats).toblock()
+        Y, Tn = g.trg(Xb, args.chi)
+        out = Y.todense().data
+        host_out = out.cpu()
+        return host_out, Tn
+    for _ in range(max(1, args.warmup // 2)):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ho, _ = e2e_step()
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    h2d = host_in.numel() * host_in.element_size()
+    d2h = ho.numel() * ho.element_size() + 8
+
+    tt = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_dev, t_e2e = tt.tolist()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    hbm_peak, peak_src = peaks()
+    tot_ms = sum(v["ms"] for v in prof.values())
+    dom = max(prof, key=lambda k: prof[k]["ms"])
+    d = prof[dom]
+    per_launch_ms = d["ms"] / max(d["launches"], 1)
+    achieved = (d["bytes"] / max(d["launches"], 1)) / (per_launch_ms * 1e-3) / 1e9 if d["bytes"] else 0.0
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "share_of_step": d["ms"] / tot_ms if tot_ms else None,
+                "avg_launch_us": per_launch_ms * 1e3, "launches_per_step": d["launches"] / args.steps}
+    shares = {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
+                  "share": v["ms"] / tot_ms if tot_ms else None} for k, v in prof.items()}
+    extra = {"kernel_shares": shares, "jacobi_sweeps_last": E.batched_svd.last_sweeps}
+    if not args.no_micro:
+        extra["microbench"] = microbench(gtn, E, torch, dev, args, hbm_peak)
+
+    cpu = None
+    if world == 1:
+        a2 = argparse.Namespace(**vars(args))
+        a2.steps, a2.warmup = 3, 1
+        v, ms, _, nthr = cpu_reference_run(a2, data, stats, label)
+        cpu = {"value": v, "unit": "steps/s",
+               "cores": "%d BLAS threads (best of 1/all) on %d logical cores" % (nthr, os.cpu_count()), "kind": "port",
+               "sample": "3 full TRG steps at chi=%d with the numpy oracle port (oracle/gtn_oracle.py trg_block)" % args.chi}
+
+    line = {"metric": "TRG coarse-grain steps/sec at chi", "value": world * args.steps / t_dev, "unit": "steps/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_dev / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "complex128",
+            "data": "synthetic", "config": config_dict(args, label, shape), "clocks": clocks,
+            "e2e": {"value": world * args.steps / t_e2e, "unit": "steps/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "extra": extra}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def microbench(gtn, E, torch, dev, args, hbm_peak):
+    """large-size numbers for the two roofline kernels (not part of `value`)."""
+    out = {}
+    import gtn_oracle as O  # only for the seeded input generator
+    # ---- sign + permute: dense 'ijkl->jkli' at D = 64 and 128 (complex128: 256 MiB / 4 GiB)
+    for D in (64, 128):
+        n = D ** 4
+        x = torch.rand(n, dtype=torch.float64, device=dev).to(torch.complex128).view(D, D, D, D)
+        A = gtn.dense(x, statistics=(1, 1, -1, -1))
+        bt = A._get_bt()
+        from grassmanntn_b200 import _ops
+        for _ in range(3):
+            r = _ops.einsum_bt('ijkl->jkli', [bt])
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10 if D == 64 else 3
+        s.record()
+        for _ in range(reps):
+            r = _ops.einsum_bt('ijkl->jkli', [bt])
+        e.record()
+        torch.cuda.synchronize()
+        ms = s.elapsed_time(e) / reps
+        gbs = 2 * n * 16 / (ms * 1e-3) / 1e9
+        out["sign_permute_D%d" % D] = {"ms": ms, "GBps": gbs, "frac_hbm": gbs / hbm_peak,
+                                       "bytes": 2 * n * 16, "note": "all 16 parity blocks, full (non-even) tensor"}
+        del x, A, bt, r
+    # ---- DMMA grouped GEMM vs cuBLAS ZGEMM yard-stick
+    for N in (2048, 4096):
+        a = torch.randn(N, N, dtype=torch.complex128, device=dev)
+        b = torch.randn(N, N, dtype=torch.complex128, device=dev)
+        for _ in range(2):
+            c = E.gemm(a.view(-1), b.view(-1), N, N, N)
+            c2 = a @ b
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(3):
+            c = E.gemm(a.view(-1), b.view(-1), N, N, N)
+        e.record()
+        s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s2.record()
+        for _ in range(3):
+            c2 = a @ b
+        e2.record()
+        torch.cuda.synchronize()
+        fl = 8.0 * N ** 3
+        ours, cub = fl / (s.elapsed_time(e) / 3 * 1e-3) / 1e12, fl / (s2.elapsed_time(e2) / 3 * 1e-3) / 1e12
+        err = float((c.view(N, N) - c2).abs().max() / c2.abs().max())
+        out["zgemm_%d" % N] = {"ours_TFLOPs": ours, "cublas_zgemm_TFLOPs": cub, "frac_of_cublas": ours / cub,
+                               "max_rel_diff_vs_cublas": err}
+    return out
+
+
+if __name__ == "__main__":
+    main()

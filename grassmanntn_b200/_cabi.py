@@ -56,8 +56,8 @@ def _load():
         "gtn_sign_permute": (i32, [vp, vp, i32, vp, vp, i32, i64, dbl, dbl, vp]),
         "gtn_gemm_plan_host": (i64, [C.POINTER(GemmGroup), i32, i32]),
         "gtn_grouped_gemm": (i32, [vp, vp, vp, i32, vp, i32, i64, vp]),
-        "gtn_jacobi_init": (i32, [vp, i32, vp, i32, i32, vp]),
-        "gtn_jacobi_sweep": (i32, [vp, vp, i32, vp, i32, i32, i32, dbl, vp, vp]),
+        "gtn_jacobi_init": (i32, [vp, vp, i32, vp, i32, i32, vp, vp, vp, vp]),
+        "gtn_jacobi_sweep": (i32, [vp, vp, i32, vp, i32, i32, i32, dbl, vp, vp, vp, vp, vp]),
         "gtn_jacobi_finish": (i32, [vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, i32, i32, i32, vp]),
         "gtn_sumsq": (i32, [vp, i64, i32, vp, i32, vp]),
         "gtn_rowsum": (i32, [vp, vp, i64, i64, i32, vp]),

@@ -33,6 +33,54 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+class _Profiler:
+    """Optional per-kernel-family timing with CUDA events on the launching stream (bench.py)."""
+
+    def __init__(self):
+        self.enabled = False
+        self.records = []
+
+    def start(self):
+        self.enabled = True
+        self.records = []
+
+    def stop(self):
+        self.enabled = False
+        torch.cuda.synchronize()
+        out = {}
+        for name, s, e, launches, nbytes, flops in self.records:
+            d = out.setdefault(name, dict(ms=0.0, calls=0, launches=0, bytes=0, flops=0))
+            d["ms"] += s.elapsed_time(e)
+            d["calls"] += 1
+            d["launches"] += launches
+            d["bytes"] += nbytes
+            d["flops"] += flops
+        self.records = []
+        return out
+
+
+PROF = _Profiler()
+
+
+class prof_region:
+    def __init__(self, name, launches=1, nbytes=0, flops=0):
+        self.a = (name, launches, nbytes, flops)
+
+    def __enter__(self):
+        if PROF.enabled:
+            self.s = torch.cuda.Event(enable_timing=True)
+            self.s.record()
+        return self
+
+    def __exit__(self, *exc):
+        count(self.a[1])
+        if PROF.enabled:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            PROF.records.append((self.a[0], self.s, e, self.a[1], self.a[2], self.a[3]))
+        return False
+
+
 def dtype_code(dt):
     if dt == torch.complex128:
         return _cabi.GTN_C128
@@ -190,8 +238,11 @@ class PermutePlan:
         # jobs: list of (fields, tabs)
         self.njobs = len(jobs)
         self.max_tiles = 0
+        self.elems = 0
         if self.njobs == 0:
             return
+        for f, tabs in jobs:
+            self.elems += int(np.prod([len(t) for t in tabs], dtype=np.int64))
         arr = (PermuteJob * self.njobs)()
         chunks, start = [], 0
         for k, (f, tabs) in enumerate(jobs):
@@ -217,9 +268,9 @@ class PermutePlan:
         code = dtype_code(src.dtype)
         s = complex(scale)
         # grid.y is limited to 65535 jobs; far above any block count we generate
-        check(lib.gtn_sign_permute(_ptr(src), _ptr(dst), code, _ptr(self.jobs_dev), _ptr(self.entries_dev),
-                                   self.njobs, self.max_tiles, s.real, s.imag, _stream()), "gtn_sign_permute")
-        count()
+        with prof_region("sign_permute", 1, 2 * self.elems * src.element_size()):
+            check(lib.gtn_sign_permute(_ptr(src), _ptr(dst), code, _ptr(self.jobs_dev), _ptr(self.entries_dev),
+                                       self.njobs, self.max_tiles, s.real, s.imag, _stream()), "gtn_sign_permute")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -540,8 +591,15 @@ class GemmPlan:
     def __init__(self, groups, dtype):
         self.n = len(groups)
         self.tiles = 0
+        self.flops = 0
+        self.bytes = 0
         if self.n == 0:
             return
+        cplx = dtype == torch.complex128
+        for g in groups:
+            b = g.get("batch", 1)
+            self.flops += (8 if cplx else 2) * b * g["m"] * g["n"] * g["k"]
+            self.bytes += (16 if cplx else 8) * b * (g["m"] * g["k"] + g["k"] * g["n"] + g["m"] * g["n"])
         arr = (GemmGroup * self.n)()
         for k, g in enumerate(groups):
             a = arr[k]
@@ -558,9 +616,9 @@ class GemmPlan:
     def run(self, A, B, Cm):
         if self.n == 0 or self.tiles == 0:
             return
-        check(lib.gtn_grouped_gemm(_ptr(A), _ptr(B), _ptr(Cm), dtype_code(A.dtype), _ptr(self.dev), self.n,
-                                   self.tiles, _stream()), "gtn_grouped_gemm")
-        count()
+        with prof_region("grouped_gemm", 1, self.bytes, self.flops):
+            check(lib.gtn_grouped_gemm(_ptr(A), _ptr(B), _ptr(Cm), dtype_code(A.dtype), _ptr(self.dev), self.n,
+                                       self.tiles, _stream()), "gtn_grouped_gemm")
 
 
 def gemm(A, B, m, n, k, lda=None, ldb=None, ldc=None, out=None):
@@ -576,7 +634,7 @@ def gemm(A, B, m, n, k, lda=None, ldb=None, ldc=None, out=None):
 # ------------------------------------------------------------------------------------------------
 #  batched Jacobi SVD
 # ------------------------------------------------------------------------------------------------
-JACOBI_TOL = 1e-15
+JACOBI_TOL = 4e-15
 JACOBI_MAX_SWEEPS = 60
 
 
@@ -617,16 +675,22 @@ def batched_svd(mats):
     pdev = _to_dev_bytes(bytes(parr))
     odev = _to_dev_bytes(bytes(oarr))
     st = _stream()
-    check(lib.gtn_jacobi_init(_ptr(Z), code, _ptr(pdev), nprob, maxp, st), "gtn_jacobi_init")
+    rn2 = torch.empty(max(soff, 1), dtype=torch.float64, device=dev)
+    fro2 = torch.empty(nprob, dtype=torch.float64, device=dev)
+    rn_off = torch.tensor([pr[4] for pr in probs], dtype=torch.int64).to(dev, non_blocking=True)
+    check(lib.gtn_jacobi_init(_ptr(W), _ptr(Z), code, _ptr(pdev), nprob, maxp, _ptr(rn2), _ptr(fro2), _ptr(rn_off),
+                              st), "gtn_jacobi_init")
     count()
     offd = torch.zeros(nprob, dtype=torch.float64, device=dev)
     sweeps = 0
     if maxp >= 2:
         while True:
-            check(lib.gtn_jacobi_sweep(_ptr(W), _ptr(Z), code, _ptr(pdev), nprob, maxp, maxq, JACOBI_TOL,
-                                       _ptr(offd), st), "gtn_jacobi_sweep")
             P = (maxp + 1) & ~1
-            count(P - 1)
+            esz = W.element_size()
+            rb = sum(2 * esz * (pr[2] * pr[3] + pr[2] * pr[2]) for pr in probs)   # every row of W and Z read+written
+            with prof_region("jacobi_round", P - 1, rb * (P - 1)):
+                check(lib.gtn_jacobi_sweep(_ptr(W), _ptr(Z), code, _ptr(pdev), nprob, maxp, maxq, JACOBI_TOL,
+                                           _ptr(offd), _ptr(rn2), _ptr(fro2), _ptr(rn_off), st), "gtn_jacobi_sweep")
             sweeps += 1
             if float(offd.max().item()) <= JACOBI_TOL:
                 break

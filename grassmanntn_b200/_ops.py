@@ -399,7 +399,7 @@ def _block_jobs(bt, live, alpha, beta, Q, place):
     return jobs
 
 
-def decompose_bt(bt, nl, cutoff, kind, rule):
+def _decompose_prepare(bt, nl, kind):
     """U, S, V of the (first nl legs | remaining legs) matricisation.
     rule 'dense': reference BlockSVD/BlockEig rank rule (int(cutoff/2) per sector, pad to a power of
     two, __init__.py:3998-4015); rule 'block': decompose_block's (ceil/floor, pad to max, :5076-5103)."""
@@ -467,7 +467,15 @@ def decompose_bt(bt, nl, cutoff, kind, rule):
             dn, mn = [math.sqrt(v) for v in nrm2.cpu().tolist()]
             if mn >= NUMER_CUTOFF and dn / mn > NUMER_CUTOFF:
                 _err("Error[SortedEig]: The input matrix is not Hermitian!")
-    usv = batched_svd(mats)
+    return dict(locals())
+
+
+def _decompose_finish(ctx, usv, cutoff, kind, rule):
+    bt, nl, this_fmt = ctx["bt"], ctx["nl"], ctx["this_fmt"]
+    Rl, Cl, fR, fC = ctx["Rl"], ctx["Cl"], ctx["fR"], ctx["fC"]
+    layR, layC, sectors, rows, cols = ctx["layR"], ctx["layC"], ctx["sectors"], ctx["rows"], ctx["cols"]
+    alpha, beta, Q, fpos_R, fpos_C = ctx["alpha"], ctx["beta"], ctx["Q"], ctx["fpos_R"], ctx["fpos_C"]
+    dev = ctx["dev"]
 
     # ---- rank rule
     if len(sectors) == 2:
@@ -612,6 +620,26 @@ def decompose_bt(bt, nl, cutoff, kind, rule):
     if this_fmt == "matrix":
         outs = [bt_switch_format(x) for x in outs]
     return outs[0], outs[1], outs[2], tuple(keep)
+
+
+
+
+def decompose_many(items, cutoff, kind, rule):
+    """items: list of (bt, nl).  All sector matrices of all items go through ONE batched Jacobi
+    run (the two SVDs of a TRG step share their sweeps)."""
+    ctxs = [_decompose_prepare(bt, nl, kind) for bt, nl in items]
+    mats = [m for c in ctxs for m in c["mats"]]
+    usv = batched_svd(mats)
+    outs, k = [], 0
+    for c in ctxs:
+        n = len(c["mats"])
+        outs.append(_decompose_finish(c, usv[k:k + n], cutoff, kind, rule))
+        k += n
+    return outs
+
+
+def decompose_bt(bt, nl, cutoff, kind, rule):
+    return decompose_many([(bt, nl)], cutoff, kind, rule)[0]
 
 
 def hconjugate_bt(bt, nl):

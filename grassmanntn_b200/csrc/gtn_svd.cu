@@ -75,7 +75,8 @@ template <bool CPLX>
 __global__ void __launch_bounds__(JT)
     jacobi_round_kernel(typename Elem<CPLX>::T* __restrict__ Wb, typename Elem<CPLX>::T* __restrict__ Zb,
                         const gtn_svd_problem* __restrict__ probs, int round, double tol,
-                        double* __restrict__ offdiag) {
+                        double* __restrict__ offdiag, double* __restrict__ rn2,
+                        const double* __restrict__ fro2, const int64_t* __restrict__ rn_off) {
   using T = typename Elem<CPLX>::T;
   const gtn_svd_problem pr = probs[blockIdx.y];
   const int p = pr.p, q = pr.q;
@@ -88,6 +89,18 @@ __global__ void __launch_bounds__(JT)
   else { i = (round + k) % (P - 1); j = (round - k + (P - 1)) % (P - 1); }
   if (i >= p || j >= p) return;
   if (i > j) { int tmp = i; i = j; j = tmp; }
+
+  // dead-row test on the stored squared row norms.  A row whose norm has fallen below
+  // 2e-15 * (largest row norm seen so far <= s_0) can only carry singular values that the rank rule
+  // s_i/s_0 > 1e-14 (reference __init__.py:3939-3941) discards anyway, and its overlap with a live
+  // row perturbs that row by O(1e-15) relative -- so such pairs are never read again.  This is what
+  // makes rank-deficient sectors (the normal case for the gauge tensors) cheap.
+  double* rn = rn2 + rn_off[blockIdx.y];
+  {
+    const double as = rn[i], bs = rn[j];
+    const double dead = 4e-30 * fro2[blockIdx.y];      // fro2[] holds max_i |row_i|^2 (monotone)
+    if (fmin(as, bs) <= dead) return;
+  }
 
   T* x = Wb + pr.w_off + int64_t(i) * q;
   T* y = Wb + pr.w_off + int64_t(j) * q;
@@ -141,6 +154,7 @@ __global__ void __launch_bounds__(JT)
     const double cabs = sqrt(CR * CR + CI * CI);
     const double denom = sqrt(A) * sqrt(B);
     double cs = 1.0, sn = 0.0, phr = 1.0, phi = 0.0, act = 0.0;
+    rn[i] = A; rn[j] = B;
     if (denom > 0.0 && cabs > 0.0) {
       const double off = cabs / denom;
       if (off > tol) {
@@ -151,6 +165,8 @@ __global__ void __launch_bounds__(JT)
         sn = cs * tt;
         phr = CR / cabs; phi = CI / cabs;
         act = 1.0;
+        rn[i] = fmax(A - tt * cabs, 0.0); rn[j] = B + tt * cabs;
+        atomic_max_pos(const_cast<double*>(fro2) + blockIdx.y, fmax(rn[i], rn[j]));
       }
     }
     rotp[0] = cs; rotp[1] = sn; rotp[2] = phr; rotp[3] = phi; rotp[4] = act;
@@ -187,8 +203,10 @@ __global__ void __launch_bounds__(JT)
 }
 
 template <bool CPLX>
-__global__ void jacobi_init_kernel(typename Elem<CPLX>::T* __restrict__ Zb,
-                                   const gtn_svd_problem* __restrict__ probs) {
+__global__ void __launch_bounds__(128)
+    jacobi_init_kernel(const typename Elem<CPLX>::T* __restrict__ Wb, typename Elem<CPLX>::T* __restrict__ Zb,
+                       const gtn_svd_problem* __restrict__ probs, double* __restrict__ rn2,
+                       double* __restrict__ fro2, const int64_t* __restrict__ rn_off) {
   using T = typename Elem<CPLX>::T;
   const gtn_svd_problem pr = probs[blockIdx.y];
   const int r = blockIdx.x;
@@ -197,6 +215,21 @@ __global__ void jacobi_init_kernel(typename Elem<CPLX>::T* __restrict__ Zb,
   for (int e = threadIdx.x; e < pr.p; e += blockDim.x) {
     if constexpr (CPLX) { T v; v.re = (e == r) ? 1.0 : 0.0; v.im = 0.0; Elem<CPLX>::st(z + e, v); }
     else Elem<CPLX>::st(z + e, (e == r) ? 1.0 : 0.0);
+  }
+  const T* x = Wb + pr.w_off + int64_t(r) * pr.q;
+  double a = 0;
+  for (int e = threadIdx.x; e < pr.q; e += blockDim.x) {
+    const T v = Elem<CPLX>::ld(x + e);
+    if constexpr (CPLX) a += v.re * v.re + v.im * v.im; else a += v * v;
+  }
+  __shared__ double red[4];
+  a = warp_sum(a);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const double A = red[0] + red[1] + red[2] + red[3];
+    rn2[rn_off[blockIdx.y] + r] = A;
+    atomic_max_pos(fro2 + blockIdx.y, A);
   }
 }
 
@@ -281,19 +314,24 @@ __global__ void __launch_bounds__(JT)
 
 }  // namespace
 
-extern "C" int gtn_jacobi_init(void* Z, int dtype, const gtn_svd_problem* probs_dev, int nprob,
-                               int max_p, void* stream) {
+extern "C" int gtn_jacobi_init(const void* W, void* Z, int dtype, const gtn_svd_problem* probs_dev,
+                               int nprob, int max_p, double* rownorm2_dev, double* fro2_dev,
+                               const int64_t* rn_off_dev, void* stream) {
   if (nprob <= 0 || max_p <= 0) return GTN_OK;
   dim3 grid(max_p, nprob), block(128);
   cudaStream_t s = (cudaStream_t)stream;
-  if (dtype == GTN_C128) jacobi_init_kernel<true><<<grid, block, 0, s>>>((c128*)Z, probs_dev);
-  else if (dtype == GTN_F64) jacobi_init_kernel<false><<<grid, block, 0, s>>>((double*)Z, probs_dev);
+  cudaMemsetAsync(fro2_dev, 0, sizeof(double) * nprob, s);
+  if (dtype == GTN_C128)
+    jacobi_init_kernel<true><<<grid, block, 0, s>>>((const c128*)W, (c128*)Z, probs_dev, rownorm2_dev, fro2_dev, rn_off_dev);
+  else if (dtype == GTN_F64)
+    jacobi_init_kernel<false><<<grid, block, 0, s>>>((const double*)W, (double*)Z, probs_dev, rownorm2_dev, fro2_dev, rn_off_dev);
   else return GTN_ERR_BAD_ARG;
   return (int)cudaGetLastError();
 }
 
 extern "C" int gtn_jacobi_sweep(void* W, void* Z, int dtype, const gtn_svd_problem* probs_dev,
                                 int nprob, int max_p, int max_q, double tol, double* offdiag_dev,
+                                double* rownorm2_dev, const double* fro2_dev, const int64_t* rn_off_dev,
                                 void* stream) {
   (void)max_q;
   if (nprob <= 0 || max_p < 2) return GTN_OK;
@@ -303,9 +341,11 @@ extern "C" int gtn_jacobi_sweep(void* W, void* Z, int dtype, const gtn_svd_probl
   cudaMemsetAsync(offdiag_dev, 0, sizeof(double) * nprob, s);
   for (int r = 0; r < P - 1; ++r) {
     if (dtype == GTN_C128)
-      jacobi_round_kernel<true><<<grid, block, 0, s>>>((c128*)W, (c128*)Z, probs_dev, r, tol, offdiag_dev);
+      jacobi_round_kernel<true><<<grid, block, 0, s>>>((c128*)W, (c128*)Z, probs_dev, r, tol, offdiag_dev,
+                                                       rownorm2_dev, fro2_dev, rn_off_dev);
     else if (dtype == GTN_F64)
-      jacobi_round_kernel<false><<<grid, block, 0, s>>>((double*)W, (double*)Z, probs_dev, r, tol, offdiag_dev);
+      jacobi_round_kernel<false><<<grid, block, 0, s>>>((double*)W, (double*)Z, probs_dev, r, tol, offdiag_dev,
+                                                        rownorm2_dev, fro2_dev, rn_off_dev);
     else
       return GTN_ERR_BAD_ARG;
   }

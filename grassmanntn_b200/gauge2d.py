@@ -68,8 +68,7 @@ def trg(T, dcut=64, iternum=None, error_test=False):
         gtn.error("Error[trg]: The statistics must be (1,1,-1,-1)!")
     T1 = gtn.einsum("ijkl->jkli", T)
     T2 = gtn.einsum("ijkl->klij", T)
-    U1, S1, V1 = T1.svd("ab|cd", dcut)
-    U2, S2, V2 = T2.svd("ab|cd", dcut)
+    (U1, S1, V1), (U2, S2, V2) = gtn.svd_many([T1, T2], "ab|cd", dcut)
     sq = gtn.sqrt(S1)
     U1 = gtn.einsum("abx,xc->abc", U1, sq)
     V1 = gtn.einsum("ax,xbc->abc", sq, V1)
@@ -94,9 +93,12 @@ def atrg2dy(T1, T2, dcut=64, intermediate_dcut=None, iternum=None, error_test=Fa
         intermediate_dcut = dcut
     T1o, T2o = T1, T2
     T1 = gtn.einsum("ijkl->lijk", T1)
-    T2 = gtn.einsum("ijkl->lijk", T2)
-    U1, S1, V1 = T1.svd("li|jk", intermediate_dcut)
-    U2, S2, V2 = T2.svd("li|jk", intermediate_dcut)
+    T2 = T1 if T1o is T2o else gtn.einsum("ijkl->lijk", T2)
+    if T1o is T2o:
+        U1, S1, V1 = T1.svd("li|jk", intermediate_dcut)
+        U2, S2, V2 = U1, S1, V1
+    else:
+        (U1, S1, V1), (U2, S2, V2) = gtn.svd_many([T1, T2], "li|jk", intermediate_dcut)
     A = V1
     B = gtn.einsum("lia,ab->lib", U1, S1)
     C = gtn.einsum("ab,bjk->ajk", S2, V2)

@@ -139,10 +139,17 @@ typedef struct {
   int32_t p, q;
 } gtn_svd_problem;
 
-int gtn_jacobi_init(void* Z, int dtype, const gtn_svd_problem* probs_dev, int nprob, int max_p,
+/* rownorm2_dev: double[sum p_b] (problem b at rn_off_dev[b]) receives the squared row norms,
+ * fro2_dev: double[nprob] the largest squared row norm seen so far (a lower bound of s_0^2); both
+ * are maintained by the sweeps and let a CTA skip a row pair without reading it when one of the
+ * rows has decayed below 2e-15 * s_0 (rank-deficient sectors: such rows are discarded by the
+ * reference's rank rule s_i/s_0 > 1e-14 anyway). */
+int gtn_jacobi_init(const void* W, void* Z, int dtype, const gtn_svd_problem* probs_dev, int nprob,
+                    int max_p, double* rownorm2_dev, double* fro2_dev, const int64_t* rn_off_dev,
                     void* stream);
 int gtn_jacobi_sweep(void* W, void* Z, int dtype, const gtn_svd_problem* probs_dev, int nprob,
-                     int max_p, int max_q, double tol, double* offdiag_dev, void* stream);
+                     int max_p, int max_q, double tol, double* offdiag_dev, double* rownorm2_dev,
+                     const double* fro2_dev, const int64_t* rn_off_dev, void* stream);
 /* s_out: double[sum p_b] at offsets s_off_b (descending); U_out (p x p row-major) at u_off;
  * Vh_out: rows of W normalised and permuted, at w_off.  order_dev: int32 [sum p_b] receives the
  * permutation; norm_scratch_dev: double [sum p_b] scratch. */
