@@ -269,7 +269,9 @@ def main():
                 "avg_launch_us": per_launch_ms * 1e3, "launches_per_step": d["launches"] / args.steps}
     shares = {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
                   "share": v["ms"] / tot_ms if tot_ms else None} for k, v in prof.items()}
-    extra = {"kernel_shares": shares, "jacobi_sweeps_last": E.batched_svd.last_sweeps}
+    from grassmanntn_b200 import _ops
+    extra = {"kernel_shares": shares, "jacobi_sweeps_last": E.batched_svd.last_sweeps,
+             "svd_paths": dict(_ops.SVD_PATH_STATS), "trunc_refinements_last": E.truncated_svd_batch.last_iters}
     if not args.no_micro:
         extra["microbench"] = microbench(gtn, E, torch, dev, args, hbm_peak)
 

@@ -54,13 +54,16 @@ def _load():
     vp, i32, i64, dbl = C.c_void_p, C.c_int, C.c_int64, C.c_double
     sigs = {
         "gtn_sign_permute": (i32, [vp, vp, i32, vp, vp, i32, i64, dbl, dbl, vp]),
-        "gtn_gemm_plan_host": (i64, [C.POINTER(GemmGroup), i32, i32]),
-        "gtn_grouped_gemm": (i32, [vp, vp, vp, i32, vp, i32, i64, vp]),
+        "gtn_gemm_plan_host": (i64, [C.POINTER(GemmGroup), i32, i32, i32]),
+        "gtn_grouped_gemm": (i32, [vp, vp, vp, i32, vp, i32, i64, i32, vp]),
         "gtn_jacobi_init": (i32, [vp, vp, i32, vp, i32, i32, vp, vp, vp, vp]),
         "gtn_jacobi_sweep": (i32, [vp, vp, i32, vp, i32, i32, i32, dbl, vp, vp, vp, vp, vp]),
         "gtn_jacobi_finish": (i32, [vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, i32, i32, i32, vp]),
+        "gtn_small_eigh_whiten": (i32, [vp, vp, i32, vp, vp, vp, i32, i32, dbl, vp, vp, vp, vp]),
+        "gtn_small_chol_whiten": (i32, [vp, vp, i32, vp, vp, vp, i32, i32, dbl, vp, vp]),
         "gtn_sumsq": (i32, [vp, i64, i32, vp, i32, vp]),
         "gtn_rowsum": (i32, [vp, vp, i64, i64, i32, vp]),
+        "gtn_row_sumsq": (i32, [vp, vp, i64, i64, i32, vp]),
         "gtn_pow_rcond": (i32, [vp, i64, i32, dbl, dbl, vp]),
         "gtn_scale": (i32, [vp, i64, i32, dbl, dbl, vp]),
         "gtn_odd_checker": (i32, [vp, i64, i64, i32, vp, vp]),

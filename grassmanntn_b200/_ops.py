@@ -16,12 +16,14 @@ import numpy as np
 import torch
 
 from . import _planner as P
-from ._engine import (BT, FERMI, GemmPlan, GroupLayout, PermutePlan, _cached, _ptr, _row_strides, _stream,
-                      batched_svd, bt_force_standard, bt_switch_format, build_job, dtype_code, gemm, lin_leg,
+from ._engine import (BT, FERMI, GemmPlan, GroupLayout, group_layout, PermutePlan, _cached, _ptr, _row_strides, _stream,
+                      batched_svd, truncated_svd_batch, bt_force_standard, bt_switch_format, build_job, dtype_code, gemm, lin_leg,
                       require_cuda, sigma_bits)
 from ._cabi import check, count, lib
 
 NUMER_CUTOFF = 1.0e-14      # reference __init__.py:30 (module global numer_cutoff)
+SVD_PATH_STATS = {"truncated": 0, "truncated_rejected": 0, "full": 0}
+TRUNCATED_SVD = True        # randomized subspace path for truncated decompositions (with certificate)
 
 
 def _err(msg):
@@ -94,41 +96,47 @@ def _pack_jobs(bt, labels, info, groups, lays, assigned, out_elems_mult=None):
     return jobs, used
 
 
-def _pack(bt, labels, info, groups, assigned, restrict_even=None):
-    """returns (buffer [B*R*C] after the t-sum, layouts, set of written (pB,pR,pC,pT))."""
-    lays = {g: GroupLayout([info[ch] for ch in groups[g]]) for g in ("B", "R", "C", "T")}
-    key = ("pack", bt.key(), tuple(labels), tuple((g, tuple(groups[g])) for g in ("B", "R", "C", "T")),
-           tuple(sorted(assigned[0])), tuple(sorted(assigned[1])), tuple(sorted(tuple(sorted(p)) for p in assigned[2])))
+class PackPlan:
+    """cached launch plan that packs every live block of an operand layout into [B][R][C][T]
+    (then sums the T axis away)."""
 
-    def build():
+    def __init__(self, bt, labels, info, groups, assigned, restrict_even=None):
+        self.lays = lays = {g: group_layout([info[ch] for ch in groups[g]]) for g in ("B", "R", "C", "T")}
         jobs, used = _pack_jobs(bt, labels, info, groups, lays, assigned)
-        return PermutePlan(jobs), used
-    plan, used = _cached(key, build)
-    total = lays["B"].total * lays["R"].total * lays["C"].total * lays["T"].total
-    # which regions will be read?  if the operand is even, consumers only touch parity-matched
-    # sectors; zero-fill whenever some region that may be read is not written.
-    need = 1
-    for g in ("B", "R", "C", "T"):
-        need *= len(lays[g].pats)
-    even = bt.is_even() if restrict_even is None else restrict_even
-    if even:
-        # traced labels are diagonal in parity; parity(pR)+parity(pC) must be even
-        readable = sum(1 for pb in lays["B"].pats for pr in lays["R"].pats for pc in lays["C"].pats
-                       for pt in lays["T"].pats if (sum(pr) + sum(pc)) % 2 == 0)
-        full = len(used) >= readable
-    else:
-        full = len(used) >= need
-    dev = require_cuda()
-    buf = (torch.empty if full else torch.zeros)(max(total, 1), dtype=bt.dtype, device=dev)
-    plan.run(bt.buf, buf)
-    if lays["T"].total > 1 or groups["T"]:
-        rows = lays["B"].total * lays["R"].total * lays["C"].total
-        red = torch.empty(max(rows, 1), dtype=bt.dtype, device=dev)
-        check(lib.gtn_rowsum(_ptr(buf), _ptr(red), rows, lays["T"].total, dtype_code(bt.dtype), _stream()),
-              "gtn_rowsum")
-        count()
-        buf = red
-    return buf, lays, even
+        self.plan = PermutePlan(jobs)
+        self.total = lays["B"].total * lays["R"].total * lays["C"].total * lays["T"].total
+        need = 1
+        for g in ("B", "R", "C", "T"):
+            need *= len(lays[g].pats)
+        self.even = bt.is_even() if restrict_even is None else restrict_even
+        if self.even:
+            # consumers of an even operand only touch parity-matched sectors
+            readable = sum(1 for pb in lays["B"].pats for pr in lays["R"].pats for pc in lays["C"].pats
+                           for pt in lays["T"].pats if (sum(pr) + sum(pc)) % 2 == 0)
+            self.full = len(used) >= readable
+        else:
+            self.full = len(used) >= need
+        self.reduce = lays["T"].total > 1 or bool(groups["T"])
+        self.rows = lays["B"].total * lays["R"].total * lays["C"].total
+        self.tcols = lays["T"].total
+
+    def run(self, bt):
+        dev = bt.buf.device
+        buf = (torch.empty if self.full else torch.zeros)(max(self.total, 1), dtype=bt.dtype, device=dev)
+        self.plan.run(bt.buf, buf)
+        if self.reduce:
+            red = torch.empty(max(self.rows, 1), dtype=bt.dtype, device=dev)
+            check(lib.gtn_rowsum(_ptr(buf), _ptr(red), self.rows, self.tcols, dtype_code(bt.dtype), _stream()),
+                  "gtn_rowsum")
+            count()
+            buf = red
+        return buf
+
+
+def _pack(bt, labels, info, groups, assigned, restrict_even=None):
+    """returns (buffer [B*R*C] after the t-sum, layouts, even flag)."""
+    pp = PackPlan(bt, labels, info, groups, assigned, restrict_even)
+    return pp.run(bt), pp.lays, pp.even
 
 
 def _out_bt(info, out_labels, dtype, lays_order, pats_offsets):
@@ -143,23 +151,37 @@ def _out_bt(info, out_labels, dtype, lays_order, pats_offsets):
 # ------------------------------------------------------------------------------------------------
 #  einsum
 # ------------------------------------------------------------------------------------------------
+_einsum_cache = {}
+
+
 def einsum_bt(subscripts, ops, ignore_anticommutation=False):
+    ops = [bt_force_standard(o) for o in ops]
+    dt = torch.complex128 if any(o.dtype == torch.complex128 for o in ops) else torch.float64
+    ops = [o if o.dtype == dt else _cast(o, dt) for o in ops]
+    key = (subscripts, bool(ignore_anticommutation), tuple(o.key() for o in ops))
+    ex = _einsum_cache.get(key)
+    if ex is None:
+        if len(_einsum_cache) > 2048:
+            _einsum_cache.clear()
+        ex = _build_einsum(subscripts, ops, ignore_anticommutation)
+        _einsum_cache[key] = ex
+    return ex(ops)
+
+
+def _build_einsum(subscripts, ops, ignore_anticommutation):
     inputs, output = P.parse_subscripts(subscripts)
     if len(inputs) != len(ops):
         _err("Error[einsum]: the number of subscripts does not match the number of operands")
-    ops = [bt_force_standard(o) for o in ops]
     for sub, o in zip(inputs, ops):
         if len(sub) != o.ndim:
             _err("Error[einsum]: subscript '%s' does not match a tensor with %d legs" % (sub, o.ndim))
-    dt = torch.complex128 if any(o.dtype == torch.complex128 for o in ops) else torch.float64
-    ops = [o if o.dtype == dt else _cast(o, dt) for o in ops]
     if len(ops) > 2:
-        return _einsum_fold(inputs, output, ops, ignore_anticommutation)
+        return lambda ops_: _einsum_fold(inputs, output, ops_, ignore_anticommutation)
     prog, first_stat, contracted = P.einsum_sign_program(inputs, output, [o.stats for o in ops],
                                                          ignore_anticommutation)
     if len(ops) == 1:
-        return _einsum_single(inputs[0], output, ops[0], prog)
-    return _einsum_pair(inputs, output, ops, prog)
+        return _plan_single(inputs[0], output, ops[0], prog)
+    return _plan_pair(inputs, output, ops, prog)
 
 
 def _cast(bt, dt):
@@ -200,7 +222,19 @@ def _scalar(buf):
     return v
 
 
-def _einsum_single(labels, output, bt, prog):
+def _bt_from_layout(info, labels, dtype, lay, even, buf):
+    res = _out_bt(info, labels, dtype, None, {})
+    for p in lay.pats:
+        if even and sum(p) % 2 == 1:
+            continue
+        if lay.size[p] > 0:
+            res.off[p] = lay.offset[p]
+    # the layout is parity-sorted: for an even tensor the (never written) odd part is the tail
+    res.buf = buf[: max(lay.even_total, 1)] if even else buf
+    return res
+
+
+def _plan_single(labels, output, bt, prog):
     info = _label_legs(bt, labels)
     out = output or ""
     t_labels = [ch for ch in dict.fromkeys(labels) if ch not in out]
@@ -208,21 +242,17 @@ def _einsum_single(labels, output, bt, prog):
         if labels.count(ch) == 2 and ch in out:
             raise NotImplementedError("einsum: a repeated index that is kept in the output is not supported")
     groups = {"B": [], "R": list(out), "C": [], "T": t_labels}
-    buf, lays, even = _pack(bt, labels, info, groups, (prog.alpha, prog.beta, prog.Q))
-    if output is None:
-        return _scalar(buf)
-    res = _out_bt(info, out, bt.dtype, None, {})
-    for p in lays["R"].pats:
-        if even and sum(p) % 2 == 1:
-            continue
-        if lays["R"].size[p] > 0:
-            res.off[p] = lays["R"].offset[p]
-    # the layout is parity-sorted: for an even tensor the (never written) odd part is the tail
-    res.buf = buf[: max(lays["R"].even_total, 1)] if even else buf
-    return res
+    pp = PackPlan(bt, labels, info, groups, (prog.alpha, prog.beta, prog.Q))
+
+    def run(ops):
+        buf = pp.run(ops[0])
+        if output is None:
+            return _scalar(buf)
+        return _bt_from_layout(info, out, ops[0].dtype, pp.lays["R"], pp.even, buf)
+    return run
 
 
-def _einsum_pair(inputs, output, ops, prog):
+def _plan_pair(inputs, output, ops, prog):
     la, lb = inputs
     A, B = ops
     infoA, infoB = _label_legs(A, la), _label_legs(B, lb)
@@ -283,8 +313,9 @@ def _einsum_pair(inputs, output, ops, prog):
     gL = {"B": batch, "R": L[3], "C": K, "T": L[4]}
     gR = {"B": batch, "R": K, "C": R[3], "T": R[4]}
     even = L[0].is_even() and R[0].is_even()
-    bufL, layL, _ = _pack(L[0], L[1], info, gL, asg["L"], restrict_even=even)
-    bufR, layR, _ = _pack(R[0], R[1], info, gR, asg["R"], restrict_even=even)
+    ppL = PackPlan(L[0], L[1], info, gL, asg["L"], restrict_even=even)
+    ppR = PackPlan(R[0], R[1], info, gR, asg["R"], restrict_even=even)
+    layL, layR = ppL.lays, ppR.lays
     layM, layK, layN, layB = layL["R"], layL["C"], layR["C"], layL["B"]
     Mtot, Ktot, Ntot, Btot = layM.total, layK.total, layN.total, layB.total
     tmp_labels = batch + L[3] + R[3]
@@ -316,36 +347,47 @@ def _einsum_pair(inputs, output, ops, prog):
                                lda=Ktot, ldb=Ntot, ldc=n, m=m, n=n, k=kl, batch=Btot,
                                bsa=Mtot * Ktot, bsb=Ktot * Ntot, bsc=m * n, alpha=-1.0 if e else 1.0))
             acc += Btot * m * n
-    dev = require_cuda()
-    res.buf = torch.empty(max(acc, 1), dtype=A.dtype, device=dev)
-    key = ("gemmplan", str(A.dtype), tuple(tuple(sorted(g.items())) for g in groups))
-    plan = _cached(key, lambda: GemmPlan(groups, A.dtype))
-    if Ktot == 0:
-        res.buf.zero_()
-    else:
-        plan.run(bufL, bufR, res.buf)
-    if output is None:
-        return _scalar(res.buf)
-    if "".join(tmp_labels) == out:
-        return res
-    # bring the legs into the requested order (all signs are already applied)
-    return permute_bt(res, "".join(tmp_labels), out)
+    plan = GemmPlan(groups, A.dtype)
+    res_off = dict(res.off)
+    res_meta = (res.stats, res.e, res.o)
+    tmp = "".join(tmp_labels)
+    fin = None
+    if output is not None and tmp != out:
+        # bring the legs into the requested order (all signs are already applied)
+        res.buf = None
+        fin = _plan_permute(res, tmp, out)
+
+    def run(ops_):
+        A_, B_ = ops_
+        Lop, Rop = (B_, A_) if swap else (A_, B_)
+        bufL, bufR = ppL.run(Lop), ppR.run(Rop)
+        r = BT(res_meta[0], res_meta[1], res_meta[2], A_.dtype)
+        r.off = dict(res_off)
+        r.buf = torch.empty(max(acc, 1), dtype=A_.dtype, device=A_.buf.device)
+        if Ktot == 0:
+            r.buf.zero_()
+        else:
+            plan.run(bufL, bufR, r.buf)
+        if output is None:
+            return _scalar(r.buf)
+        return r if fin is None else fin(r)
+    return run
+
+
+def _plan_permute(bt, labels, out_labels):
+    info = _label_legs(bt, labels)
+    groups = {"B": [], "R": list(out_labels), "C": [], "T": []}
+    pp = PackPlan(bt, labels, info, groups, (set(), set(), set()))
+
+    def run(x):
+        return _bt_from_layout(info, out_labels, x.dtype, pp.lays["R"], pp.even, pp.run(x))
+    return run
+
 
 
 def permute_bt(bt, labels, out_labels):
     """sign-free leg permutation of a BT (one launch)."""
-    info = _label_legs(bt, labels)
-    groups = {"B": [], "R": list(out_labels), "C": [], "T": []}
-    buf, lays, even = _pack(bt, labels, info, groups, (set(), set(), set()))
-    res = _out_bt(info, out_labels, bt.dtype, None, {})
-    for p in lays["R"].pats:
-        if even and sum(p) % 2 == 1:
-            continue
-        if lays["R"].size[p] > 0:
-            res.off[p] = lays["R"].offset[p]
-    # the layout is parity-sorted: for an even tensor the (never written) odd part is the tail
-    res.buf = buf[: max(lays["R"].even_total, 1)] if even else buf
-    return res
+    return _plan_permute(bt, labels, out_labels)(bt)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -411,8 +453,8 @@ def _decompose_prepare(bt, nl, kind):
     fR, fC = any(ferm[a] for a in Rl), any(ferm[a] for a in Cl)
     if not bt.is_even():
         _err("Error[BlockSVD]: This matrix is not constructed from a Grassmann-even tensor.")
-    layR = GroupLayout([bt.leg(a) for a in Rl])
-    layC = GroupLayout([bt.leg(a) for a in Cl])
+    layR = group_layout([bt.leg(a) for a in Rl])
+    layC = group_layout([bt.leg(a) for a in Cl])
     sectors = [0, 1] if (fR and fC) else [0]
     if fR != fC:
         # one side purely bosonic: an even tensor then lives entirely in the parity-0 rows/cols
@@ -629,7 +671,22 @@ def decompose_many(items, cutoff, kind, rule):
     run (the two SVDs of a TRG step share their sweeps)."""
     ctxs = [_decompose_prepare(bt, nl, kind) for bt, nl in items]
     mats = [m for c in ctxs for m in c["mats"]]
-    usv = batched_svd(mats)
+    usv = None
+    if cutoff is not None and kind == "svd" and TRUNCATED_SVD:
+        # how many triplets per sector can survive the rank rule (same formulas as _decompose_finish)
+        ks = []
+        for c in ctxs:
+            if len(c["sectors"]) == 2:
+                ks += ([int(cutoff / 2)] * 2 if rule == "dense" else
+                       [int(math.ceil(cutoff / 2)), int(math.floor(cutoff / 2))])
+            else:
+                ks += [cutoff]
+        if all(k >= 1 and 2 * k + 8 <= 80 and 4 * (2 * k + 8) <= min(m.shape) for k, m in zip(ks, mats)):
+            usv = truncated_svd_batch(mats, ks)
+            SVD_PATH_STATS["truncated" if usv is not None else "truncated_rejected"] += 1
+    if usv is None:
+        usv = batched_svd(mats)
+        SVD_PATH_STATS["full"] += 1
     outs, k = [], 0
     for c in ctxs:
         n = len(c["mats"])

@@ -22,18 +22,23 @@
 
 namespace {
 
-constexpr int BM = 64, BN = 64, STAGES = 3, NTHREADS = 128;
+constexpr int STAGES = 3, NTHREADS = 128;
 
-template <bool CPLX>
+// two tile configurations: 64x64 (K step = 128 B of A row) for the large sector GEMMs, and
+// 32x32 with a 4x deeper K step for the skinny (l x p x q, l ~ 40) products of the randomized
+// subspace iteration, which would otherwise occupy 8 CTAs per matrix and be latency bound.
+template <bool CPLX, int BM_, int BN_, int AROW_>
 struct Cfg {
+  static constexpr int BM = BM_, BN = BN_;
   static constexpr int ELEM = CPLX ? 16 : 8;             // bytes per element
-  static constexpr int BK = 128 / ELEM;                  // 8 complex / 16 real
-  static constexpr int A_STRIDE = 128 + (CPLX ? 64 : 32);  // bytes per A row in smem
+  static constexpr int BK = AROW_ / ELEM;                // elements of K per stage
+  static constexpr int A_STRIDE = AROW_ + (CPLX ? 64 : 32);  // bytes per A row in smem
   static constexpr int B_STRIDE = BN * ELEM + 32;        // bytes per B row in smem
   static constexpr int A_BYTES = BM * A_STRIDE;
   static constexpr int B_BYTES = BK * B_STRIDE;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int SMEM = STAGES * STAGE_BYTES;
+  static constexpr int MT = BM / 16, NT = BN / 16;       // m8 / n8 tiles per warp (2 x 2 warps)
 };
 
 __device__ __forceinline__ void cp_async(uint32_t dst, const void* src, int bytes16, bool pred) {
@@ -67,12 +72,13 @@ __device__ __forceinline__ int find_group(const gtn_gemm_group* g, int ng, int64
   return lo;
 }
 
-template <bool CPLX>
+template <bool CPLX, int BM, int BN, int AROW>
 __global__ void __launch_bounds__(NTHREADS)
     grouped_gemm_kernel(const char* __restrict__ Abase, const char* __restrict__ Bbase,
                         char* __restrict__ Cbase, const gtn_gemm_group* __restrict__ groups,
                         int ngroups) {
-  using C = Cfg<CPLX>;
+  using C = Cfg<CPLX, BM, BN, AROW>;
+  constexpr int MT = C::MT, NT = C::NT, WM = BM / 2, WN = BN / 2;
   extern __shared__ __align__(128) unsigned char smem[];
 
   const int64_t gtile = blockIdx.x;
@@ -127,12 +133,12 @@ __global__ void __launch_bounds__(NTHREADS)
   };
 
   // accumulators: 4 (m8) x 4 (n8) tiles, 2 doubles each, re (+ im)
-  double cre[4][4][2];
-  double cim[CPLX ? 4 : 1][CPLX ? 4 : 1][2];
+  double cre[MT][NT][2];
+  double cim[CPLX ? MT : 1][CPLX ? NT : 1][2];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < MT; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < NT; ++j) {
       cre[i][j][0] = cre[i][j][1] = 0.0;
       if (CPLX) cim[CPLX ? i : 0][CPLX ? j : 0][0] = cim[CPLX ? i : 0][CPLX ? j : 0][1] = 0.0;
     }
@@ -156,54 +162,54 @@ __global__ void __launch_bounds__(NTHREADS)
 #pragma unroll
     for (int ks = 0; ks < C::BK / 4; ++ks) {
       if (CPLX) {
-        double are[4], aim[4], nim[4], bre[4], bim[4];
+        double are[MT], aim[MT], nim[MT], bre[NT], bim[NT];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < MT; ++i) {
           const double2 v = *reinterpret_cast<const double2*>(
-              sa + (wm * 32 + i * 8 + g) * C::A_STRIDE + (ks * 4 + t) * 16);
+              sa + (wm * WM + i * 8 + g) * C::A_STRIDE + (ks * 4 + t) * 16);
           are[i] = v.x; aim[i] = v.y; nim[i] = -v.y;
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < NT; ++j) {
           const double2 v = *reinterpret_cast<const double2*>(
-              sb + (ks * 4 + t) * C::B_STRIDE + (wn * 32 + j * 8 + g) * 16);
+              sb + (ks * 4 + t) * C::B_STRIDE + (wn * WN + j * 8 + g) * 16);
           bre[j] = v.x; bim[j] = v.y;
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < MT; ++i)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < NT; ++j) {
             dmma(cre[i][j][0], cre[i][j][1], are[i], bre[j]);
             dmma(cim[CPLX ? i : 0][CPLX ? j : 0][0], cim[CPLX ? i : 0][CPLX ? j : 0][1], are[i], bim[j]);
             dmma(cre[i][j][0], cre[i][j][1], nim[i], bim[j]);
             dmma(cim[CPLX ? i : 0][CPLX ? j : 0][0], cim[CPLX ? i : 0][CPLX ? j : 0][1], aim[i], bre[j]);
           }
       } else {
-        double a[4], b[4];
+        double a[MT], b[NT];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          a[i] = *reinterpret_cast<const double*>(sa + (wm * 32 + i * 8 + g) * C::A_STRIDE + (ks * 4 + t) * 8);
+        for (int i = 0; i < MT; ++i)
+          a[i] = *reinterpret_cast<const double*>(sa + (wm * WM + i * 8 + g) * C::A_STRIDE + (ks * 4 + t) * 8);
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          b[j] = *reinterpret_cast<const double*>(sb + (ks * 4 + t) * C::B_STRIDE + (wn * 32 + j * 8 + g) * 8);
+        for (int j = 0; j < NT; ++j)
+          b[j] = *reinterpret_cast<const double*>(sb + (ks * 4 + t) * C::B_STRIDE + (wn * WN + j * 8 + g) * 8);
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < MT; ++i)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) dmma(cre[i][j][0], cre[i][j][1], a[i], b[j]);
+          for (int j = 0; j < NT; ++j) dmma(cre[i][j][0], cre[i][j][1], a[i], b[j]);
       }
     }
   }
   cp_wait<0>();
 
-  // epilogue: thread owns rows (wm*32 + i*8 + g), cols (wn*32 + j*8 + 2t, +1)
+  // epilogue: thread owns rows (wm*WM + i*8 + g), cols (wn*WN + j*8 + 2t, +1)
   const double alpha = grp.alpha, beta = grp.beta;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int r = m0 + wm * 32 + i * 8 + g;
+  for (int i = 0; i < MT; ++i) {
+    const int r = m0 + wm * WM + i * 8 + g;
     if (r >= M) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int c = n0 + wn * 32 + j * 8 + 2 * t;
+    for (int j = 0; j < NT; ++j) {
+      const int c = n0 + wn * WN + j * 8 + 2 * t;
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         if (c + e >= N) continue;
@@ -225,10 +231,27 @@ __global__ void __launch_bounds__(NTHREADS)
   }
 }
 
+template <bool CPLX, int BM, int BN, int AROW>
+int launch_cfg(const void* A, const void* B, void* C, const gtn_gemm_group* groups_dev, int ngroups,
+               int64_t total_tiles, cudaStream_t s) {
+  using K = Cfg<CPLX, BM, BN, AROW>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(grouped_gemm_kernel<CPLX, BM, BN, AROW>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  grouped_gemm_kernel<CPLX, BM, BN, AROW><<<dim3((unsigned)total_tiles), dim3(NTHREADS), K::SMEM, s>>>(
+      (const char*)A, (const char*)B, (char*)C, groups_dev, ngroups);
+  return (int)cudaGetLastError();
+}
+
 }  // namespace
 
-extern "C" int64_t gtn_gemm_plan_host(gtn_gemm_group* groups, int ngroups, int dtype) {
+extern "C" int64_t gtn_gemm_plan_host(gtn_gemm_group* groups, int ngroups, int dtype, int config) {
   (void)dtype;
+  const int64_t BM = config == 1 ? 32 : 64, BN = config == 1 ? 32 : 64;
   int64_t acc = 0;
   for (int i = 0; i < ngroups; ++i) {
     groups[i].tile_start = acc;
@@ -241,23 +264,16 @@ extern "C" int64_t gtn_gemm_plan_host(gtn_gemm_group* groups, int ngroups, int d
 
 extern "C" int gtn_grouped_gemm(const void* A, const void* B, void* C, int dtype,
                                 const gtn_gemm_group* groups_dev, int ngroups,
-                                int64_t total_tiles, void* stream) {
+                                int64_t total_tiles, int config, void* stream) {
   if (ngroups <= 0 || total_tiles <= 0) return GTN_OK;
   if (total_tiles > 2147483647LL) return GTN_ERR_BAD_ARG;
   cudaStream_t s = (cudaStream_t)stream;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(grouped_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<true>::SMEM);
-    cudaFuncSetAttribute(grouped_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<false>::SMEM);
-    attr_set = true;
-  }
-  dim3 grid((unsigned)total_tiles), block(NTHREADS);
   if (dtype == GTN_C128) {
-    grouped_gemm_kernel<true><<<grid, block, Cfg<true>::SMEM, s>>>((const char*)A, (const char*)B, (char*)C, groups_dev, ngroups);
+    if (config == 1) return launch_cfg<true, 32, 32, 512>(A, B, C, groups_dev, ngroups, total_tiles, s);
+    return launch_cfg<true, 64, 64, 128>(A, B, C, groups_dev, ngroups, total_tiles, s);
   } else if (dtype == GTN_F64) {
-    grouped_gemm_kernel<false><<<grid, block, Cfg<false>::SMEM, s>>>((const char*)A, (const char*)B, (char*)C, groups_dev, ngroups);
-  } else {
-    return GTN_ERR_BAD_ARG;
+    if (config == 1) return launch_cfg<false, 32, 32, 512>(A, B, C, groups_dev, ngroups, total_tiles, s);
+    return launch_cfg<false, 64, 64, 128>(A, B, C, groups_dev, ngroups, total_tiles, s);
   }
-  return (int)cudaGetLastError();
+  return GTN_ERR_BAD_ARG;
 }

@@ -62,6 +62,24 @@ __global__ void __launch_bounds__(RT) rowsum_kernel(const double* __restrict__ x
   }
 }
 
+// out[r] = sum_c |x[r, c]|^2
+template <bool CPLX>
+__global__ void __launch_bounds__(RT) row_sumsq_kernel(const double* __restrict__ x, double* __restrict__ y,
+                                                       int64_t rows, int64_t cols) {
+  const int64_t r = blockIdx.x;
+  if (r >= rows) return;
+  double a = 0;
+  if (CPLX) {
+    const double2* p = reinterpret_cast<const double2*>(x) + r * cols;
+    for (int64_t c = threadIdx.x; c < cols; c += RT) { const double2 v = __ldg(p + c); a += v.x * v.x + v.y * v.y; }
+  } else {
+    const double* p = x + r * cols;
+    for (int64_t c = threadIdx.x; c < cols; c += RT) { const double v = __ldg(p + c); a += v * v; }
+  }
+  a = block_sum(a);
+  if (threadIdx.x == 0) y[r] = a;
+}
+
 // complex power: principal branch of z^p, like numpy.power on complex128
 __device__ __forceinline__ void cpow(double& re, double& im, double p) {
   const double r = hypot(re, im);
@@ -148,6 +166,16 @@ extern "C" int gtn_rowsum(const void* x, void* y, int64_t rows, int64_t cols, in
   cudaStream_t s = (cudaStream_t)stream;
   if (dtype == GTN_C128) rowsum_kernel<true><<<(unsigned)rows, RT, 0, s>>>((const double*)x, (double*)y, rows, cols);
   else if (dtype == GTN_F64) rowsum_kernel<false><<<(unsigned)rows, RT, 0, s>>>((const double*)x, (double*)y, rows, cols);
+  else return GTN_ERR_BAD_ARG;
+  return (int)cudaGetLastError();
+}
+
+extern "C" int gtn_row_sumsq(const void* x, double* y, int64_t rows, int64_t cols, int dtype, void* stream) {
+  if (rows <= 0) return GTN_OK;
+  if (rows > 2147483647LL) return GTN_ERR_BAD_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == GTN_C128) row_sumsq_kernel<true><<<(unsigned)rows, RT, 0, s>>>((const double*)x, y, rows, cols);
+  else if (dtype == GTN_F64) row_sumsq_kernel<false><<<(unsigned)rows, RT, 0, s>>>((const double*)x, y, rows, cols);
   else return GTN_ERR_BAD_ARG;
   return (int)cudaGetLastError();
 }

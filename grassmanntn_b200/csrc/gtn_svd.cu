@@ -375,3 +375,319 @@ extern "C" int gtn_jacobi_finish(const void* W, const void* Z, void* U_out, void
   }
   return (int)cudaGetLastError();
 }
+
+// ------------------------------------------------------------------------------------------------
+//  small Hermitian eigen-solver (two-sided Jacobi, one CTA per matrix, everything in shared memory)
+//  used to orthonormalise the l x p iterates of the randomized subspace iteration through their
+//  l x l Gram matrix:  G = E L E^H  ->  T = L^{-1/2} E^H  (rows with L_i <= rel_thr * L_max are zeroed),
+//  so that (T Y)(T Y)^H = I on the retained directions.
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int EIG_MAXN = 80;
+constexpr int EIG_T = 256;
+
+template <bool CPLX>
+__global__ void __launch_bounds__(EIG_T)
+    small_eigh_whiten_kernel(const typename Elem<CPLX>::T* __restrict__ Gb, typename Elem<CPLX>::T* __restrict__ Tb,
+                             const int64_t* __restrict__ g_off, const int64_t* __restrict__ t_off,
+                             const int32_t* __restrict__ ns, double rel_thr, int32_t* __restrict__ kept,
+                             double* __restrict__ evals, const int64_t* __restrict__ e_off) {
+  using T = typename Elem<CPLX>::T;
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  const int n = ns[blockIdx.x];
+  const int ld = n + 1;
+  c128* G = reinterpret_cast<c128*>(sm_raw);
+  c128* E = G + n * ld;
+  double* rot = reinterpret_cast<double*>(E + n * ld);   // per pair: cs, sn, phr, phi
+  int* pq = reinterpret_cast<int*>(rot + 4 * (EIG_MAXN / 2));
+  __shared__ double offmax_s;
+  __shared__ double lmax_s;
+  const int tid = threadIdx.x;
+  const T* Gin = Gb + g_off[blockIdx.x];
+  for (int e = tid; e < n * n; e += EIG_T) {
+    const int i = e / n, j = e % n;
+    c128 v;
+    if constexpr (CPLX) { const T t = Elem<CPLX>::ld(Gin + e); v.re = t.re; v.im = t.im; }
+    else { v.re = Elem<CPLX>::ld(Gin + e); v.im = 0.0; }
+    G[i * ld + j] = v;
+    c128 id; id.re = (i == j) ? 1.0 : 0.0; id.im = 0.0;
+    E[i * ld + j] = id;
+  }
+  __syncthreads();
+  const int P = (n + 1) & ~1;
+  const int npairs = P / 2;
+  for (int sweep = 0; sweep < 40; ++sweep) {
+    if (tid == 0) offmax_s = 0.0;
+    __syncthreads();
+    for (int round = 0; round < P - 1; ++round) {
+      if (tid < npairs) {
+        int i, j;
+        if (tid == 0) { i = P - 1; j = round; }
+        else { i = (round + tid) % (P - 1); j = (round - tid + (P - 1)) % (P - 1); }
+        if (i > j) { const int t = i; i = j; j = t; }
+        double cs = 1.0, sn = 0.0, phr = 1.0, phi = 0.0;
+        int act = 0;
+        if (j < n) {
+          const double a = G[i * ld + i].re, b = G[j * ld + j].re;
+          const c128 c = G[i * ld + j];
+          const double cabs = sqrt(c.re * c.re + c.im * c.im);
+          const double den = sqrt(fabs(a)) * sqrt(fabs(b));
+          if (cabs > 0.0 && den > 0.0 && cabs > 1e-15 * den) {
+            const double zeta = (b - a) / (2.0 * cabs);
+            const double tt = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+            cs = 1.0 / sqrt(1.0 + tt * tt);
+            sn = cs * tt;
+            phr = c.re / cabs; phi = c.im / cabs;
+            act = 1;
+            atomicMax(reinterpret_cast<unsigned long long*>(&offmax_s),
+                      (unsigned long long)__double_as_longlong(cabs / den));
+          }
+        }
+        rot[4 * tid + 0] = cs; rot[4 * tid + 1] = sn; rot[4 * tid + 2] = phr; rot[4 * tid + 3] = phi;
+        pq[2 * tid] = act ? i : -1; pq[2 * tid + 1] = j;
+      }
+      __syncthreads();
+      // rows: [x; y] <- Jr [x; y] on G and E,  Jr = [[cs, -sn ph], [sn, cs ph]]
+      for (int w = tid; w < npairs * n * 2; w += EIG_T) {
+        const int k = w / (2 * n), r = w % (2 * n);
+        const int which = r / n, col = r % n;
+        const int i = pq[2 * k], j = pq[2 * k + 1];
+        if (i < 0) continue;
+        c128* Mx = which ? E : G;
+        c128 x = Mx[i * ld + col], y = Mx[j * ld + col];
+        {
+          const double cs = rot[4 * k], sn = rot[4 * k + 1], phr = rot[4 * k + 2], phi = rot[4 * k + 3];
+          const double yr = phr * y.re - phi * y.im, yi = phr * y.im + phi * y.re;
+          c128 xn, yn;
+          xn.re = cs * x.re - sn * yr; xn.im = cs * x.im - sn * yi;
+          yn.re = sn * x.re + cs * yr; yn.im = sn * x.im + cs * yi;
+          Mx[i * ld + col] = xn; Mx[j * ld + col] = yn;
+        }
+      }
+      __syncthreads();
+      // columns of G: [g_ri, g_rj] <- [g_ri, g_rj] Jr^H
+      for (int w = tid; w < npairs * n; w += EIG_T) {
+        const int k = w / n, row = w % n;
+        const int i = pq[2 * k], j = pq[2 * k + 1];
+        if (i < 0) continue;
+        const double cs = rot[4 * k], sn = rot[4 * k + 1], phr = rot[4 * k + 2], phi = rot[4 * k + 3];
+        const c128 gi = G[row * ld + i], gj = G[row * ld + j];
+        // conj(ph) * gj
+        const double jr = phr * gj.re + phi * gj.im, ji = phr * gj.im - phi * gj.re;
+        c128 ni, nj;
+        ni.re = cs * gi.re - sn * jr; ni.im = cs * gi.im - sn * ji;
+        nj.re = sn * gi.re + cs * jr; nj.im = sn * gi.im + cs * ji;
+        G[row * ld + i] = ni; G[row * ld + j] = nj;
+      }
+      __syncthreads();
+    }
+    if (offmax_s <= 1e-15) break;
+    __syncthreads();
+  }
+  // eigenvalues on the diagonal; T = L^{-1/2} Eacc (rows), small ones zeroed
+  if (tid == 0) {
+    double m = 0.0;
+    for (int i = 0; i < n; ++i) m = fmax(m, G[i * ld + i].re);
+    lmax_s = m;
+    int cnt = 0;
+    for (int i = 0; i < n; ++i) cnt += (G[i * ld + i].re > rel_thr * m) ? 1 : 0;
+    kept[blockIdx.x] = cnt;
+  }
+  __syncthreads();
+  T* Tout = Tb + t_off[blockIdx.x];
+  double* ev = evals + e_off[blockIdx.x];
+  for (int e = tid; e < n * n; e += EIG_T) {
+    const int i = e / n, j = e % n;
+    const double lam = G[i * ld + i].re;
+    const double sc = (lam > rel_thr * lmax_s && lam > 0.0) ? rsqrt(lam) : 0.0;
+    const c128 v = E[i * ld + j];
+    if constexpr (CPLX) { T t; t.re = v.re * sc; t.im = v.im * sc; Elem<CPLX>::st(Tout + e, t); }
+    else Elem<CPLX>::st(Tout + e, v.re * sc);
+    if (j == 0) ev[i] = lam;
+  }
+}
+
+}  // namespace
+
+extern "C" int gtn_small_eigh_whiten(const void* G, void* T, int dtype, const int64_t* g_off_dev,
+                                     const int64_t* t_off_dev, const int32_t* n_dev, int nprob, int max_n,
+                                     double rel_thr, int32_t* kept_dev, double* evals_dev,
+                                     const int64_t* e_off_dev, void* stream) {
+  if (nprob <= 0) return GTN_OK;
+  if (max_n > EIG_MAXN) return GTN_ERR_UNSUPPORTED;
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t smem = size_t(2) * max_n * (max_n + 1) * 16 + 4 * (EIG_MAXN / 2) * 8 + 2 * (EIG_MAXN / 2) * 4 + 64;
+  static size_t attr = 0;
+  if (smem > attr) {
+    cudaError_t e1 = cudaFuncSetAttribute(small_eigh_whiten_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e2 = cudaFuncSetAttribute(small_eigh_whiten_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e1 != cudaSuccess) return (int)e1;
+    if (e2 != cudaSuccess) return (int)e2;
+    attr = smem;
+  }
+  if (dtype == GTN_C128)
+    small_eigh_whiten_kernel<true><<<nprob, EIG_T, smem, s>>>((const c128*)G, (c128*)T, g_off_dev, t_off_dev, n_dev,
+                                                             rel_thr, kept_dev, evals_dev, e_off_dev);
+  else if (dtype == GTN_F64)
+    small_eigh_whiten_kernel<false><<<nprob, EIG_T, smem, s>>>((const double*)G, (double*)T, g_off_dev, t_off_dev,
+                                                              n_dev, rel_thr, kept_dev, evals_dev, e_off_dev);
+  else
+    return GTN_ERR_BAD_ARG;
+  return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+//  pivoted-Cholesky whitening of a small Gram matrix (one CTA per matrix, shared memory):
+//     P^T G P = L L^H (rank r, stop when the largest remaining diagonal <= rel_thr * first pivot)
+//     T = [ L_r^{-1}  0 ] P^T        =>   (T Y)(T Y)^H = I_r   when G = Y Y^H
+//  ~5 block barriers per pivot instead of the ~120 per sweep of the Jacobi eigen-solver above.
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+template <bool CPLX>
+__global__ void __launch_bounds__(EIG_T)
+    small_chol_whiten_kernel(const typename Elem<CPLX>::T* __restrict__ Gb, typename Elem<CPLX>::T* __restrict__ Tb,
+                             const int64_t* __restrict__ g_off, const int64_t* __restrict__ t_off,
+                             const int32_t* __restrict__ ns, double rel_thr, int32_t* __restrict__ kept) {
+  using T = typename Elem<CPLX>::T;
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  const int n = ns[blockIdx.x];
+  const int ld = n + 1;
+  c128* G = reinterpret_cast<c128*>(sm_raw);       // lower triangle becomes L
+  c128* Li = G + n * ld;                           // inverse of L_r
+  __shared__ int perm[EIG_MAXN];
+  __shared__ double redv[EIG_T / 32];
+  __shared__ int redi[EIG_T / 32];
+  __shared__ int piv_s, rank_s;
+  __shared__ double first_s;
+  const int tid = threadIdx.x;
+  const T* Gin = Gb + g_off[blockIdx.x];
+  for (int e = tid; e < n * n; e += EIG_T) {
+    const int i = e / n, j = e % n;
+    c128 v;
+    if constexpr (CPLX) { const T t = Elem<CPLX>::ld(Gin + e); v.re = t.re; v.im = t.im; }
+    else { v.re = Elem<CPLX>::ld(Gin + e); v.im = 0.0; }
+    G[i * ld + j] = v;
+    c128 z; z.re = 0.0; z.im = 0.0;
+    Li[i * ld + j] = z;
+  }
+  if (tid < n) perm[tid] = tid;
+  if (tid == 0) { rank_s = n; first_s = 0.0; }
+  __syncthreads();
+  for (int k = 0; k < n; ++k) {
+    // ---- pivot: arg max of the remaining diagonal
+    double best = -1.0; int bi = k;
+    for (int i = k + tid; i < n; i += EIG_T) {
+      const double d = G[i * ld + i].re;
+      if (d > best) { best = d; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if ((tid & 31) == 0) { redv[tid >> 5] = best; redi[tid >> 5] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+      double b = redv[0]; int x = redi[0];
+      for (int w = 1; w < EIG_T / 32; ++w)
+        if (redv[w] > b || (redv[w] == b && redi[w] < x)) { b = redv[w]; x = redi[w]; }
+      if (k == 0) first_s = b;
+      piv_s = (b > rel_thr * first_s && b > 0.0) ? x : -1;
+      if (piv_s < 0) rank_s = k;
+    }
+    __syncthreads();
+    const int pv = piv_s;
+    if (pv < 0) break;
+    // ---- symmetric swap k <-> pv (rows and columns; includes the finished L columns < k)
+    if (pv != k) {
+      for (int j = tid; j < n; j += EIG_T) {
+        const c128 a = G[k * ld + j]; G[k * ld + j] = G[pv * ld + j]; G[pv * ld + j] = a;
+      }
+      __syncthreads();
+      for (int i = tid; i < n; i += EIG_T) {
+        const c128 a = G[i * ld + k]; G[i * ld + k] = G[i * ld + pv]; G[i * ld + pv] = a;
+      }
+      if (tid == 0) { const int t = perm[k]; perm[k] = perm[pv]; perm[pv] = t; }
+      __syncthreads();
+    }
+    // ---- column k of L
+    const double dkk = sqrt(G[k * ld + k].re);
+    const double inv = 1.0 / dkk;
+    __syncthreads();
+    for (int i = k + tid; i < n; i += EIG_T) {
+      c128 v = G[i * ld + k];
+      if (i == k) { v.re = dkk; v.im = 0.0; } else { v.re *= inv; v.im *= inv; }
+      G[i * ld + k] = v;
+    }
+    __syncthreads();
+    // ---- trailing update G[i][j] -= L[i][k] conj(L[j][k]),  i,j > k
+    const int m = n - k - 1;
+    for (int e = tid; e < m * m; e += EIG_T) {
+      const int i = k + 1 + e / m, j = k + 1 + e % m;
+      const c128 a = G[i * ld + k], b = G[j * ld + k];
+      c128 g = G[i * ld + j];
+      g.re -= a.re * b.re + a.im * b.im;
+      g.im -= a.im * b.re - a.re * b.im;
+      G[i * ld + j] = g;
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  const int r = rank_s;
+  // ---- Li = L_r^{-1}: one thread per column c, forward substitution
+  for (int c = tid; c < r; c += EIG_T) {
+    for (int i = c; i < r; ++i) {
+      double sr = (i == c) ? 1.0 : 0.0, si = 0.0;
+      for (int j = c; j < i; ++j) {
+        const c128 l = G[i * ld + j], x = Li[j * ld + c];
+        sr -= l.re * x.re - l.im * x.im;
+        si -= l.re * x.im + l.im * x.re;
+      }
+      const double d = 1.0 / G[i * ld + i].re;
+      c128 o; o.re = sr * d; o.im = si * d;
+      Li[i * ld + c] = o;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) kept[blockIdx.x] = r;
+  T* Tout = Tb + t_off[blockIdx.x];
+  for (int e = tid; e < n * n; e += EIG_T) {
+    const int i = e / n, c = e % n;       // T[i][perm[c]] = Li[i][c]
+    c128 v; v.re = 0.0; v.im = 0.0;
+    if (i < r && c < r) v = Li[i * ld + c];
+    T* dst = Tout + int64_t(i) * n + perm[c];
+    if constexpr (CPLX) { T t; t.re = v.re; t.im = v.im; Elem<CPLX>::st(dst, t); }
+    else Elem<CPLX>::st(dst, v.re);
+  }
+}
+
+}  // namespace
+
+extern "C" int gtn_small_chol_whiten(const void* G, void* T, int dtype, const int64_t* g_off_dev,
+                                     const int64_t* t_off_dev, const int32_t* n_dev, int nprob, int max_n,
+                                     double rel_thr, int32_t* kept_dev, void* stream) {
+  if (nprob <= 0) return GTN_OK;
+  if (max_n > EIG_MAXN) return GTN_ERR_UNSUPPORTED;
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t smem = size_t(2) * max_n * (max_n + 1) * 16 + 64;
+  static size_t attr = 0;
+  if (smem > attr) {
+    cudaError_t e1 = cudaFuncSetAttribute(small_chol_whiten_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e2 = cudaFuncSetAttribute(small_chol_whiten_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e1 != cudaSuccess) return (int)e1;
+    if (e2 != cudaSuccess) return (int)e2;
+    attr = smem;
+  }
+  if (dtype == GTN_C128)
+    small_chol_whiten_kernel<true><<<nprob, EIG_T, smem, s>>>((const c128*)G, (c128*)T, g_off_dev, t_off_dev, n_dev,
+                                                             rel_thr, kept_dev);
+  else if (dtype == GTN_F64)
+    small_chol_whiten_kernel<false><<<nprob, EIG_T, smem, s>>>((const double*)G, (double*)T, g_off_dev, t_off_dev,
+                                                              n_dev, rel_thr, kept_dev);
+  else
+    return GTN_ERR_BAD_ARG;
+  return (int)cudaGetLastError();
+}

@@ -110,12 +110,14 @@ typedef struct {
   int64_t tile_start; /* prefix sum of CTA tiles (filled by gtn_gemm_plan_host) */
 } gtn_gemm_group;
 
-/* Fills tile_start for all groups on the HOST array and returns the total CTA count. */
-int64_t gtn_gemm_plan_host(gtn_gemm_group* groups_host, int ngroups, int dtype);
+/* Fills tile_start for all groups on the HOST array and returns the total CTA count.
+ * config 0: 64x64 CTA tiles (large sector GEMMs); config 1: 32x32 tiles with a 4x deeper K step
+ * (skinny l x p x q products of the randomized subspace iteration).  Same config at launch. */
+int64_t gtn_gemm_plan_host(gtn_gemm_group* groups_host, int ngroups, int dtype, int config);
 
 int gtn_grouped_gemm(const void* A, const void* B, void* C, int dtype,
                      const gtn_gemm_group* groups_dev, int ngroups, int64_t total_tiles,
-                     void* stream);
+                     int config, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Batched one-sided Jacobi SVD (Hestenes) of the parity-sector matrices.
@@ -161,6 +163,25 @@ int gtn_jacobi_finish(const void* W, const void* Z, void* U_out, void* Vh_out, d
                       int32_t* order_dev, double* norm_scratch_dev, int nprob, int max_p,
                       int max_q, void* stream);
 
+/* Whitening transform from a small Hermitian Gram matrix (two-sided Jacobi, one CTA per matrix, all
+ * in shared memory; n_b <= 80).  For every problem b: G_b (n_b x n_b, row-major) = E L E^H and
+ * T_b = L^{-1/2} E^H with the rows of eigenvalues <= rel_thr * L_max zeroed (kept_dev[b] = number
+ * retained, evals_dev[e_off[b] + i] = L_i), so that T_b Y orthonormalises the rows of Y when
+ * G_b = Y Y^H.  Used by the randomized subspace iteration of the truncated sector SVD -- the
+ * "Gram-matrix / randomized-projection" replacement of LAPACK's full gesdd in reference SortedSVD
+ * (__init__.py:3932) when only the first `cutoff` triplets survive (:3943-3948). */
+int gtn_small_eigh_whiten(const void* G, void* T, int dtype, const int64_t* g_off_dev,
+                          const int64_t* t_off_dev, const int32_t* n_dev, int nprob, int max_n,
+                          double rel_thr, int32_t* kept_dev, double* evals_dev,
+                          const int64_t* e_off_dev, void* stream);
+
+/* Same contract as gtn_small_eigh_whiten with a diagonally pivoted Cholesky factorisation
+ * P^T G P = L L^H (stopped at numerical rank r: remaining diagonal <= rel_thr * first pivot):
+ * T = [L_r^{-1} 0] P^T, rows >= r zero, kept_dev[b] = r.  ~10x fewer block barriers. */
+int gtn_small_chol_whiten(const void* G, void* T, int dtype, const int64_t* g_off_dev,
+                          const int64_t* t_off_dev, const int32_t* n_dev, int nprob, int max_n,
+                          double rel_thr, int32_t* kept_dev, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Small element-wise / reduction helpers.
  * ------------------------------------------------------------------------------------------ */
@@ -172,6 +193,9 @@ int gtn_sumsq(const void* x, int64_t n, int dtype, double* out_dev, int zero_fir
  * 'IJIJ' -- the final reduction of oe.contract at __init__.py:2295 when nothing is left to
  * multiply).  y has `rows` elements of the same dtype. */
 int gtn_rowsum(const void* x, void* y, int64_t rows, int64_t cols, int dtype, void* stream);
+
+/* y[r] = sum_c |x[r*cols + c]|^2 (double): residual norms of the truncated-SVD certificate. */
+int gtn_row_sumsq(const void* x, double* y, int64_t rows, int64_t cols, int dtype, void* stream);
 
 /* x_i <- |x_i| > rcond ? x_i^p : 0   (power_ds, __init__.py:6059-6069; fixed power_block :6071). */
 int gtn_pow_rcond(void* x, int64_t n, int dtype, double p, double rcond, void* stream);

@@ -170,3 +170,46 @@ def test_cg_step_vs_oracle(gtn, algo, fmt):
     Fr = O.logZ(Tr, 'anti-periodic', block_format=(fmt == "block"))
     Fg = g.logZ(Tg, 'anti-periodic')
     assert abs(Fg - Fr) <= 1e-10 * max(abs(Fr), 1.0)
+
+
+def _decaying_even_tensor(D, rng, rate=0.5):
+    """Grassmann-even (D,D,D,D) tensor whose (ab|cd) sector matrices have a geometric spectrum."""
+    a = O.random_dense((D, D, D, D), (1, 1, -1, -1), dtype=complex, rng=rng)
+    U, S, V = O.svd(a, 'ab|cd')
+    d = S.data.copy()
+    n = d.shape[0]
+    for i in range(n):
+        d[i, i] = d[i, i] / max(abs(d[i, i]), 1e-300) * np.exp(-rate * (i // 2))
+    S2 = O.Dense(d, S.statistics, S.encoder, S.format)
+    return O.einsum('abx,xy,ycd->abcd', U, S2, V)
+
+
+@pytest.mark.parametrize("kind", ["decaying", "flat"])
+def test_truncated_svd_path(gtn, kind):
+    """the randomized subspace path (accepted for decaying spectra, rejected -> full Jacobi for flat
+    ones) must give the same kept singular values as the oracle's full LAPACK SVD"""
+    from grassmanntn_b200 import _ops
+    rng = np.random.RandomState(31)
+    D = 16
+    a = _decaying_even_tensor(D, rng) if kind == "decaying" else O.random_dense((D,) * 4, (1, 1, -1, -1), dtype=complex, rng=rng)
+    A = gtn.dense(a.data, statistics=(1, 1, -1, -1))
+    before = dict(_ops.SVD_PATH_STATS)
+    for cut, fmt in ((8, "dense"), (10, "block")):
+        Ur, Sr, Vr, counts = O.svd(a, 'ab|cd', cut, rule=fmt, return_counts=True)
+        X = A if fmt == "dense" else A.toblock()
+        U, S, V = X.svd('ab|cd', cut)
+        if fmt == "dense":
+            sg = np.sort(np.abs(np.diag(S.data.cpu().numpy())))[::-1]
+            rec_g = gtn.einsum('abx,xy,ycd->abcd', U, S, V).data.cpu().numpy()
+        else:
+            sg = np.sort(np.abs(np.diag(S.todense().data.cpu().numpy())))[::-1]
+            rec_g = gtn.einsum('abx,xy,ycd->abcd', U, S, V).todense().data.cpu().numpy()
+        sr = np.sort(np.abs(np.diag(Sr.data)))[::-1]
+        n = min(len(sr), len(sg))
+        assert np.abs(sr[:n] - sg[:n]).max() <= 1e-10 * sr[0], (kind, fmt)
+        assert np.count_nonzero(sg > 1e-14 * sg[0]) == sum(counts)
+        rec_r = O.einsum('abx,xy,ycd->abcd', Ur, Sr, Vr).data
+        assert _relerr(rec_g, rec_r) < 1e-9, (kind, fmt)
+    after = _ops.SVD_PATH_STATS
+    if kind == "decaying":
+        assert after["truncated"] > before["truncated"]
