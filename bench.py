@@ -322,6 +322,51 @@ def microbench(gtn, E, torch, dev, args, hbm_peak):
         out["sign_permute_D%d" % D] = {"ms": ms, "GBps": gbs, "frac_hbm": gbs / hbm_peak,
                                        "bytes": 2 * n * 16, "note": "all 16 parity blocks, full (non-even) tensor"}
         del x, A, bt, r
+    # ---- the TRG main contraction 'lxzk,jzxi->ijkl' (gauge2d.py:1734) on Grassmann-even block tensors:
+    #      2 pack launches + 8 sector GEMMs in one grouped launch; algorithmic flops = 8*m*n*k over the
+    #      non-zero parity sectors = 2*chi^6 (a quarter of the dense count)
+    from grassmanntn_b200 import _ops as _o
+    for D in (64, 128):
+        try:
+            np.random.seed(1)
+            half = D // 2
+            def even_block(stats):
+                b = gtn.zero_block_eo((half,) * 4, (half,) * 4, stats, dtype=complex)
+                bt = b._bt
+                for p_ in bt.patterns():
+                    if sum(p_) % 2 == 0:
+                        v = bt.block_view(p_)
+                        v.copy_(torch.rand(v.shape, dtype=torch.float64, device=dev) + 1j * torch.rand(v.shape, dtype=torch.float64, device=dev))
+                    else:
+                        bt.zero.add(p_)
+                return b
+            VV = even_block((1, 1, -1, 1))
+            UU = even_block((-1, 1, -1, 1))
+            for _ in range(2):
+                r = gtn.einsum('lxzk,jzxi->ijkl', VV, UU)
+            torch.cuda.synchronize()
+            E.PROF.start()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 3
+            s.record()
+            for _ in range(reps):
+                r = gtn.einsum('lxzk,jzxi->ijkl', VV, UU)
+            e.record()
+            torch.cuda.synchronize()
+            pr = E.PROF.stop()
+            ms = s.elapsed_time(e) / reps
+            flops = 2.0 * D ** 6
+            gm = pr["grouped_gemm"]
+            out["trg_contraction_D%d" % D] = {
+                "ms_total": ms, "TFLOPs_total": flops / (ms * 1e-3) / 1e12,
+                "ms_gemm": gm["ms"] / reps, "TFLOPs_gemm": gm["flops"] / reps / (gm["ms"] / reps * 1e-3) / 1e12,
+                "ms_pack": pr["sign_permute"]["ms"] / reps,
+                "pack_GBps": pr["sign_permute"]["bytes"] / reps / (pr["sign_permute"]["ms"] / reps * 1e-3) / 1e9,
+                "algorithmic_flops": flops}
+            del VV, UU, r
+            torch.cuda.empty_cache()
+        except Exception as ex:       # e.g. out of memory on a smaller part
+            out["trg_contraction_D%d" % D] = {"error": repr(ex)[:200]}
     # ---- DMMA grouped GEMM vs cuBLAS ZGEMM yard-stick
     for N in (2048, 4096):
         a = torch.randn(N, N, dtype=torch.complex128, device=dev)

@@ -667,6 +667,7 @@ def gemm(A, B, m, n, k, lda=None, ldb=None, ldc=None, out=None):
 # ------------------------------------------------------------------------------------------------
 JACOBI_TOL = 4e-15
 JACOBI_MAX_SWEEPS = 60
+PERSISTENT_MAX_ROWS = 160   # batches up to this many rows try the one-launch cooperative Jacobi kernel
 
 
 def batched_svd(mats):
@@ -712,9 +713,27 @@ def batched_svd(mats):
     check(lib.gtn_jacobi_init(_ptr(W), _ptr(Z), code, _ptr(pdev), nprob, maxp, _ptr(rn2), _ptr(fro2), _ptr(rn_off),
                               st), "gtn_jacobi_init")
     count()
-    offd = torch.zeros(nprob, dtype=torch.float64, device=dev)
+    offd = torch.zeros(2 * nprob, dtype=torch.float64, device=dev)
     sweeps = 0
-    if maxp >= 2:
+    done = False
+    if 2 <= maxp <= PERSISTENT_MAX_ROWS:
+        # small problems: the whole sweep loop in one cooperative launch
+        sw = torch.zeros(2, dtype=torch.int32, device=dev)
+        P = (maxp + 1) & ~1
+        esz = W.element_size()
+        rb = sum(2 * esz * (pr[2] * pr[3] + pr[2] * pr[2]) for pr in probs)
+        with prof_region("jacobi_persistent", 1, 0):
+            rc = lib.gtn_jacobi_persistent(_ptr(W), _ptr(Z), code, _ptr(pdev), nprob, maxp, JACOBI_TOL, _ptr(offd),
+                                           _ptr(rn2), _ptr(fro2), _ptr(rn_off), JACOBI_MAX_SWEEPS, _ptr(sw), st)
+        if rc == 0:
+            swh = sw.cpu().tolist()
+            sweeps = swh[0]
+            if not swh[1]:
+                raise _cabi.GtnError("Jacobi SVD did not converge in %d sweeps" % sweeps)
+            done = True
+        elif rc != -2:
+            check(rc, "gtn_jacobi_persistent")
+    if maxp >= 2 and not done:
         while True:
             P = (maxp + 1) & ~1
             esz = W.element_size()
@@ -723,7 +742,7 @@ def batched_svd(mats):
                 check(lib.gtn_jacobi_sweep(_ptr(W), _ptr(Z), code, _ptr(pdev), nprob, maxp, maxq, JACOBI_TOL,
                                            _ptr(offd), _ptr(rn2), _ptr(fro2), _ptr(rn_off), st), "gtn_jacobi_sweep")
             sweeps += 1
-            if float(offd.max().item()) <= JACOBI_TOL:
+            if float(offd[:nprob].max().item()) <= JACOBI_TOL:
                 break
             if sweeps >= JACOBI_MAX_SWEEPS:
                 raise _cabi.GtnError("Jacobi SVD did not converge in %d sweeps" % sweeps)

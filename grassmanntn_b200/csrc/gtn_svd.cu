@@ -14,10 +14,13 @@
 // pairs per sweep, one launch per round for the WHOLE batch of sector matrices (the E and O
 // sectors of both SVDs of a TRG step go in one batch).  Row elements stay in registers between
 // the reduction and the rotation when q <= 256*CACHE.
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include "../../include/gtn_b200.h"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -71,19 +74,20 @@ __device__ __forceinline__ void rot(double& x, double& y, double cs, double sn, 
   y = sn * xx + cs * yy;
 }
 
+// one (round, pair) step of the one-sided Jacobi iteration for problem `prob`, executed by one CTA
 template <bool CPLX>
-__global__ void __launch_bounds__(JT)
-    jacobi_round_kernel(typename Elem<CPLX>::T* __restrict__ Wb, typename Elem<CPLX>::T* __restrict__ Zb,
-                        const gtn_svd_problem* __restrict__ probs, int round, double tol,
-                        double* __restrict__ offdiag, double* __restrict__ rn2,
-                        const double* __restrict__ fro2, const int64_t* __restrict__ rn_off) {
+__device__ __forceinline__ void jacobi_pair_step(typename Elem<CPLX>::T* __restrict__ Wb,
+                                                 typename Elem<CPLX>::T* __restrict__ Zb,
+                                                 const gtn_svd_problem* __restrict__ probs, int prob, int k,
+                                                 int round, double tol, double* __restrict__ offdiag,
+                                                 double* __restrict__ rn2, const double* __restrict__ fro2,
+                                                 const int64_t* __restrict__ rn_off) {
   using T = typename Elem<CPLX>::T;
-  const gtn_svd_problem pr = probs[blockIdx.y];
+  const gtn_svd_problem pr = probs[prob];
   const int p = pr.p, q = pr.q;
   const int P = (p + 1) & ~1;
   if (P < 2 || round >= P - 1) return;
-  const int k = blockIdx.x;
-  if (k >= P / 2) return;
+    if (k >= P / 2) return;
   int i, j;
   if (k == 0) { i = P - 1; j = round; }
   else { i = (round + k) % (P - 1); j = (round - k + (P - 1)) % (P - 1); }
@@ -95,10 +99,10 @@ __global__ void __launch_bounds__(JT)
   // s_i/s_0 > 1e-14 (reference __init__.py:3939-3941) discards anyway, and its overlap with a live
   // row perturbs that row by O(1e-15) relative -- so such pairs are never read again.  This is what
   // makes rank-deficient sectors (the normal case for the gauge tensors) cheap.
-  double* rn = rn2 + rn_off[blockIdx.y];
+  double* rn = rn2 + rn_off[prob];
   {
     const double as = rn[i], bs = rn[j];
-    const double dead = 4e-30 * fro2[blockIdx.y];      // fro2[] holds max_i |row_i|^2 (monotone)
+    const double dead = 4e-30 * fro2[prob];      // fro2[] holds max_i |row_i|^2 (monotone)
     if (fmin(as, bs) <= dead) return;
   }
 
@@ -158,7 +162,7 @@ __global__ void __launch_bounds__(JT)
     if (denom > 0.0 && cabs > 0.0) {
       const double off = cabs / denom;
       if (off > tol) {
-        atomic_max_pos(offdiag + blockIdx.y, off);
+        atomic_max_pos(offdiag + prob, off);
         const double zeta = (B - A) / (2.0 * cabs);
         const double tt = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
         cs = 1.0 / sqrt(1.0 + tt * tt);
@@ -166,7 +170,7 @@ __global__ void __launch_bounds__(JT)
         phr = CR / cabs; phi = CI / cabs;
         act = 1.0;
         rn[i] = fmax(A - tt * cabs, 0.0); rn[j] = B + tt * cabs;
-        atomic_max_pos(const_cast<double*>(fro2) + blockIdx.y, fmax(rn[i], rn[j]));
+        atomic_max_pos(const_cast<double*>(fro2) + prob, fmax(rn[i], rn[j]));
       }
     }
     rotp[0] = cs; rotp[1] = sn; rotp[2] = phr; rotp[3] = phi; rotp[4] = act;
@@ -199,6 +203,53 @@ __global__ void __launch_bounds__(JT)
     rot(xv, yv, cs, sn, phr, phi);
     Elem<CPLX>::st(zx + e, xv);
     Elem<CPLX>::st(zy + e, yv);
+  }
+}
+
+template <bool CPLX>
+__global__ void __launch_bounds__(JT)
+    jacobi_round_kernel(typename Elem<CPLX>::T* __restrict__ Wb, typename Elem<CPLX>::T* __restrict__ Zb,
+                        const gtn_svd_problem* __restrict__ probs, int round, double tol,
+                        double* __restrict__ offdiag, double* __restrict__ rn2,
+                        const double* __restrict__ fro2, const int64_t* __restrict__ rn_off) {
+  jacobi_pair_step<CPLX>(Wb, Zb, probs, blockIdx.y, blockIdx.x, round, tol, offdiag, rn2, fro2, rn_off);
+}
+
+// Persistent variant for small problems (all CTAs co-resident, cooperative launch): the whole
+// sweep loop runs inside ONE kernel with grid-wide barriers between rounds, and convergence is
+// decided on the device -- no per-round launches and no per-sweep host round trip.  Used for the
+// l x q projected matrices of the truncated path (l <= 80 rows).
+template <bool CPLX>
+__global__ void __launch_bounds__(JT)
+    jacobi_persistent_kernel(typename Elem<CPLX>::T* __restrict__ Wb, typename Elem<CPLX>::T* __restrict__ Zb,
+                             const gtn_svd_problem* __restrict__ probs, int nprob, int max_p, double tol,
+                             double* __restrict__ offdiag2, double* __restrict__ rn2,
+                             const double* __restrict__ fro2, const int64_t* __restrict__ rn_off,
+                             int max_sweeps, int32_t* __restrict__ sweeps_out) {
+  cg::grid_group grid = cg::this_grid();
+  const int P = (max_p + 1) & ~1;
+  const int prob = blockIdx.y, k = blockIdx.x;
+  int sweep = 0;
+  for (; sweep < max_sweeps; ++sweep) {
+    double* off = offdiag2 + (sweep & 1) * nprob;
+    double* off_next = offdiag2 + ((sweep + 1) & 1) * nprob;
+    for (int round = 0; round < P - 1; ++round) {
+      jacobi_pair_step<CPLX>(Wb, Zb, probs, prob, k, round, tol, off, rn2, fro2, rn_off);
+      __threadfence();
+      grid.sync();
+      if (round == 0 && k == 0 && threadIdx.x == 0) off_next[prob] = 0.0;
+    }
+    // converged when no pair of any problem rotated in this sweep
+    double m = 0.0;
+    for (int b = 0; b < nprob; ++b) m = fmax(m, off[b]);
+    if (m == 0.0) { ++sweep; break; }
+  }
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+    sweeps_out[0] = sweep;
+    double m = 0.0;
+    const double* off = offdiag2 + ((sweep - 1) & 1) * nprob;
+    for (int b = 0; b < nprob; ++b) m = fmax(m, off[b]);
+    sweeps_out[1] = (m == 0.0) ? 1 : 0;
   }
 }
 
@@ -350,6 +401,32 @@ extern "C" int gtn_jacobi_sweep(void* W, void* Z, int dtype, const gtn_svd_probl
       return GTN_ERR_BAD_ARG;
   }
   return (int)cudaGetLastError();
+}
+
+extern "C" int gtn_jacobi_persistent(void* W, void* Z, int dtype, const gtn_svd_problem* probs_dev,
+                                     int nprob, int max_p, double tol, double* offdiag2_dev,
+                                     double* rownorm2_dev, const double* fro2_dev,
+                                     const int64_t* rn_off_dev, int max_sweeps, int32_t* sweeps_dev,
+                                     void* stream) {
+  if (nprob <= 0 || max_p < 2) return GTN_ERR_UNSUPPORTED;
+  const int P = (max_p + 1) & ~1;
+  dim3 grid(P / 2, nprob), block(JT);
+  cudaStream_t s = (cudaStream_t)stream;
+  const void* fn = dtype == GTN_C128 ? (const void*)jacobi_persistent_kernel<true>
+                                     : (const void*)jacobi_persistent_kernel<false>;
+  if (dtype != GTN_C128 && dtype != GTN_F64) return GTN_ERR_BAD_ARG;
+  int dev = 0, sms = 0, per_sm = 0, coop = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (dtype == GTN_C128) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jacobi_persistent_kernel<true>, JT, 0);
+  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jacobi_persistent_kernel<false>, JT, 0);
+  if (!coop || (long long)grid.x * grid.y > (long long)per_sm * sms) return GTN_ERR_UNSUPPORTED;
+  cudaMemsetAsync(offdiag2_dev, 0, sizeof(double) * 2 * nprob, s);
+  void* args[] = {&W, &Z, (void*)&probs_dev, &nprob, &max_p, &tol, &offdiag2_dev, &rownorm2_dev,
+                  (void*)&fro2_dev, (void*)&rn_off_dev, &max_sweeps, &sweeps_dev};
+  cudaError_t e = cudaLaunchCooperativeKernel(fn, grid, block, args, 0, s);
+  return (int)e;
 }
 
 extern "C" int gtn_jacobi_finish(const void* W, const void* Z, void* U_out, void* Vh_out,

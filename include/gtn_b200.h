@@ -152,6 +152,15 @@ int gtn_jacobi_init(const void* W, void* Z, int dtype, const gtn_svd_problem* pr
 int gtn_jacobi_sweep(void* W, void* Z, int dtype, const gtn_svd_problem* probs_dev, int nprob,
                      int max_p, int max_q, double tol, double* offdiag_dev, double* rownorm2_dev,
                      const double* fro2_dev, const int64_t* rn_off_dev, void* stream);
+/* Whole sweep loop in ONE cooperative launch (grid-wide barriers between rounds, convergence decided on
+ * the device) for batches whose (max_p/2 x nprob) CTAs are all co-resident; returns
+ * GTN_ERR_UNSUPPORTED otherwise (use gtn_jacobi_sweep).  offdiag2_dev: double[2*nprob] scratch,
+ * sweeps_dev: int32[2] = {sweeps executed, converged flag}. */
+int gtn_jacobi_persistent(void* W, void* Z, int dtype, const gtn_svd_problem* probs_dev, int nprob,
+                          int max_p, double tol, double* offdiag2_dev, double* rownorm2_dev,
+                          const double* fro2_dev, const int64_t* rn_off_dev, int max_sweeps,
+                          int32_t* sweeps_dev, void* stream);
+
 /* s_out: double[sum p_b] at offsets s_off_b (descending); U_out (p x p row-major) at u_off;
  * Vh_out: rows of W normalised and permuted, at w_off.  order_dev: int32 [sum p_b] receives the
  * permutation; norm_scratch_dev: double [sum p_b] scratch. */

@@ -23,11 +23,9 @@ if which in ("all", "gemm"):
         c = E.gemm(a.view(-1), b.view(-1), N, N, N)
     torch.cuda.synchronize()
 if which in ("all", "trg"):
-    import gtn_oracle as O
-    rng = np.random.RandomState(0)
-    T = O.random_dense((8, 8, 8, 8), (1, 1, -1, -1), dtype=complex, rng=rng)
-    X = gtn.dense(T.data, statistics=T.statistics).toblock()
-    for _ in range(3):
+    g = gtn.gauge2d
+    X = g.zcap(g.load_initial_tensor()).toblock()      # the bench workload: Z2 site tensor, chi = 32
+    for _ in range(5):
         X, n = gtn.gauge2d.trg(X, 32)
     torch.cuda.synchronize()
     print("Tnorm", n)
