@@ -871,6 +871,7 @@ def _whiten(ws, hG, hT, rel_thr=1e-13):
 
 WHITEN = "chol"            # "chol": pivoted Cholesky kernel (default); "eigh": Jacobi eigen-solver kernel
 _trunc_iters_hint = {}
+_trunc_fail = {}
 
 
 def truncated_svd_batch(mats, ks, robust=False):
@@ -893,6 +894,13 @@ def truncated_svd_batch(mats, ks, robust=False):
     P_ = [m.shape[0] for m in mats]
     Q_ = [m.shape[1] for m in mats]
     L_ = [min(p, q, 2 * k + 8, 80) for p, q, k in zip(P_, Q_, ks)]
+    key = (tuple(P_), tuple(Q_), tuple(ks), str(dt))
+    fails = _trunc_fail.get(key, 0)
+    if fails >= 2 and not robust:
+        # this shape keeps failing the certificate (flat spectrum): go straight to the full SVD, but
+        # re-try every 16th call in case the spectrum has changed
+        _trunc_fail[key] = fails + 1 if fails < 17 else 1
+        return None
     ws = _WS(dt, dev)
     hW = [ws.add(p, q) for p, q in zip(P_, Q_)]
     hWh = [ws.add(q, p) for p, q in zip(P_, Q_)]
@@ -940,7 +948,7 @@ def truncated_svd_batch(mats, ks, robust=False):
             _ws_gemm(ws, list(zip(hT2, cur, out)))
             cur = out
 
-    key = (tuple(P_), tuple(Q_), tuple(ks), str(dt))
+    prev_worst = None
     start_it = max(0, _trunc_iters_hint.get(key, 0) - 1) if not robust else 0
     _ws_gemm(ws, list(zip(hG, hWh, hYh)))
     orth(hYh, hQh, "p", 2 if start_it == 0 else 1)
@@ -978,11 +986,14 @@ def truncated_svd_batch(mats, ks, robust=False):
         res = np.sqrt(res2.cpu().numpy())
         kept_host = None if (robust or dropped[0] is None) else dropped[0].cpu().numpy()
         ok, o = True, 0
+        worst = 0.0
         for b in range(nb):
             s = svals[b]
             s0 = s[0] if len(s) else 0.0
             nnz = int(np.sum(np.abs(s / (abs(s0) + 1e-14)) > 1e-14)) if len(s) else 0
             kk = min(ks[b], nnz)
+            if kk > 0:
+                worst = max(worst, float(np.max(res[o: o + kk])) / max(s0, 1e-300))
             if kk > 0 and np.max(res[o: o + kk]) > TRUNC_TOL * s0:
                 ok = False
             if nnz < ks[b] and kept_host is not None and kept_host[b] < L_[b] and nnz >= kept_host[b]:
@@ -992,11 +1003,17 @@ def truncated_svd_batch(mats, ks, robust=False):
                 return None
             o += L_[b]
         truncated_svd_batch.last_iters = it
+        if not ok and prev_worst is not None and worst > 0.25 * prev_worst and it >= 2:
+            # the subspace iteration has stalled (flat spectrum at the cut): stop wasting GEMMs
+            _trunc_fail[key] = _trunc_fail.get(key, 0) + 1
+            return None
+        prev_worst = worst
         if ok:
             _trunc_iters_hint[key] = it
+            _trunc_fail[key] = 0
             _ws_ctranspose(ws, list(zip(hUh, hU)))
             return [(ws.view(hU[b]), svals[b], ws.view(hVk[b])) for b in range(nb)]
-    _trunc_iters_hint[key] = TRUNC_MAX_ITERS
+    _trunc_fail[key] = _trunc_fail.get(key, 0) + 1
     return None
 
 

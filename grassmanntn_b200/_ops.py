@@ -681,7 +681,7 @@ def decompose_many(items, cutoff, kind, rule):
                        [int(math.ceil(cutoff / 2)), int(math.floor(cutoff / 2))])
             else:
                 ks += [cutoff]
-        if all(k >= 1 and k + 8 <= 80 and 4 * min(2 * k + 8, 80) <= min(m.shape) for k, m in zip(ks, mats)):
+        if all(k >= 1 and 3 * k // 2 + 8 <= 80 and 4 * min(2 * k + 8, 80) <= min(m.shape) for k, m in zip(ks, mats)):
             usv = truncated_svd_batch(mats, ks)
             SVD_PATH_STATS["truncated" if usv is not None else "truncated_rejected"] += 1
     if usv is None:

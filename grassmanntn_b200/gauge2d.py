@@ -48,15 +48,23 @@ def logZ(T, boundary_conditions="periodic"):
     (reference gauge2d.py:1599-1615).  Like gauge2d_block.py:1608 the anti-periodic sign is NOT
     applied to block tensors."""
     if boundary_conditions == "anti-periodic" and not isinstance(T, gtn.block):
-        # (-1)^{p(J)} on leg J == switch_parity restricted to leg 1; as a Grassmann einsum this is
-        # the trace with the sign vector folded into the block signs
-        bt = T._get_bt().clone()
-        for p in bt.live():
-            if dict(zip(bt.faxes, p)).get(1, 0) == 1:
-                bt.buf[bt.off[p]: bt.off[p] + bt.block_size(p)].neg_()
-        T = gtn.dense._from_bt(bt, T.encoder)
+        T = _flip_leg_parity(T, 1)
     Z = gtn.einsum("IJIJ", T)
     return np.log(Z)
+
+
+def _flip_leg_parity(T, leg):
+    """(-1)^{p} on one leg (the anti-periodic boundary sign, reference gauge2d.py:1606-1611): a
+    block-constant sign, applied with the scale kernel to the odd blocks of that leg."""
+    from grassmanntn_b200 import _cabi, _engine
+    bt = T._get_bt().clone()
+    for p in bt.live():
+        if dict(zip(bt.faxes, p)).get(leg, 0) == 1:
+            v = bt.buf[bt.off[p]: bt.off[p] + bt.block_size(p)]
+            _cabi.check(_cabi.lib.gtn_scale(_engine._ptr(v), v.numel(), _engine.dtype_code(v.dtype), -1.0, 0.0,
+                                            _engine._stream()), "gtn_scale")
+            _cabi.count()
+    return gtn.dense._from_bt(bt, T.encoder)
 
 
 def trg(T, dcut=64, iternum=None, error_test=False):
@@ -138,6 +146,88 @@ def atrg2dx(T1, T2, dcut=64, intermediate_dcut=None, iternum=None, error_test=Fa
     T2 = T1 if same else _swap_xy(T2)
     out = atrg2dy(T1, T2, dcut, intermediate_dcut, iternum, error_test, alignment="x")
     return (_swap_xy(out[0]),) + tuple(out[1:])
+
+
+def hotrg3dz(T1, T2, dcut=64, intermediate_dcut=None, iternum=None, error_test=False):
+    """Flavour-direction HOTRG-type step merging two 6-leg site tensors (legs 5,6 bosonic)
+    (reference gauge2d.py:1891-2145).  Same contraction network as the reference: three
+    decompositions per input, Gram matrices of the XX / YY environments, isometries from the
+    truncated eigen-decompositions, then the final merge.  Returns (T, Tnorm[, err])."""
+    E = gtn.einsum
+    if intermediate_dcut is None:
+        intermediate_dcut = dcut
+    T1o, T2o = T1, T2
+
+    def split3(T):
+        T = E('i1 i2 i3 i4 mn-> i1 i3 mn i2 i4', T)
+        X, S, Y = T.svd('(i1 i3 m)(n i2 i4)', intermediate_dcut)
+        sq = gtn.sqrt(S)
+        X = E('i1 i3 m a,ab->i1 i3 b m', X, sq)
+        Y = E('ab,b n i2 i4->n a i2 i4', sq, Y)
+        X, S, Pm = X.svd('(i1 i3)(a m)', intermediate_dcut)
+        X = E('i1 i3 x, xy -> i1 i3 y', X, S)
+        Q, S, Y = Y.svd('(na)(i2 i4)', intermediate_dcut)
+        Y = E('xy, y i2 i4 -> x i2 i4', S, Y)
+        return X, Pm, Q, Y
+
+    same = T1 is T2
+    X1, P1, Q1, Y1 = split3(T1)
+    X2, P2, Q2, Y2 = (X1, P1, Q1, Y1) if same else split3(T2)
+
+    def isometry(A1, A2, first, chain, h1, g1, h2, g2):
+        AA = E(first, A1, A2)
+        for sub in chain:
+            AA = E(sub, AA)
+        cA = AA.hconjugate(h1)
+        Ma = E(g1, cA, AA)
+        Ua, Sa, _ = Ma.eig('(I J)(i j)', dcut)
+        cB = AA.hconjugate(h2)
+        Mb = E(g2, AA, cB)
+        Ub, Sb, _ = Mb.eig('(I J)(i j)', dcut)
+        return AA, (Ua if Sa.shape[0] < Sb.shape[0] else Ub)
+
+    XX, Ux = isometry(X1, X2, 'i1 i3 a, j1 j3 b -> i1 i3 ab j1 j3',
+                      ['i1 i3 ab j1 j3 -> i1 i3 ab j3 j1', 'i1 i3 ab j3 j1 -> i1 i3 j3 ab j1',
+                       'i1 i3 j3 ab j1 -> i3 j3 i1 ab j1', 'i3 j3 i1 ab j1 -> i3 j3 ab i1 j1'],
+                      '(i3 j3 ab)(i1 j1)', ' I1 J1 i3 j3 ab, i3 j3 ab i1 j1 -> I1 J1 i1 j1',
+                      '(i3 j3)(ab i1 j1)', ' I3 J3 ab i1 j1, ab i1 j1 i3 j3  -> I3 J3 i3 j3')
+    cUx = Ux.hconjugate('ij|a')
+    XX = E('i3 j3 ab i1 j1 -> j3 i3 ab i1 j1', XX)
+    XX = E('j3 i3 ab i1 j1 -> j3 i3 ab j1 i1', XX)
+    Xp = E('s i3 j3,j3 i3 kl j1 i1 -> s kl j1 i1', cUx, XX)
+    Xp = E('s kl j1 i1, i1 j1 t -> s kl t', Xp, Ux)
+    Xp = E('s kl t -> t s kl', Xp)
+    Xp = E('t s kl , kam -> t s al m', Xp, P1)
+    Xp = E('t s al m , lbm -> t s ab m', Xp, P2)
+
+    YY, Uy = isometry(Y2, Y1, 'b j2 j4, a i2 i4 -> j2 j4 ba i2 i4',
+                      ['j2 j4 ba i2 i4 -> j2 j4 i4 ba i2', 'j2 j4 i4 ba i2 -> j4 i4 j2 ba i2',
+                       'j4 i4 j2 ba i2 -> j4 i4 ba i2 j2', 'j4 i4 ba i2 j2 -> i4 j4 ba i2 j2'],
+                      '(i4 j4 ba)(i2 j2)', ' I2 J2 i4 j4 ba, i4 j4 ba i2 j2 -> I2 J2 i2 j2',
+                      '(i4 j4)(ba i2 j2)', ' I4 J4 ba i2 j2, ba i2 j2 i4 j4  -> I4 J4 i4 j4')
+    cUy = Uy.hconjugate('ij|a')
+    YY = E('i4 j4 b a i2 j2 -> j4 i4 b a i2 j2', YY)
+    YY = E('j4 i4 b a i2 j2 -> j4 i4 b a j2 i2', YY)
+    Yp = E('s i4 j4,j4 i4 lk j2 i2 -> s lk j2 i2', cUy, YY)
+    Yp = E('s lk j2 i2, i2 j2 t -> s lk t', Yp, Uy)
+    Yp = E('s lk t -> lk t s', Yp)
+    Yp = E('nak, lk t s -> n la t s', Q1, Yp)
+    Yp = E('nbl, n la t s -> n ba t s', Q2, Yp)
+    T = E(' t1 t3 kl m, n lk t2 t4 -> t1 t2 t3 t4 mn ', Xp, Yp)
+    err = None
+    if error_test:
+        Z1 = E('IJIJmn,KLKLmn->mn', T1o, T2o)
+        Z2 = E('IJIJmn->mn', T)
+        err = (Z1 - Z2).norm / Z1.norm
+    T, Tnorm = _normalised(T)
+    return (T, Tnorm, err) if error_test else (T, Tnorm)
+
+
+def logZhotrg3dz(T1, T2, boundary_conditions="periodic"):
+    """reference gauge2d.py:1617-1641"""
+    if boundary_conditions == "anti-periodic" and not isinstance(T1, gtn.block):
+        T1, T2 = _flip_leg_parity(T1, 1), _flip_leg_parity(T2, 1)
+    return np.log(gtn.einsum('IJIJmn,KLKLmn', T1, T2))
 
 
 def coarse_grain(T, cgsteps=5, dcut=32, method="atrg", boundary_conditions="anti-periodic", error_test=False):

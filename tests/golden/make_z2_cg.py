@@ -20,7 +20,7 @@ CONFIGS = {
     "dense_trg_chi16": ("dense", "trg", 16, 2),
     "dense_atrg_chi8": ("dense", "atrg", 8, 3),
 }
-want = sys.argv[1:] or list(CONFIGS)
+want = [w for w in sys.argv[1:] if w in CONFIGS] or ([] if sys.argv[1:] else list(CONFIGS))
 out_path = os.path.join(HERE, "z2_cg.npz")
 out = dict(np.load(out_path)) if os.path.exists(out_path) else {}
 bc = "anti-periodic"
@@ -48,3 +48,21 @@ with threadpool_limits(limits=1):
             print(name, i, Tn, err, F, shp, "%.1f s" % (time.time() - t0), flush=True)
         out[name] = np.array(rec, dtype=float)
         np.savez_compressed(out_path, **out)
+
+# ---- flavour coarse-graining (example.py:144-154 with --Nf 2): hotrg3dz(T,T,Zcut) -> zcap -> trg
+if not sys.argv[1:] or "hotrg" in sys.argv[1:]:
+    with threadpool_limits(limits=1):
+        for cut in (8, 16):
+            T, Tn, err = gtn.gauge2d.hotrg3dz(T0.copy(), T0.copy(), cut, iternum=0, error_test=True)
+            logNorm = np.log(Tn)
+            Tc = gtn.gauge2d.zcap(T)
+            F = gtn.gauge2d.logZ(Tc.copy(), bc) + logNorm
+            rec = [[Tn, err, F.real, F.imag, T.shape[0], T.shape[1]]]
+            for i in range(2):
+                Tc, Tn2, err2 = gtn.gauge2d.trg(Tc, cut, iternum=i, error_test=True)
+                logNorm = 2 * logNorm + np.log(Tn2)
+                F = (gtn.gauge2d.logZ(Tc.copy(), bc) + logNorm) / 2 ** (i + 1)
+                rec.append([Tn2, err2, F.real, F.imag, Tc.shape[0], Tc.shape[1]])
+            out["dense_hotrg_chi%d" % cut] = np.array(rec, dtype=float)
+            print("hotrg", cut, rec, flush=True)
+            np.savez_compressed(out_path, **out)
