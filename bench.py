@@ -252,6 +252,9 @@ def main():
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     t_dev, t_e2e = tt.tolist()
+    sharded = None
+    if world > 1:
+        sharded = sharded_contraction(gtn, torch, dist, dev, 128 if not args.no_micro else 64)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -270,7 +273,7 @@ def main():
     shares = {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
                   "share": v["ms"] / tot_ms if tot_ms else None} for k, v in prof.items()}
     from grassmanntn_b200 import _ops
-    extra = {"kernel_shares": shares, "jacobi_sweeps_last": E.batched_svd.last_sweeps,
+    extra = {"sharded_contraction": sharded, "kernel_shares": shares, "jacobi_sweeps_last": E.batched_svd.last_sweeps,
              "svd_paths": dict(_ops.SVD_PATH_STATS), "trunc_refinements_last": E.truncated_svd_batch.last_iters}
     if not args.no_micro:
         extra["microbench"] = microbench(gtn, E, torch, dev, args, hbm_peak)
@@ -294,6 +297,51 @@ def main():
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def sharded_contraction(gtn, torch, dist, dev, D):
+    """strong scaling of the TRG main contraction 'lxzk,jzxi->ijkl' at D = chi: output row tiles of the
+    8 parity-block GEMMs sharded over the ranks, blocks completed with in-place NCCL all-gathers
+    (grassmanntn_b200/parallel.py).  Device time, max over ranks."""
+    from grassmanntn_b200 import parallel
+    half = D // 2
+
+    def even_block(stats, seed):
+        gen = torch.Generator(device="cpu")
+        gen.manual_seed(seed)
+        b = gtn.zero_block_eo((half,) * 4, (half,) * 4, stats, dtype=complex)
+        bt = b._bt
+        for p_ in bt.patterns():
+            if sum(p_) % 2 == 0:
+                v = bt.block_view(p_)
+                v.copy_(torch.view_as_complex(torch.rand(tuple(v.shape) + (2,), generator=gen, dtype=torch.float64)).to(dev))
+            else:
+                bt.zero.add(p_)
+        return b
+    VV, UU = even_block((1, 1, -1, 1), 1), even_block((-1, 1, -1, 1), 2)
+
+    def timeit(n):
+        torch.cuda.synchronize()
+        dist.barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(n):
+            gtn.einsum('lxzk,jzxi->ijkl', VV, UU)
+        e.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([s.elapsed_time(e) / n], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    parallel.disable()
+    timeit(1)
+    ms1 = timeit(3)
+    parallel.enable(min_flops=0.0)
+    timeit(1)
+    msN = timeit(3)
+    parallel.disable()
+    fl = 2.0 * D ** 6
+    return {"D": D, "ranks": dist.get_world_size(), "ms_one_gpu": ms1, "ms_sharded": msN, "speedup": ms1 / msN,
+            "TFLOPs_sharded_aggregate": fl / (msN * 1e-3) / 1e12, "scaling": "strong"}
 
 
 def microbench(gtn, E, torch, dev, args, hbm_peak):

@@ -996,6 +996,15 @@ def truncated_svd_batch(mats, ks, robust=False):
                 worst = max(worst, float(np.max(res[o: o + kk])) / max(s0, 1e-300))
             if kk > 0 and np.max(res[o: o + kk]) > TRUNC_TOL * s0:
                 ok = False
+            if 0 < kk < len(s):
+                # the accepted triplets must also be the LARGEST ones: a Ritz pair j > kk with residual
+                # r_j stands for an exact singular value within r_j of it, so none of them may reach
+                # above the smallest accepted value (a direction that is still poorly represented in
+                # the subspace shows up here as a low Ritz value with a large residual)
+                hi = s[kk:] + res[o + kk: o + len(s)]
+                if np.max(hi) > s[kk - 1] + max(TRUNC_TOL * s0, res[o + kk - 1]):
+                    ok = False
+                    worst = max(worst, float(np.max(hi) - s[kk - 1]) / max(s0, 1e-300))
             if nnz < ks[b] and kept_host is not None and kept_host[b] < L_[b] and nnz >= kept_host[b]:
                 # fewer triplets than requested AND the Gram whitening could not resolve every direction:
                 # a small-but-valid singular direction may have been dropped -> do not trust the count

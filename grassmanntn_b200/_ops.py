@@ -16,6 +16,7 @@ import numpy as np
 import torch
 
 from . import _planner as P
+from . import parallel
 from ._engine import (BT, FERMI, GemmPlan, GroupLayout, group_layout, PermutePlan, _cached, _ptr, _row_strides, _stream,
                       batched_svd, truncated_svd_batch, bt_force_standard, bt_switch_format, build_job, dtype_code, gemm, lin_leg,
                       require_cuda, sigma_bits)
@@ -348,6 +349,7 @@ def _plan_pair(inputs, output, ops, prog):
                                bsa=Mtot * Ktot, bsb=Ktot * Ntot, bsc=m * n, alpha=-1.0 if e else 1.0))
             acc += Btot * m * n
     plan = GemmPlan(groups, A.dtype)
+    shard_cache = {}
     res_off = dict(res.off)
     res_meta = (res.stats, res.e, res.o)
     tmp = "".join(tmp_labels)
@@ -366,6 +368,17 @@ def _plan_pair(inputs, output, ops, prog):
         r.buf = torch.empty(max(acc, 1), dtype=A_.dtype, device=A_.buf.device)
         if Ktot == 0:
             r.buf.zero_()
+        elif (parallel.active() and parallel._state["gemm"] and Btot == 1
+              and plan.flops >= parallel._state["min_flops"]):
+            # output-tile sharding: this rank computes its row range of every output block, then the
+            # blocks are completed with one in-place all-gather each (grassmanntn_b200/parallel.py)
+            key = (parallel.rank(), parallel.world())
+            if key not in shard_cache:
+                sg, pieces = parallel.shard_groups(groups, key[0], key[1])
+                shard_cache[key] = (GemmPlan([g for g in sg if g["m"] > 0], A_.dtype), pieces)
+            splan, pieces = shard_cache[key]
+            splan.run(bufL, bufR, r.buf)
+            parallel.gather_blocks(r.buf, pieces)
         else:
             plan.run(bufL, bufR, r.buf)
         if output is None:
@@ -671,28 +684,64 @@ def decompose_many(items, cutoff, kind, rule):
     run (the two SVDs of a TRG step share their sweeps)."""
     ctxs = [_decompose_prepare(bt, nl, kind) for bt, nl in items]
     mats = [m for c in ctxs for m in c["mats"]]
-    usv = None
-    if cutoff is not None and kind == "svd" and TRUNCATED_SVD:
-        # how many triplets per sector can survive the rank rule (same formulas as _decompose_finish)
-        ks = []
+    if parallel.active():
+        # always through the owner/broadcast path in multi-GPU mode: the replicated operands of the
+        # sharded contractions must be bit-identical on every rank (SVD gauges are not unique)
+        usv = _svd_distributed(mats, ctxs, cutoff, kind, rule)
+        outs, k = [], 0
         for c in ctxs:
-            if len(c["sectors"]) == 2:
-                ks += ([int(cutoff / 2)] * 2 if rule == "dense" else
-                       [int(math.ceil(cutoff / 2)), int(math.floor(cutoff / 2))])
-            else:
-                ks += [cutoff]
-        if all(k >= 1 and 3 * k // 2 + 8 <= 80 and 4 * min(2 * k + 8, 80) <= min(m.shape) for k, m in zip(ks, mats)):
-            usv = truncated_svd_batch(mats, ks)
-            SVD_PATH_STATS["truncated" if usv is not None else "truncated_rejected"] += 1
-    if usv is None:
-        usv = batched_svd(mats)
-        SVD_PATH_STATS["full"] += 1
+            n = len(c["mats"])
+            outs.append(_decompose_finish(c, usv[k:k + n], cutoff, kind, rule))
+            k += n
+        return outs
+    usv = _svd_local(mats, ctxs, cutoff, kind, rule)
     outs, k = [], 0
     for c in ctxs:
         n = len(c["mats"])
         outs.append(_decompose_finish(c, usv[k:k + n], cutoff, kind, rule))
         k += n
     return outs
+
+
+def _sector_cuts(ctxs, cutoff, rule):
+    ks = []
+    for c in ctxs:
+        if len(c["sectors"]) == 2:
+            ks += ([int(cutoff / 2)] * 2 if rule == "dense" else
+                   [int(math.ceil(cutoff / 2)), int(math.floor(cutoff / 2))])
+        else:
+            ks += [cutoff]
+    return ks
+
+
+def _svd_distributed(mats, ctxs, cutoff, kind, rule):
+    """sector problems are independent: problem i is solved by rank i % W, the isometries are
+    broadcast from their owners"""
+    w, r = parallel.world(), parallel.rank()
+    ks = _sector_cuts(ctxs, cutoff, rule) if cutoff is not None else [None] * len(mats)
+    mine = [i for i in range(len(mats)) if i % w == r]
+    res = {}
+    if mine:
+        sub = _svd_core([mats[i] for i in mine], [ks[i] for i in mine], cutoff, kind)
+        res = {i: sub[j] for j, i in enumerate(mine)}
+    return parallel.broadcast_usv(res, len(mats), mats[0].device, mats[0].dtype)
+
+
+def _svd_local(mats, ctxs, cutoff, kind, rule):
+    ks = _sector_cuts(ctxs, cutoff, rule) if cutoff is not None else [None] * len(mats)
+    return _svd_core(mats, ks, cutoff, kind)
+
+
+def _svd_core(mats, ks, cutoff, kind):
+    usv = None
+    if cutoff is not None and kind == "svd" and TRUNCATED_SVD:
+        if all(k >= 1 and 3 * k // 2 + 8 <= 80 and 4 * min(2 * k + 8, 80) <= min(m.shape) for k, m in zip(ks, mats)):
+            usv = truncated_svd_batch(mats, ks)
+            SVD_PATH_STATS["truncated" if usv is not None else "truncated_rejected"] += 1
+    if usv is None:
+        usv = batched_svd(mats)
+        SVD_PATH_STATS["full"] += 1
+    return usv
 
 
 def decompose_bt(bt, nl, cutoff, kind, rule):
