@@ -268,15 +268,22 @@ def main():
     achieved = (d["bytes"] / max(d["launches"], 1)) / (per_launch_ms * 1e-3) / 1e9 if d["bytes"] else 0.0
     roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "note": "at chi=32 every kernel of the step works on L2-resident data (the whole tensor is 16 MiB) and "
+                        "is launch/latency bound; the HBM and FP64-tensor rooflines of the same kernels at "
+                        "chi>=64/128 are in extra.microbench",
                 "share_of_step": d["ms"] / tot_ms if tot_ms else None,
                 "avg_launch_us": per_launch_ms * 1e3, "launches_per_step": d["launches"] / args.steps}
     shares = {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
-                  "share": v["ms"] / tot_ms if tot_ms else None} for k, v in prof.items()}
+                  "share": v["ms"] / tot_ms if tot_ms else None,
+                  "algorithmic_GBps": (v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] and v["bytes"] else None,
+                  "algorithmic_TFLOPs": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["ms"] and v["flops"] else None}
+              for k, v in prof.items()}
     from grassmanntn_b200 import _ops
     extra = {"sharded_contraction": sharded, "kernel_shares": shares, "jacobi_sweeps_last": E.batched_svd.last_sweeps,
              "svd_paths": dict(_ops.SVD_PATH_STATS), "trunc_refinements_last": E.truncated_svd_batch.last_iters}
     if not args.no_micro:
         extra["microbench"] = microbench(gtn, E, torch, dev, args, hbm_peak)
+        extra["other_workloads"] = other_workloads(gtn, torch, data, stats, args)
 
     cpu = None
     if world == 1:
@@ -297,6 +304,47 @@ def main():
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def other_workloads(gtn, torch, data, stats, args):
+    """steps/s of the other coarse-graining drivers on the same Z2 tensor (not part of `value`):
+    ATRG (example.py's default) in block and dense format, TRG in dense format, and TRG on a random
+    Grassmann-even tensor (flat spectrum: the truncated SVD is rejected, full Jacobi SVD runs)."""
+    import gtn_oracle as O
+    g = gtn.gauge2d
+    out = {}
+
+    def timed(fn, T, n=5, warm=2):
+        X = T
+        for _ in range(warm):
+            X = fn(X)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        X = T
+        for _ in range(n):
+            X = fn(X)
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / n * 1e3
+
+    Td = g.zcap(gtn.dense(data, statistics=stats))
+    Tb = Td.toblock()
+    sat_b, sat_d = Tb, Td
+    for _ in range(2):
+        sat_b, _ = g.trg(sat_b, args.chi)
+        sat_d, _ = g.trg(sat_d, args.chi)
+    flip = [0]
+
+    def atrg(X):
+        flip[0] ^= 1
+        return (g.atrg2dx if flip[0] else g.atrg2dy)(X, X, args.chi)[0]
+    out["atrg_block_chi%d_ms" % args.chi] = timed(atrg, sat_b)
+    out["atrg_dense_chi%d_ms" % args.chi] = timed(atrg, sat_d)
+    out["trg_dense_chi%d_ms" % args.chi] = timed(lambda X: g.trg(X, args.chi)[0], sat_d)
+    rng = np.random.RandomState(3)
+    R = O.random_dense((16, 16, 16, 16), (1, 1, -1, -1), dtype=complex, rng=rng)
+    Rb = gtn.dense(R.data, statistics=R.statistics).toblock()
+    out["trg_block_random_D16_chi16_ms"] = timed(lambda X: g.trg(X, 16)[0], Rb, n=2, warm=1)
+    return out
 
 
 def sharded_contraction(gtn, torch, dist, dev, D):

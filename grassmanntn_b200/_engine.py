@@ -73,6 +73,9 @@ class prof_region:
             self.s.record()
         return self
 
+    def set_bytes(self, nbytes):
+        self.a = (self.a[0], self.a[1], nbytes, self.a[3])
+
     def __exit__(self, *exc):
         count(self.a[1])
         if PROF.enabled:
@@ -722,11 +725,13 @@ def batched_svd(mats):
         P = (maxp + 1) & ~1
         esz = W.element_size()
         rb = sum(2 * esz * (pr[2] * pr[3] + pr[2] * pr[2]) for pr in probs)
-        with prof_region("jacobi_persistent", 1, 0):
+        with prof_region("jacobi_persistent", 1, 0) as pr_:
             rc = lib.gtn_jacobi_persistent(_ptr(W), _ptr(Z), code, _ptr(pdev), nprob, maxp, JACOBI_TOL, _ptr(offd),
                                            _ptr(rn2), _ptr(fro2), _ptr(rn_off), JACOBI_MAX_SWEEPS, _ptr(sw), st)
+            swh = sw.cpu().tolist() if rc == 0 else [0, 0]
+            # algorithmic bytes: every row of W and Z read + written once per round
+            pr_.set_bytes(rb * (P - 1) * max(swh[0], 1))
         if rc == 0:
-            swh = sw.cpu().tolist()
             sweeps = swh[0]
             if not swh[1]:
                 raise _cabi.GtnError("Jacobi SVD did not converge in %d sweeps" % sweeps)
@@ -776,7 +781,7 @@ batched_svd.last_sweeps = 0
 #  truncated SVD: randomized subspace iteration (GEMM-bound) + small Jacobi + residual certificate
 # ------------------------------------------------------------------------------------------------
 TRUNC_TOL = 1e-11          # certificate: max_i ||W^H u_i - s_i v_i|| <= TRUNC_TOL * s_0
-TRUNC_MAX_ITERS = 8
+TRUNC_MAX_ITERS = 20
 _rand_cache = {}
 
 
@@ -869,6 +874,7 @@ def _whiten(ws, hG, hT, rel_thr=1e-13):
     return kept
 
 
+DEBUG_TRUNC = bool(int(__import__("os").environ.get("GTN_DEBUG_TRUNC", "0")))
 WHITEN = "chol"            # "chol": pivoted Cholesky kernel (default); "eigh": Jacobi eigen-solver kernel
 _trunc_iters_hint = {}
 _trunc_fail = {}
@@ -948,19 +954,19 @@ def truncated_svd_batch(mats, ks, robust=False):
             _ws_gemm(ws, list(zip(hT2, cur, out)))
             cur = out
 
-    prev_worst = None
+    prev_worst, prev_it, next_check = None, None, 0
     start_it = max(0, _trunc_iters_hint.get(key, 0) - 1) if not robust else 0
     _ws_gemm(ws, list(zip(hG, hWh, hYh)))
     orth(hYh, hQh, "p", 2 if start_it == 0 else 1)
     code = dtype_code(dt)
     for it in range(TRUNC_MAX_ITERS + 1):
         if it > 0:
-            last = it >= start_it
+            last = it >= start_it and it >= next_check
             _ws_gemm(ws, list(zip(hQh, hW, hZh)))
             orth(hZh, hPh, "q", 1)
             _ws_gemm(ws, list(zip(hPh, hWh, hYh)))
             orth(hYh, hQh, "p", 2 if last else 1)
-        if it < start_it:
+        if it < start_it or it < next_check:
             continue
         _ws_gemm(ws, list(zip(hQh, hW, hB)))
         usv = batched_svd([ws.view(h) for h in hB])
@@ -1012,11 +1018,23 @@ def truncated_svd_batch(mats, ks, robust=False):
                 return None
             o += L_[b]
         truncated_svd_batch.last_iters = it
-        if not ok and prev_worst is not None and worst > 0.25 * prev_worst and it >= 2:
-            # the subspace iteration has stalled (flat spectrum at the cut): stop wasting GEMMs
-            _trunc_fail[key] = _trunc_fail.get(key, 0) + 1
-            return None
-        prev_worst = worst
+        if DEBUG_TRUNC:
+            print("[trunc] it", it, "worst %.2e" % worst, "ok", ok, "shapes", list(zip(P_, Q_)), "k", ks, "L", L_,
+                  "s[k-2:k+3]/s0", [np.array2string(sv[max(0, k - 2):k + 3] / sv[0], precision=5) for sv, k in zip(svals, ks)], flush=True)
+        if not ok and prev_worst is not None and it >= 2:
+            rate = (worst / prev_worst) ** (1.0 / max(it - prev_it, 1)) if prev_worst > 0 else 1.0
+            if rate > 0.6:
+                # the subspace iteration has stalled (flat spectrum at the cut): stop wasting GEMMs
+                _trunc_fail[key] = _trunc_fail.get(key, 0) + 1
+                return None
+            # geometric convergence: skip the (Jacobi-SVD + residual) check until the predicted
+            # iteration, it costs more than the two GEMM + two whitening launches of an iteration
+            need = math.log(max(TRUNC_TOL * 0.3, 1e-300) / max(worst, 1e-300)) / math.log(max(rate, 1e-3))
+            next_check = it + max(1, min(int(math.ceil(need)), 6))
+            if next_check > TRUNC_MAX_ITERS:
+                _trunc_fail[key] = _trunc_fail.get(key, 0) + 1
+                return None
+        prev_worst, prev_it = worst, it
         if ok:
             _trunc_iters_hint[key] = it
             _trunc_fail[key] = 0
