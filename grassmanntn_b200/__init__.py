@@ -375,11 +375,10 @@ class dense:
         return block(self)
 
     def join_legs(self, string_inp, make_format="standard", intermediate_stat=None, save_memory=False):
-        raise NotImplementedError("grassmanntn_b200: dense.join_legs (user-level hybrid joins) is not part of the "
-                                  "accelerated hot path; svd/eig/hconjugate join internally")
+        return join_legs(self, string_inp, make_format, intermediate_stat, save_memory)
 
-    def split_legs(self, *a, **k):
-        raise NotImplementedError("grassmanntn_b200: dense.split_legs is not part of the accelerated hot path")
+    def split_legs(self, string_inp, final_stat, final_shape, intermediate_stat=None, save_memory=False):
+        return split_legs(self, string_inp, final_stat, final_shape, intermediate_stat, save_memory)
 
 
 # ================================================================================================
@@ -618,6 +617,136 @@ def random_block(effective_shape, statistics, format="standard", dtype=float, sk
 # ================================================================================================
 #  functions
 # ================================================================================================
+def _group_info(grouping_string, stats, shape):
+    """groups and their bosons-to-the-left ordering (reference get_group_info :3172-3248)"""
+    groups, loc = [], 0
+    for ind in _planner.parse_groups(grouping_string):
+        st = [stats[loc + k] for k in range(len(ind))]
+        sh = [shape[loc + k] for k in range(len(ind))]
+        ax = [loc + k for k in range(len(ind))]
+        loc += len(ind)
+        order = []
+        for k in range(len(ind)):
+            if st[k] in bose_type:
+                order.insert(0, k)
+            else:
+                order.append(k)
+        groups.append(dict(axes=ax, stats=st, shape=sh, order=order))
+    return groups
+
+
+def _joined_layout(groups, intermediate_stat):
+    """reference get_intermediate_info (:3277-3316)"""
+    new_shape, new_stats, final_shape, final_stats = [], [], [], []
+    for g, ist in zip(groups, intermediate_stat):
+        fd = bd = 1
+        fn = bn = 0
+        for s_, d_ in zip(g["stats"], g["shape"]):
+            if s_ in fermi_type:
+                fd *= d_
+                fn += 1
+            else:
+                bd *= d_
+                bn += 1
+        if bn:
+            new_shape.append(bd)
+            new_stats.append(0)
+        if fn:
+            new_shape.append(fd)
+            new_stats.append(ist)
+        final_shape.append(bd * fd)
+        final_stats.append(hybrid_symbol if (bn and fn) else ist)
+    return tuple(new_stats), tuple(new_shape), tuple(final_stats), tuple(final_shape)
+
+
+def join_legs(InpObj, string_inp, make_format="standard", intermediate_stat=None, save_memory=False):
+    """Join tensor legs (reference join_legs __init__.py:2947-3068): bosons to the left inside every
+    group with (-1)^p on the +1 legs that join into a -1 leg (one fused sign+permute launch),
+    reshape, optional switch to the matrix format, parity-preserving encoder, and a boson x fermion
+    merge into a hybrid '*' leg.  Always returns the parity-preserving encoder."""
+    string_inp = denumerate(string_inp.replace(" ", ""))
+    intermediate_stat = make_tuple(intermediate_stat)
+    obj = InpObj.force_format("standard").force_encoder("canonical")
+    groups = _group_info(string_inp, obj.statistics, obj.shape)
+    if sum(len(g["axes"]) for g in groups) != obj.ndim:
+        error("Error[join_legs]: The number of indices is not consistent with the object's shape.")
+    if len(groups) != len(intermediate_stat):
+        error("Error[get_grouping_sign_factors]: Inconsistent number of intermediate_stat and groupings!")
+    perm, alpha, sorted_stats = [], [], []
+    for g, ist in zip(groups, intermediate_stat):
+        for k in g["order"]:
+            perm.append(g["axes"][k])
+            sorted_stats.append(g["stats"][k])
+            if g["stats"][k] == 1 and ist == -1:
+                alpha.append(g["axes"][k])
+    data = _engine.dense_sign_permute(obj.data, perm, alpha)
+    new_stats, new_shape, final_stats, final_shape = _joined_layout(groups, intermediate_stat)
+    global skip_power_of_two_check
+    J = dense(data.reshape(new_shape), statistics=new_stats)
+    if make_format == "matrix":
+        J = J.switch_format()
+    J = J.switch_encoder()
+    out = dense()
+    out._data = J.data.reshape(final_shape)
+    out.statistics, out.format, out.encoder = final_stats, J.format, J.encoder
+    return out
+
+
+def split_legs(InpObj, string_inp, final_stat, final_shape, intermediate_stat=None, save_memory=False):
+    """Inverse of join_legs (reference split_legs __init__.py:3070-3170)."""
+    string_inp = denumerate(string_inp.replace(" ", ""))
+    intermediate_stat = make_tuple(intermediate_stat)
+    final_stat, final_shape = make_tuple(final_stat), make_tuple(final_shape)
+    this_format, this_encoder = InpObj.format, InpObj.encoder
+    groups = _group_info(string_inp, final_stat, final_shape)
+    new_stats, new_shape, _, _ = _joined_layout(groups, intermediate_stat)
+    J = dense(InpObj.data.reshape(new_shape), statistics=new_stats, encoder=this_encoder, format=this_format)
+    if this_encoder == "parity-preserving":
+        J = J.switch_encoder()
+    if this_format == "matrix":
+        J = J.switch_format()
+    sorted_axes, sorted_shape, alpha_sorted = [], [], []
+    for g, ist in zip(groups, intermediate_stat):
+        for k in g["order"]:
+            if g["stats"][k] == 1 and ist == -1:
+                alpha_sorted.append(len(sorted_axes))
+            sorted_axes.append(g["axes"][k])
+            sorted_shape.append(g["shape"][k])
+    inv = [sorted_axes.index(a) for a in range(len(sorted_axes))]
+    data = _engine.dense_sign_permute(J.data.reshape(sorted_shape), inv, alpha_sorted)
+    out = dense(data, statistics=final_stat, encoder=J.encoder, format=J.format)
+    if this_format == "matrix":
+        return out.switch_format()
+    if this_encoder == "parity-preserving":
+        out = out.switch_encoder()
+    return out
+
+
+# sign helpers of the reference's "Parity Calculation (internal tools)" section (__init__.py:1483-1604),
+# kept for API parity; the kernels never call them (the planner derives the same signs as one GF(2)
+# quadratic form, _planner.einsum_sign_program).
+def absolute_sign(object_set, parity):
+    odd = [x for x, p_ in zip(object_set, parity) if p_ % 2 == 1]
+    inv = sum(1 for a in range(len(odd)) for b in range(a + 1, len(odd)) if odd[a] > odd[b])
+    return -1 if inv % 2 else 1
+
+
+def relative_sign(string, parity):
+    before, after = string.split("->")
+    before = before.replace(",", "")
+    if len(before) != len(parity):
+        error("Error[relative_sign]: The number of input list and parity list are not consistent!")
+    keep = [(c, p_) for c, p_ in zip(before, parity) if before.count(c) == 1]
+    pmap = dict(keep)
+    order = {c: k for k, (c, _) in enumerate(keep)}
+    return absolute_sign([order[c] for c, _ in keep], [p_ for _, p_ in keep]) * \
+        absolute_sign([order[c] for c in after], [pmap[c] for c in after])
+
+
+def reordering(stringa, stringb, mylist):
+    return [mylist[stringa.index(b)] for b in stringb]
+
+
 def _wrap_like(bt, like, shape=None):
     if isinstance(like, block):
         return block._from_bt(bt, shape)

@@ -527,6 +527,35 @@ def bt_to_dense(bt, encoder="canonical"):
     return out
 
 
+def dense_sign_permute(data, perm, alpha_axes=()):
+    """out = transpose(data, perm) with (-1)^{popcount(i_a)} on the legs a in alpha_axes: the
+    bosons-to-the-left step of join_legs / split_legs (reference __init__.py:3003-3015, :3153-3157)
+    as ONE launch on a dense canonical tensor.  Here the parities are NOT block constants: the
+    kernel evaluates the sign per element from the popcount tables of the legs."""
+    shape = tuple(data.shape)
+    n = len(shape)
+    data = data.contiguous()
+    out_shape = tuple(shape[a] for a in perm)
+    out = torch.empty(out_shape, dtype=data.dtype, device=data.device)
+    if out.numel() == 0:
+        return out
+
+    def build():
+        in_st = _row_strides(shape)
+        ost = _row_strides(out_shape)
+        ost_of = {a: ost[k] for k, a in enumerate(perm)}
+        legs, alpha = [], []
+        for a in range(n):
+            i = np.arange(shape[a], dtype=np.int64)
+            par = (_popcount_vec(i) & 1).astype(np.uint32) if a in alpha_axes else None
+            legs.append(LegTab(shape[a], i * in_st[a], i * ost_of[a], p=par))
+            alpha.append(1 if a in alpha_axes else 0)
+        return PermutePlan([build_job(legs, alpha=alpha, in_order=list(range(n)), out_order=list(perm))])
+    plan = _cached(("dsp", shape, tuple(perm), tuple(sorted(alpha_axes)), str(data.dtype)), build)
+    plan.run(data.view(-1), out.view(-1))
+    return out
+
+
 # ---- in-place style elementwise sign passes (format switch) -----------------------------------
 def bt_switch_format(bt):
     """sigma on every conjugated (-1) leg: reference dense.switch_format (__init__.py:1011-1068) /
