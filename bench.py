@@ -344,7 +344,55 @@ def other_workloads(gtn, torch, data, stats, args):
     R = O.random_dense((16, 16, 16, 16), (1, 1, -1, -1), dtype=complex, rng=rng)
     Rb = gtn.dense(R.data, statistics=R.statistics).toblock()
     out["trg_block_random_D16_chi16_ms"] = timed(lambda X: g.trg(X, 16)[0], Rb, n=2, warm=1)
+    # flavour-direction HOTRG step (example.py --Nf 2): 6-leg tensors with bosonic legs, eig, hconjugate
+    T6 = gtn.dense(data, statistics=stats)
+    out["hotrg3dz_dense_Zcut%d_ms" % args.chi] = timed(lambda X: g.hotrg3dz(T6, T6, args.chi)[0], T6, n=2, warm=1)
+    out["einsum_sweep"] = einsum_sweep(gtn, torch, O)
     return out
+
+
+def einsum_sweep(gtn, torch, O):
+    """BASELINE.json configs[4]: synthetic Grassmann einsums, 4-8 leg complex128 tensors (seeded,
+    uniform [0,1) + i uniform [0,1), Grassmann-odd entries zeroed), sign-only and sign+contract.
+    GB/s = 2*N*16 B algorithmic; TFLOP/s = 8*m*n*k over the non-zero parity sectors.  The same
+    strings at 1/4 of the linear size are timed with the CPU oracle port for reference."""
+    from grassmanntn_b200 import _engine as E
+    cases = [
+        ("ijkl->jkli", [((64,) * 4, (1, 1, -1, -1))]),
+        ("ijkl->lkji", [((64,) * 4, (1, -1, 1, -1))]),
+        ("abcdef->fedcba", [((16,) * 6, (1, 1, 1, -1, -1, -1))]),
+        ("abcdefgh->hgfedcba", [((8,) * 8, (1, 1, 1, 1, -1, -1, -1, -1))]),
+        ("ijkl,klmn->ijmn", [((64,) * 4, (1, 1, 1, 1)), ((64,) * 4, (-1, -1, 1, 1))]),
+        ("abcdef,defghi->abcghi", [((16,) * 6, (1, 1, 1, 1, 1, 1)), ((16,) * 6, (-1, -1, -1, 1, 1, 1))]),
+        ("abcd,cdef,efgh->abgh", [((32,) * 4, (1, 1, 1, 1)), ((32,) * 4, (-1, -1, 1, 1)), ((32,) * 4, (-1, -1, 1, 1))]),
+        ("ijkl,klij", [((64,) * 4, (1, 1, 1, 1)), ((64,) * 4, (-1, -1, -1, -1))]),
+    ]
+    res = {}
+    for sub, ops in cases:
+        rng = np.random.RandomState(11)
+        objs = []
+        for shape, st in ops:
+            d = O.random_dense(shape, st, dtype=complex, rng=rng)
+            objs.append(gtn.dense(d.data, statistics=st).toblock())
+        for _ in range(2):
+            r = gtn.einsum(sub, *objs)
+        torch.cuda.synchronize()
+        E.PROF.start()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(5):
+            r = gtn.einsum(sub, *objs)
+        e.record()
+        torch.cuda.synchronize()
+        pr = E.PROF.stop()
+        ms = s.elapsed_time(e) / 5
+        ent = {"ms": ms}
+        if "sign_permute" in pr:
+            ent["permute_GBps"] = pr["sign_permute"]["bytes"] / (pr["sign_permute"]["ms"] * 1e-3) / 1e9
+        if "grouped_gemm" in pr and pr["grouped_gemm"]["flops"]:
+            ent["gemm_TFLOPs"] = pr["grouped_gemm"]["flops"] / (pr["grouped_gemm"]["ms"] * 1e-3) / 1e12
+        res[sub] = ent
+    return res
 
 
 def sharded_contraction(gtn, torch, dist, dev, D):

@@ -64,6 +64,7 @@ def _load():
         "gtn_small_chol_whiten": (i32, [vp, vp, i32, vp, vp, vp, i32, i32, dbl, vp, vp]),
         "gtn_sumsq": (i32, [vp, i64, i32, vp, i32, vp]),
         "gtn_rowsum": (i32, [vp, vp, i64, i64, i32, vp]),
+        "gtn_dot": (i32, [vp, vp, i64, i32, vp, vp, i32, vp]),
         "gtn_row_sumsq": (i32, [vp, vp, i64, i64, i32, vp]),
         "gtn_pow_rcond": (i32, [vp, i64, i32, dbl, dbl, vp]),
         "gtn_scale": (i32, [vp, i64, i32, dbl, dbl, vp]),

@@ -750,14 +750,14 @@ def batched_svd(mats):
     done = False
     if 2 <= maxp <= PERSISTENT_MAX_ROWS:
         # small problems: the whole sweep loop in one cooperative launch
-        sw = torch.zeros(2, dtype=torch.int32, device=dev)
+        sw = torch.zeros(4, dtype=torch.int32, device=dev)
         P = (maxp + 1) & ~1
         esz = W.element_size()
         rb = sum(2 * esz * (pr[2] * pr[3] + pr[2] * pr[2]) for pr in probs)
         with prof_region("jacobi_persistent", 1, 0) as pr_:
             rc = lib.gtn_jacobi_persistent(_ptr(W), _ptr(Z), code, _ptr(pdev), nprob, maxp, JACOBI_TOL, _ptr(offd),
                                            _ptr(rn2), _ptr(fro2), _ptr(rn_off), JACOBI_MAX_SWEEPS, _ptr(sw), st)
-            swh = sw.cpu().tolist() if rc == 0 else [0, 0]
+            swh = sw.cpu().tolist()[:2] if rc == 0 else [0, 0]
             # algorithmic bytes: every row of W and Z read + written once per round
             pr_.set_bytes(rb * (P - 1) * max(swh[0], 1))
         if rc == 0:

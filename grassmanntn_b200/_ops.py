@@ -21,6 +21,7 @@ from ._engine import (BT, FERMI, GemmPlan, GroupLayout, group_layout, PermutePla
                       batched_svd, truncated_svd_batch, bt_force_standard, bt_switch_format, build_job, dtype_code, gemm, lin_leg,
                       require_cuda, sigma_bits)
 from ._cabi import check, count, lib
+from ._engine import prof_region
 
 NUMER_CUTOFF = 1.0e-14      # reference __init__.py:30 (module global numer_cutoff)
 SVD_PATH_STATS = {"truncated": 0, "truncated_rejected": 0, "full": 0}
@@ -368,6 +369,16 @@ def _plan_pair(inputs, output, ops, prog):
         r.buf = torch.empty(max(acc, 1), dtype=A_.dtype, device=A_.buf.device)
         if Ktot == 0:
             r.buf.zero_()
+        elif Mtot == 1 and Ntot == 1 and Btot == 1 and len(groups) == 1:
+            # full contraction to a scalar: 1 x K x 1 is a dot product, not a GEMM
+            g0 = groups[0]
+            nparts = 1184
+            part = torch.empty(2 * nparts, dtype=torch.float64, device=A_.buf.device)
+            with prof_region("dot", 2, 2 * g0["k"] * bufL.element_size()):
+                check(lib.gtn_dot(_ptr(bufL[g0["a_off"]:]), _ptr(bufR[g0["b_off"]:]), g0["k"], dtype_code(A_.dtype),
+                                  _ptr(r.buf), _ptr(part), nparts, _stream()), "gtn_dot")
+            if g0["alpha"] < 0:
+                r.buf.neg_()
         elif (parallel.active() and parallel._state["gemm"] and Btot == 1
               and plan.flops >= parallel._state["min_flops"]):
             # output-tile sharding: this rank computes its row range of every output block, then the

@@ -80,6 +80,39 @@ __global__ void __launch_bounds__(RT) row_sumsq_kernel(const double* __restrict_
   if (threadIdx.x == 0) y[r] = a;
 }
 
+// out = sum_i a_i * b_i (no conjugation): the fully contracted Grassmann einsum ('ijkl,klij', the
+// trace checks of gauge2d.py:1738, :1856) after both operands have been packed with their signs.
+// Deterministic two-stage reduction: per-CTA partials, then one CTA.
+template <bool CPLX>
+__global__ void __launch_bounds__(RT) dot_partial_kernel(const double* __restrict__ a, const double* __restrict__ b,
+                                                         int64_t n, double* __restrict__ partial) {
+  double re = 0, im = 0;
+  const int64_t stride = int64_t(gridDim.x) * RT;
+  for (int64_t i = int64_t(blockIdx.x) * RT + threadIdx.x; i < n; i += stride) {
+    if (CPLX) {
+      const double2 x = __ldg(reinterpret_cast<const double2*>(a) + i);
+      const double2 y = __ldg(reinterpret_cast<const double2*>(b) + i);
+      re += x.x * y.x - x.y * y.y;
+      im += x.x * y.y + x.y * y.x;
+    } else {
+      re += __ldg(a + i) * __ldg(b + i);
+    }
+  }
+  re = block_sum(re);
+  if (CPLX) im = block_sum(im);
+  if (threadIdx.x == 0) { partial[2 * blockIdx.x] = re; partial[2 * blockIdx.x + 1] = im; }
+}
+
+template <bool CPLX>
+__global__ void __launch_bounds__(RT) dot_final_kernel(const double* __restrict__ partial, int nparts,
+                                                       double* __restrict__ out) {
+  double re = 0, im = 0;
+  for (int i = threadIdx.x; i < nparts; i += RT) { re += partial[2 * i]; im += partial[2 * i + 1]; }
+  re = block_sum(re);
+  im = block_sum(im);
+  if (threadIdx.x == 0) { out[0] = re; if (CPLX) out[1] = im; }
+}
+
 // complex power: principal branch of z^p, like numpy.power on complex128
 __device__ __forceinline__ void cpow(double& re, double& im, double p) {
   const double r = hypot(re, im);
@@ -177,6 +210,24 @@ extern "C" int gtn_row_sumsq(const void* x, double* y, int64_t rows, int64_t col
   if (dtype == GTN_C128) row_sumsq_kernel<true><<<(unsigned)rows, RT, 0, s>>>((const double*)x, y, rows, cols);
   else if (dtype == GTN_F64) row_sumsq_kernel<false><<<(unsigned)rows, RT, 0, s>>>((const double*)x, y, rows, cols);
   else return GTN_ERR_BAD_ARG;
+  return (int)cudaGetLastError();
+}
+
+extern "C" int gtn_dot(const void* a, const void* b, int64_t n, int dtype, void* out, double* partial_dev,
+                       int nparts, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (nparts < 1) return GTN_ERR_BAD_ARG;
+  int g = grid_for(n);
+  if (g > nparts) g = nparts;
+  if (dtype == GTN_C128) {
+    dot_partial_kernel<true><<<g, RT, 0, s>>>((const double*)a, (const double*)b, n, partial_dev);
+    dot_final_kernel<true><<<1, RT, 0, s>>>(partial_dev, g, (double*)out);
+  } else if (dtype == GTN_F64) {
+    dot_partial_kernel<false><<<g, RT, 0, s>>>((const double*)a, (const double*)b, n, partial_dev);
+    dot_final_kernel<false><<<1, RT, 0, s>>>(partial_dev, g, (double*)out);
+  } else {
+    return GTN_ERR_BAD_ARG;
+  }
   return (int)cudaGetLastError();
 }
 

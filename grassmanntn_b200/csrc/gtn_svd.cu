@@ -215,6 +215,21 @@ __global__ void __launch_bounds__(JT)
   jacobi_pair_step<CPLX>(Wb, Zb, probs, blockIdx.y, blockIdx.x, round, tol, offdiag, rn2, fro2, rn_off);
 }
 
+// grid-wide barrier on a monotonically increasing counter (all CTAs are co-resident: cooperative
+// launch).  About 3x cheaper than cooperative_groups::grid_group::sync() for the ~100-CTA grids used
+// here; the counter lives in global memory and is zeroed by the host wrapper.
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int nblocks, unsigned int& epoch) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int target = (++epoch) * nblocks;
+    atomicAdd(counter, 1u);
+    while (*reinterpret_cast<volatile unsigned int*>(counter) < target) { }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
 // Persistent variant for small problems (all CTAs co-resident, cooperative launch): the whole
 // sweep loop runs inside ONE kernel with grid-wide barriers between rounds, and convergence is
 // decided on the device -- no per-round launches and no per-sweep host round trip.  Used for the
@@ -225,23 +240,23 @@ __global__ void __launch_bounds__(JT)
                              const gtn_svd_problem* __restrict__ probs, int nprob, int max_p, double tol,
                              double* __restrict__ offdiag2, double* __restrict__ rn2,
                              const double* __restrict__ fro2, const int64_t* __restrict__ rn_off,
-                             int max_sweeps, int32_t* __restrict__ sweeps_out) {
-  cg::grid_group grid = cg::this_grid();
+                             int max_sweeps, int32_t* __restrict__ sweeps_out, unsigned int* __restrict__ bar) {
   const int P = (max_p + 1) & ~1;
   const int prob = blockIdx.y, k = blockIdx.x;
+  const unsigned int nblocks = gridDim.x * gridDim.y;
+  unsigned int epoch = 0;
   int sweep = 0;
   for (; sweep < max_sweeps; ++sweep) {
     double* off = offdiag2 + (sweep & 1) * nprob;
     double* off_next = offdiag2 + ((sweep + 1) & 1) * nprob;
     for (int round = 0; round < P - 1; ++round) {
       jacobi_pair_step<CPLX>(Wb, Zb, probs, prob, k, round, tol, off, rn2, fro2, rn_off);
-      __threadfence();
-      grid.sync();
+      grid_barrier(bar, nblocks, epoch);
       if (round == 0 && k == 0 && threadIdx.x == 0) off_next[prob] = 0.0;
     }
     // converged when no pair of any problem rotated in this sweep
     double m = 0.0;
-    for (int b = 0; b < nprob; ++b) m = fmax(m, off[b]);
+    for (int b = 0; b < nprob; ++b) m = fmax(m, *reinterpret_cast<volatile double*>(off + b));
     if (m == 0.0) { ++sweep; break; }
   }
   if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
@@ -423,8 +438,11 @@ extern "C" int gtn_jacobi_persistent(void* W, void* Z, int dtype, const gtn_svd_
   else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jacobi_persistent_kernel<false>, JT, 0);
   if (!coop || (long long)grid.x * grid.y > (long long)per_sm * sms) return GTN_ERR_UNSUPPORTED;
   cudaMemsetAsync(offdiag2_dev, 0, sizeof(double) * 2 * nprob, s);
+  // the barrier counter lives behind the two sweep counters in sweeps_dev (int32[4])
+  unsigned int* bar = reinterpret_cast<unsigned int*>(sweeps_dev) + 2;
+  cudaMemsetAsync(bar, 0, sizeof(unsigned int), s);
   void* args[] = {&W, &Z, (void*)&probs_dev, &nprob, &max_p, &tol, &offdiag2_dev, &rownorm2_dev,
-                  (void*)&fro2_dev, (void*)&rn_off_dev, &max_sweeps, &sweeps_dev};
+                  (void*)&fro2_dev, (void*)&rn_off_dev, &max_sweeps, &sweeps_dev, &bar};
   cudaError_t e = cudaLaunchCooperativeKernel(fn, grid, block, args, 0, s);
   return (int)e;
 }

@@ -155,7 +155,7 @@ int gtn_jacobi_sweep(void* W, void* Z, int dtype, const gtn_svd_problem* probs_d
 /* Whole sweep loop in ONE cooperative launch (grid-wide barriers between rounds, convergence decided on
  * the device) for batches whose (max_p/2 x nprob) CTAs are all co-resident; returns
  * GTN_ERR_UNSUPPORTED otherwise (use gtn_jacobi_sweep).  offdiag2_dev: double[2*nprob] scratch,
- * sweeps_dev: int32[2] = {sweeps executed, converged flag}. */
+ * sweeps_dev: int32[4] = {sweeps executed, converged flag, barrier counter, unused}. */
 int gtn_jacobi_persistent(void* W, void* Z, int dtype, const gtn_svd_problem* probs_dev, int nprob,
                           int max_p, double tol, double* offdiag2_dev, double* rownorm2_dev,
                           const double* fro2_dev, const int64_t* rn_off_dev, int max_sweeps,
@@ -202,6 +202,13 @@ int gtn_sumsq(const void* x, int64_t n, int dtype, double* out_dev, int zero_fir
  * 'IJIJ' -- the final reduction of oe.contract at __init__.py:2295 when nothing is left to
  * multiply).  y has `rows` elements of the same dtype. */
 int gtn_rowsum(const void* x, void* y, int64_t rows, int64_t cols, int dtype, void* stream);
+
+/* out = sum_i a_i * b_i (no conjugation; out has one element of `dtype`).  The fully contracted
+ * einsum ('ijkl,klij', 'IJIK,iKiJ': the trace-preservation checks of gauge2d.py:1738, :1856) after
+ * the operands were packed with their signs -- the degenerate 1 x K x 1 case of oe.contract
+ * (__init__.py:2295).  partial_dev: double[2*nparts] scratch; deterministic two-stage reduction. */
+int gtn_dot(const void* a, const void* b, int64_t n, int dtype, void* out, double* partial_dev, int nparts,
+            void* stream);
 
 /* y[r] = sum_c |x[r*cols + c]|^2 (double): residual norms of the truncated-SVD certificate. */
 int gtn_row_sumsq(const void* x, double* y, int64_t rows, int64_t cols, int dtype, void* stream);
