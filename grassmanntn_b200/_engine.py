@@ -811,6 +811,7 @@ batched_svd.last_sweeps = 0
 # ------------------------------------------------------------------------------------------------
 TRUNC_TOL = 1e-11          # certificate: max_i ||W^H u_i - s_i v_i|| <= TRUNC_TOL * s_0
 TRUNC_MAX_ITERS = 20
+TRUNC_LMAX = 320           # widest subspace (rows of the projected matrix); gtn_chol_whiten handles <= 512
 _rand_cache = {}
 
 
@@ -896,10 +897,12 @@ def _whiten(ws, hG, hT, rel_thr=1e-13):
                                             _ptr(meta[nb:2 * nb]), _ptr(n_dev), nb, max(ns), rel_thr, _ptr(kept),
                                             _ptr(evals), _ptr(meta[2 * nb:]), _stream()), "gtn_small_eigh_whiten")
     else:
-        with prof_region("small_chol", 1):
-            check(lib.gtn_small_chol_whiten(_ptr(ws.buf), _ptr(ws.buf), dtype_code(ws.dtype), _ptr(meta[:nb]),
-                                            _ptr(meta[nb:2 * nb]), _ptr(n_dev), nb, max(ns), rel_thr, _ptr(kept),
-                                            _stream()), "gtn_small_chol_whiten")
+        se = int(lib.gtn_chol_whiten_scratch_elems(max(ns)))
+        scratch = torch.empty(se * nb, dtype=torch.complex128, device=dev) if se else None
+        with prof_region("chol_whiten", 1):
+            check(lib.gtn_chol_whiten(_ptr(ws.buf), _ptr(ws.buf), dtype_code(ws.dtype), _ptr(meta[:nb]),
+                                      _ptr(meta[nb:2 * nb]), _ptr(n_dev), nb, max(ns), rel_thr, _ptr(kept),
+                                      _ptr(scratch) if se else None, _stream()), "gtn_chol_whiten")
     return kept
 
 
@@ -928,7 +931,7 @@ def truncated_svd_batch(mats, ks, robust=False):
     nb = len(mats)
     P_ = [m.shape[0] for m in mats]
     Q_ = [m.shape[1] for m in mats]
-    L_ = [min(p, q, 2 * k + 8, 80) for p, q, k in zip(P_, Q_, ks)]
+    L_ = [min(p, q, 2 * k + 8, TRUNC_LMAX) for p, q, k in zip(P_, Q_, ks)]
     key = (tuple(P_), tuple(Q_), tuple(ks), str(dt))
     fails = _trunc_fail.get(key, 0)
     if fails >= 2 and not robust:

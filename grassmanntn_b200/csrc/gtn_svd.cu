@@ -640,89 +640,95 @@ extern "C" int gtn_small_eigh_whiten(const void* G, void* T, int dtype, const in
 // ------------------------------------------------------------------------------------------------
 namespace {
 
-template <bool CPLX>
-__global__ void __launch_bounds__(EIG_T)
-    small_chol_whiten_kernel(const typename Elem<CPLX>::T* __restrict__ Gb, typename Elem<CPLX>::T* __restrict__ Tb,
-                             const int64_t* __restrict__ g_off, const int64_t* __restrict__ t_off,
-                             const int32_t* __restrict__ ns, double rel_thr, int32_t* __restrict__ kept) {
+constexpr int CHOL_MAXN = 512;       // global-scratch variant
+constexpr int CHOL_T_SMALL = 256;
+constexpr int CHOL_T_LARGE = 1024;
+
+// Diagonally pivoted Cholesky of the Hermitian n x n matrix G with NO data movement for the pivoting:
+// perm[] lists the original indices in pivot order, the k-th column of L is formed in place in row
+// perm[k] of G (L_k[i] = conj(G[pk][i]) / sqrt(G[pk][pk]) for the not yet pivoted i), so a step is
+// three block barriers: pivot search (warp 0) | column scaling | rank-1 update of the remaining rows.
+// The inverse of the r x r factor is then built one warp per column (dot products across lanes) into
+// LiT (transposed), and T = [L_r^{-1} 0] P^T is written out.  GLOB=false keeps G and LiT in shared
+// memory (n <= EIG_MAXN), GLOB=true in a caller-provided global scratch (L2-resident, n <= CHOL_MAXN).
+template <bool CPLX, int NT, bool GLOB>
+__global__ void __launch_bounds__(NT)
+    chol_whiten_kernel(const typename Elem<CPLX>::T* __restrict__ Gb, typename Elem<CPLX>::T* __restrict__ Tb,
+                       const int64_t* __restrict__ g_off, const int64_t* __restrict__ t_off,
+                       const int32_t* __restrict__ ns, double rel_thr, int32_t* __restrict__ kept,
+                       c128* __restrict__ scratch, int64_t scratch_stride) {
   using T = typename Elem<CPLX>::T;
   extern __shared__ __align__(16) unsigned char sm_raw[];
   const int n = ns[blockIdx.x];
   const int ld = n + 1;
-  c128* G = reinterpret_cast<c128*>(sm_raw);       // lower triangle becomes L
-  c128* Li = G + n * ld;                           // inverse of L_r
-  __shared__ int perm[EIG_MAXN];
-  __shared__ double redv[EIG_T / 32];
-  __shared__ int redi[EIG_T / 32];
-  __shared__ int piv_s, rank_s;
-  __shared__ double first_s;
-  const int tid = threadIdx.x;
+  c128* G;
+  if constexpr (GLOB) G = scratch + int64_t(blockIdx.x) * scratch_stride;
+  else G = reinterpret_cast<c128*>(sm_raw);
+  c128* LiT = G + n * ld;
+  __shared__ int perm[GLOB ? CHOL_MAXN : EIG_MAXN];
+  __shared__ int rank_s, go_s;
+  __shared__ double first_s, inv_s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const T* Gin = Gb + g_off[blockIdx.x];
-  for (int e = tid; e < n * n; e += EIG_T) {
+  for (int e = tid; e < n * n; e += NT) {
     const int i = e / n, j = e % n;
     c128 v;
     if constexpr (CPLX) { const T t = Elem<CPLX>::ld(Gin + e); v.re = t.re; v.im = t.im; }
     else { v.re = Elem<CPLX>::ld(Gin + e); v.im = 0.0; }
     G[i * ld + j] = v;
-    c128 z; z.re = 0.0; z.im = 0.0;
-    Li[i * ld + j] = z;
   }
-  if (tid < n) perm[tid] = tid;
+  for (int i = tid; i < n; i += NT) perm[i] = i;
   if (tid == 0) { rank_s = n; first_s = 0.0; }
   __syncthreads();
   for (int k = 0; k < n; ++k) {
-    // ---- pivot: arg max of the remaining diagonal
-    double best = -1.0; int bi = k;
-    for (int i = k + tid; i < n; i += EIG_T) {
-      const double d = G[i * ld + i].re;
-      if (d > best) { best = d; bi = i; }
-    }
+    if (warp == 0) {
+      // ---- pivot: arg max of the remaining diagonal (ties -> smallest original index)
+      double best = -1.0; int bpos = k, bidx = 0x7fffffff;
+      for (int pos = k + lane; pos < n; pos += 32) {
+        const int i = perm[pos];
+        const double d = G[i * ld + i].re;
+        if (d > best || (d == best && i < bidx)) { best = d; bpos = pos; bidx = i; }
+      }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-    }
-    if ((tid & 31) == 0) { redv[tid >> 5] = best; redi[tid >> 5] = bi; }
-    __syncthreads();
-    if (tid == 0) {
-      double b = redv[0]; int x = redi[0];
-      for (int w = 1; w < EIG_T / 32; ++w)
-        if (redv[w] > b || (redv[w] == b && redi[w] < x)) { b = redv[w]; x = redi[w]; }
-      if (k == 0) first_s = b;
-      piv_s = (b > rel_thr * first_s && b > 0.0) ? x : -1;
-      if (piv_s < 0) rank_s = k;
-    }
-    __syncthreads();
-    const int pv = piv_s;
-    if (pv < 0) break;
-    // ---- symmetric swap k <-> pv (rows and columns; includes the finished L columns < k)
-    if (pv != k) {
-      for (int j = tid; j < n; j += EIG_T) {
-        const c128 a = G[k * ld + j]; G[k * ld + j] = G[pv * ld + j]; G[pv * ld + j] = a;
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int op = __shfl_xor_sync(0xffffffffu, bpos, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+        if (ob > best || (ob == best && oi < bidx)) { best = ob; bpos = op; bidx = oi; }
       }
-      __syncthreads();
-      for (int i = tid; i < n; i += EIG_T) {
-        const c128 a = G[i * ld + k]; G[i * ld + k] = G[i * ld + pv]; G[i * ld + pv] = a;
+      if (lane == 0) {
+        if (k == 0) first_s = best;
+        const bool ok = best > rel_thr * first_s && best > 0.0;
+        go_s = ok ? 1 : 0;
+        if (ok) {
+          const int t = perm[k]; perm[k] = perm[bpos]; perm[bpos] = t;
+          const double dkk = sqrt(best);
+          inv_s = 1.0 / dkk;
+          c128 d; d.re = dkk; d.im = 0.0;
+          G[bidx * ld + bidx] = d;
+        } else {
+          rank_s = k;
+        }
       }
-      if (tid == 0) { const int t = perm[k]; perm[k] = perm[pv]; perm[pv] = t; }
-      __syncthreads();
-    }
-    // ---- column k of L
-    const double dkk = sqrt(G[k * ld + k].re);
-    const double inv = 1.0 / dkk;
-    __syncthreads();
-    for (int i = k + tid; i < n; i += EIG_T) {
-      c128 v = G[i * ld + k];
-      if (i == k) { v.re = dkk; v.im = 0.0; } else { v.re *= inv; v.im *= inv; }
-      G[i * ld + k] = v;
     }
     __syncthreads();
-    // ---- trailing update G[i][j] -= L[i][k] conj(L[j][k]),  i,j > k
+    if (!go_s) break;
+    const int pk = perm[k];
+    const double inv = inv_s;
+    c128* Lk = G + pk * ld;
+    // ---- column k of L, in place in row pk:  L_k[i] = conj(G[pk][i]) / dkk
+    for (int pos = k + 1 + tid; pos < n; pos += NT) {
+      const int i = perm[pos];
+      c128 v = Lk[i];
+      v.re *= inv; v.im *= -inv;
+      Lk[i] = v;
+    }
+    __syncthreads();
+    // ---- G[i][j] -= L_k[i] conj(L_k[j]) over the remaining rows / columns
     const int m = n - k - 1;
-    for (int e = tid; e < m * m; e += EIG_T) {
-      const int i = k + 1 + e / m, j = k + 1 + e % m;
-      const c128 a = G[i * ld + k], b = G[j * ld + k];
+    for (int e = tid; e < m * m; e += NT) {
+      const int i = perm[k + 1 + e / m], j = perm[k + 1 + e % m];
+      const c128 a = Lk[i], b = Lk[j];
       c128 g = G[i * ld + j];
       g.re -= a.re * b.re + a.im * b.im;
       g.im -= a.im * b.re - a.re * b.im;
@@ -732,57 +738,84 @@ __global__ void __launch_bounds__(EIG_T)
   }
   __syncthreads();
   const int r = rank_s;
-  // ---- Li = L_r^{-1}: one thread per column c, forward substitution
-  for (int c = tid; c < r; c += EIG_T) {
+  // ---- LiT[c][i] = (L_r^{-1})[i][c]; L_r[i][j] = G[perm[j]][perm[i]] (i >= j). One warp per column.
+  for (int c = warp; c < r; c += NT / 32) {
+    c128* col = LiT + c * ld;
     for (int i = c; i < r; ++i) {
-      double sr = (i == c) ? 1.0 : 0.0, si = 0.0;
-      for (int j = c; j < i; ++j) {
-        const c128 l = G[i * ld + j], x = Li[j * ld + c];
+      const int pi = perm[i];
+      double sr = 0.0, si = 0.0;
+      for (int j = c + lane; j < i; j += 32) {
+        const c128 l = G[perm[j] * ld + pi], x = col[j];
         sr -= l.re * x.re - l.im * x.im;
         si -= l.re * x.im + l.im * x.re;
       }
-      const double d = 1.0 / G[i * ld + i].re;
-      c128 o; o.re = sr * d; o.im = si * d;
-      Li[i * ld + c] = o;
+      sr = warp_sum(sr);
+      si = warp_sum(si);
+      if (lane == 0) {
+        if (i == c) sr += 1.0;
+        const double d = 1.0 / G[pi * ld + pi].re;
+        c128 o; o.re = sr * d; o.im = si * d;
+        col[i] = o;
+      }
+      __syncwarp();
     }
   }
   __syncthreads();
   if (tid == 0) kept[blockIdx.x] = r;
   T* Tout = Tb + t_off[blockIdx.x];
-  for (int e = tid; e < n * n; e += EIG_T) {
+  for (int e = tid; e < n * n; e += NT) {
     const int i = e / n, c = e % n;       // T[i][perm[c]] = Li[i][c]
     c128 v; v.re = 0.0; v.im = 0.0;
-    if (i < r && c < r) v = Li[i * ld + c];
+    if (i < r && c <= i) v = LiT[c * ld + i];
     T* dst = Tout + int64_t(i) * n + perm[c];
     if constexpr (CPLX) { T t; t.re = v.re; t.im = v.im; Elem<CPLX>::st(dst, t); }
     else Elem<CPLX>::st(dst, v.re);
   }
 }
 
+template <typename K>
+int set_smem(K kernel, size_t smem) {
+  return (int)cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+
 }  // namespace
 
-extern "C" int gtn_small_chol_whiten(const void* G, void* T, int dtype, const int64_t* g_off_dev,
-                                     const int64_t* t_off_dev, const int32_t* n_dev, int nprob, int max_n,
-                                     double rel_thr, int32_t* kept_dev, void* stream) {
+extern "C" int64_t gtn_chol_whiten_scratch_elems(int max_n) {
+  return max_n <= EIG_MAXN ? 0 : int64_t(2) * max_n * (max_n + 1);
+}
+
+extern "C" int gtn_chol_whiten(const void* G, void* T, int dtype, const int64_t* g_off_dev,
+                               const int64_t* t_off_dev, const int32_t* n_dev, int nprob, int max_n,
+                               double rel_thr, int32_t* kept_dev, void* scratch, void* stream) {
   if (nprob <= 0) return GTN_OK;
-  if (max_n > EIG_MAXN) return GTN_ERR_UNSUPPORTED;
+  if (max_n > CHOL_MAXN) return GTN_ERR_UNSUPPORTED;
+  if (dtype != GTN_C128 && dtype != GTN_F64) return GTN_ERR_BAD_ARG;
   cudaStream_t s = (cudaStream_t)stream;
-  const size_t smem = size_t(2) * max_n * (max_n + 1) * 16 + 64;
-  static size_t attr = 0;
-  if (smem > attr) {
-    cudaError_t e1 = cudaFuncSetAttribute(small_chol_whiten_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaError_t e2 = cudaFuncSetAttribute(small_chol_whiten_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e1 != cudaSuccess) return (int)e1;
-    if (e2 != cudaSuccess) return (int)e2;
-    attr = smem;
+  if (max_n <= EIG_MAXN) {
+    const size_t smem = size_t(2) * max_n * (max_n + 1) * 16 + 64;
+    static size_t attr = 0;
+    if (smem > attr) {
+      int e1 = set_smem(chol_whiten_kernel<true, CHOL_T_SMALL, false>, smem);
+      int e2 = set_smem(chol_whiten_kernel<false, CHOL_T_SMALL, false>, smem);
+      if (e1) return e1;
+      if (e2) return e2;
+      attr = smem;
+    }
+    if (dtype == GTN_C128)
+      chol_whiten_kernel<true, CHOL_T_SMALL, false><<<nprob, CHOL_T_SMALL, smem, s>>>(
+          (const c128*)G, (c128*)T, g_off_dev, t_off_dev, n_dev, rel_thr, kept_dev, nullptr, 0);
+    else
+      chol_whiten_kernel<false, CHOL_T_SMALL, false><<<nprob, CHOL_T_SMALL, smem, s>>>(
+          (const double*)G, (double*)T, g_off_dev, t_off_dev, n_dev, rel_thr, kept_dev, nullptr, 0);
+  } else {
+    if (!scratch) return GTN_ERR_BAD_ARG;
+    const int64_t stride = gtn_chol_whiten_scratch_elems(max_n);
+    if (dtype == GTN_C128)
+      chol_whiten_kernel<true, CHOL_T_LARGE, true><<<nprob, CHOL_T_LARGE, 0, s>>>(
+          (const c128*)G, (c128*)T, g_off_dev, t_off_dev, n_dev, rel_thr, kept_dev, (c128*)scratch, stride);
+    else
+      chol_whiten_kernel<false, CHOL_T_LARGE, true><<<nprob, CHOL_T_LARGE, 0, s>>>(
+          (const double*)G, (double*)T, g_off_dev, t_off_dev, n_dev, rel_thr, kept_dev, (c128*)scratch, stride);
   }
-  if (dtype == GTN_C128)
-    small_chol_whiten_kernel<true><<<nprob, EIG_T, smem, s>>>((const c128*)G, (c128*)T, g_off_dev, t_off_dev, n_dev,
-                                                             rel_thr, kept_dev);
-  else if (dtype == GTN_F64)
-    small_chol_whiten_kernel<false><<<nprob, EIG_T, smem, s>>>((const double*)G, (double*)T, g_off_dev, t_off_dev,
-                                                              n_dev, rel_thr, kept_dev);
-  else
-    return GTN_ERR_BAD_ARG;
   return (int)cudaGetLastError();
 }

@@ -186,10 +186,13 @@ int gtn_small_eigh_whiten(const void* G, void* T, int dtype, const int64_t* g_of
 
 /* Same contract as gtn_small_eigh_whiten with a diagonally pivoted Cholesky factorisation
  * P^T G P = L L^H (stopped at numerical rank r: remaining diagonal <= rel_thr * first pivot):
- * T = [L_r^{-1} 0] P^T, rows >= r zero, kept_dev[b] = r.  ~10x fewer block barriers. */
-int gtn_small_chol_whiten(const void* G, void* T, int dtype, const int64_t* g_off_dev,
-                          const int64_t* t_off_dev, const int32_t* n_dev, int nprob, int max_n,
-                          double rel_thr, int32_t* kept_dev, void* stream);
+ * T = [L_r^{-1} 0] P^T, rows >= r zero, kept_dev[b] = r.  Three block barriers per pivot.
+ * max_n <= 80: everything in shared memory (scratch may be NULL); 80 < max_n <= 512: the working
+ * copies live in `scratch` (complex128 elements, nprob * gtn_chol_whiten_scratch_elems(max_n)). */
+int64_t gtn_chol_whiten_scratch_elems(int max_n);
+int gtn_chol_whiten(const void* G, void* T, int dtype, const int64_t* g_off_dev,
+                    const int64_t* t_off_dev, const int32_t* n_dev, int nprob, int max_n,
+                    double rel_thr, int32_t* kept_dev, void* scratch, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Small element-wise / reduction helpers.

@@ -243,3 +243,31 @@ def test_join_split_legs_bit_exact(gtn, case):
     # round trip (docs joinsplit.rst: (A - split(join(A))).norm = 0.0), compared in the canonical encoder
     rt = back_g.force_format('standard').force_encoder('canonical')
     assert np.array_equal(rt.data.cpu().numpy(), a.data)
+
+
+@pytest.mark.parametrize("dtype", ["complex", "float"])
+def test_truncated_svd_wide_subspace(gtn, dtype):
+    """subspaces wider than 80 rows (chi >= 96) orthonormalise through the global-scratch variant of the
+    pivoted-Cholesky kernel; kept singular triplets must match a full LAPACK SVD (reference SortedSVD,
+    __init__.py:3931-3951) to 1e-10 * s_0."""
+    import torch
+    from grassmanntn_b200 import _engine
+    rng = np.random.RandomState(77)
+    p, q, k = 640, 768, 60
+    def rnd(*s):
+        return rng.randn(*s) + 1j * rng.randn(*s) if dtype == "complex" else rng.randn(*s)
+    U0, _ = np.linalg.qr(rnd(p, p))
+    V0, _ = np.linalg.qr(rnd(q, q))
+    s0 = np.exp(-0.12 * np.arange(p))
+    M = (U0 * s0) @ V0[:, :p].conj().T
+    mats = [torch.from_numpy(M).cuda(), torch.from_numpy(np.ascontiguousarray(M[:600, :700])).cuda()]
+    out = _engine.truncated_svd_batch(mats, [k, k - 7])
+    assert out is not None, "certificate failed on a geometric spectrum"
+    for (U, s, Vh), Mx, kk in zip(out, mats, (k, k - 7)):
+        assert U.shape[1] >= 2 * kk + 8 > 80
+        sr = np.linalg.svd(Mx.cpu().numpy(), compute_uv=False)
+        assert np.abs(s[:kk] - sr[:kk]).max() <= 1e-10 * sr[0]
+        Uk, Vk = U[:, :kk].cpu().numpy(), Vh[:kk].cpu().numpy()
+        R = Mx.cpu().numpy() @ Vk.conj().T - Uk * s[:kk]
+        assert np.abs(R).max() <= 1e-10 * sr[0]
+        assert np.abs(Uk.conj().T @ Uk - np.eye(kk)).max() <= 1e-10
