@@ -881,35 +881,262 @@ def _ws_ctranspose(ws, pairs):
     _cached(key, build).run(ws.buf, ws.buf)
 
 
-def _whiten(ws, hG, hT, rel_thr=1e-13):
-    """T_b = L^{-1/2} E^H of the Gram matrices G_b (gtn_small_eigh_whiten); returns kept counts (device)."""
-    nb = len(hG)
-    dev = ws.dev
-    ns = [ws.items[h][1] for h in hG]
-    meta = torch.tensor([ws.off(h) for h in hG] + [ws.off(h) for h in hT] + list(np.cumsum([0] + ns[:-1])),
-                        dtype=torch.int64).to(dev, non_blocking=True)
-    n_dev = torch.tensor(ns, dtype=torch.int32).to(dev, non_blocking=True)
-    kept = torch.empty(nb, dtype=torch.int32, device=dev)
-    evals = torch.empty(sum(ns), dtype=torch.float64, device=dev)
-    if WHITEN == "eigh":
-        with prof_region("small_eigh", 1):
-            check(lib.gtn_small_eigh_whiten(_ptr(ws.buf), _ptr(ws.buf), dtype_code(ws.dtype), _ptr(meta[:nb]),
-                                            _ptr(meta[nb:2 * nb]), _ptr(n_dev), nb, max(ns), rel_thr, _ptr(kept),
-                                            _ptr(evals), _ptr(meta[2 * nb:]), _stream()), "gtn_small_eigh_whiten")
-    else:
-        se = int(lib.gtn_chol_whiten_scratch_elems(max(ns)))
-        scratch = torch.empty(se * nb, dtype=torch.complex128, device=dev) if se else None
-        with prof_region("chol_whiten", 1):
-            check(lib.gtn_chol_whiten(_ptr(ws.buf), _ptr(ws.buf), dtype_code(ws.dtype), _ptr(meta[:nb]),
-                                      _ptr(meta[nb:2 * nb]), _ptr(n_dev), nb, max(ns), rel_thr, _ptr(kept),
-                                      _ptr(scratch) if se else None, _stream()), "gtn_chol_whiten")
-    return kept
-
-
 DEBUG_TRUNC = bool(int(__import__("os").environ.get("GTN_DEBUG_TRUNC", "0")))
 WHITEN = "chol"            # "chol": pivoted Cholesky kernel (default); "eigh": Jacobi eigen-solver kernel
+USE_GRAPHS = bool(int(__import__("os").environ.get("GTN_GRAPHS", "1")))
+TRUNC_PLAN_CACHE_BYTES = 1 << 30     # plans (workspace + CUDA graphs) are kept for workspaces up to this size
 _trunc_iters_hint = {}
 _trunc_fail = {}
+_trunc_plans = {}
+
+
+class _TruncPlan:
+    """Static workspace, device metadata and launch sequence of one truncated-SVD batch shape.
+    Every step (start / iterate / check) only enqueues launches on the current stream; the one host
+    read-back per check happens in read().  Because nothing in a step depends on host data, the
+    steady-state schedule 'start, n iterations, check' is captured once per n as a CUDA graph and
+    replayed -- ~75 launches and four host round trips of a chi=32 TRG step become one graph launch and
+    one read-back."""
+
+    def __init__(self, P_, Q_, ks, L_, dt, dev):
+        self.P_, self.Q_, self.ks, self.L_, self.dt, self.dev = P_, Q_, ks, L_, dt, dev
+        nb = self.nb = len(P_)
+        ws = self.ws = _WS(dt, dev)
+        add = lambda rows, cols: [ws.add(r, c) for r, c in zip(rows, cols)]
+        self.hW, self.hWh = add(P_, Q_), add(Q_, P_)
+        self.hG, self.hYh, self.hQh = add(L_, Q_), add(L_, P_), add(L_, P_)
+        self.hZh, self.hPh = add(L_, Q_), add(L_, Q_)
+        self.hB, self.hVk = add(L_, Q_), add(L_, Q_)          # same sizes, same order: constant offset delta
+        self.hZ, self.hUb, self.hUbH = add(L_, L_), add(L_, L_), add(L_, L_)
+        self.hUh, self.hU, self.hXh = add(L_, P_), add(P_, L_), add(L_, P_)
+        self.hD, self.hT1, self.hT2 = add(L_, L_), add(L_, L_), add(L_, L_)
+        self.hCp, self.hCq = add(P_, L_), add(Q_, L_)         # conj-transposed iterates
+        self.hSp, self.hSq = add(L_, P_), add(L_, Q_)
+        ws.alloc()
+        self.nbytes = ws.buf.numel() * ws.buf.element_size()
+        for b in range(nb):
+            ws.view(self.hG[b]).view(-1).copy_(_randn(L_[b] * Q_[b], dt, dev))
+            ws.view(self.hD[b]).zero_()
+        sumL = self.sumL = sum(L_)
+        self.soff = list(np.cumsum([0] + L_[:-1]))
+        i64 = lambda v: torch.tensor(list(v), dtype=torch.int64).to(dev)
+        # whitening
+        self.g_off, self.t_off = i64(ws.off(h) for h in self.hT1), i64(ws.off(h) for h in self.hT2)
+        self.e_off = i64(self.soff)
+        self.n_dev = torch.tensor(L_, dtype=torch.int32).to(dev)
+        self.kept = [torch.zeros(nb, dtype=torch.int32, device=dev) for _ in range(2)]
+        self.evals = torch.empty(sumL, dtype=torch.float64, device=dev)
+        se = int(lib.gtn_chol_whiten_scratch_elems(max(L_)))
+        self.chol_scratch = torch.empty(se * nb, dtype=torch.complex128, device=dev) if se else None
+        # small Jacobi SVD of B, in place inside the workspace
+        parr, oarr = (SvdProblem * nb)(), (SvdOut * nb)()
+        for b in range(nb):
+            parr[b].w_off, parr[b].z_off, parr[b].p, parr[b].q = ws.off(self.hB[b]), ws.off(self.hZ[b]), L_[b], Q_[b]
+            oarr[b].s_off, oarr[b].u_off = self.soff[b], ws.off(self.hUb[b])
+        self.pdev, self.odev = _to_dev_bytes(bytes(parr)), _to_dev_bytes(bytes(oarr))
+        self.vh_delta = ws.off(self.hVk[0]) - ws.off(self.hB[0])
+        assert all(ws.off(v) - ws.off(h) == self.vh_delta for v, h in zip(self.hVk, self.hB))
+        self.rn2 = torch.empty(sumL, dtype=torch.float64, device=dev)
+        self.fro2 = torch.empty(nb, dtype=torch.float64, device=dev)
+        self.rn_off = i64(self.soff)
+        self.offd = torch.zeros(2 * nb, dtype=torch.float64, device=dev)
+        self.sw = torch.zeros(4, dtype=torch.int32, device=dev)
+        self.s_dev = torch.empty(sumL, dtype=torch.float64, device=dev)
+        self.order = torch.empty(sumL, dtype=torch.int32, device=dev)
+        self.nscratch = torch.empty(sumL, dtype=torch.float64, device=dev)
+        self.res2 = torch.empty(sumL, dtype=torch.float64, device=dev)
+        self.out_dev = torch.empty(2 * sumL + nb + 2, dtype=torch.float64, device=dev)
+        self.out_host = torch.empty(2 * sumL + nb + 2, dtype=torch.float64).pin_memory()
+        self.maxL, self.maxQ = max(L_), max(Q_)
+        self.persistent = 2 <= self.maxL <= PERSISTENT_MAX_ROWS
+        self.graphable = self.persistent and WHITEN == "chol"
+        self.graphs, self.graph_launches = {}, {}
+        self.host_sweeps = None
+        torch.cuda.current_stream().synchronize()       # metadata uploads done before any capture
+
+    # ---- launch sequences (enqueue only) -------------------------------------------------------
+    def load(self, mats):
+        for b in range(self.nb):
+            self.ws.view(self.hW[b]).copy_(mats[b])
+        _ws_ctranspose(self.ws, list(zip(self.hW, self.hWh)))
+
+    def _whiten(self, slot, rel_thr=1e-13):
+        ws, nb = self.ws, self.nb
+        code = dtype_code(self.dt)
+        if WHITEN == "eigh":
+            with prof_region("small_eigh", 1):
+                check(lib.gtn_small_eigh_whiten(_ptr(ws.buf), _ptr(ws.buf), code, _ptr(self.g_off), _ptr(self.t_off),
+                                                _ptr(self.n_dev), nb, self.maxL, rel_thr, _ptr(self.kept[slot]),
+                                                _ptr(self.evals), _ptr(self.e_off), _stream()), "gtn_small_eigh_whiten")
+        else:
+            with prof_region("chol_whiten", 1):
+                check(lib.gtn_chol_whiten(_ptr(ws.buf), _ptr(ws.buf), code, _ptr(self.g_off), _ptr(self.t_off),
+                                          _ptr(self.n_dev), nb, self.maxL, rel_thr, _ptr(self.kept[slot]),
+                                          _ptr(self.chol_scratch) if self.chol_scratch is not None else None,
+                                          _stream()), "gtn_chol_whiten")
+
+    def orth(self, src, dst, side, passes, robust=False):
+        ws = self.ws
+        if robust:
+            res = batched_svd([ws.view(h) for h in src])
+            for b in range(self.nb):
+                ws.view(dst[b]).copy_(res[b][2])
+            return
+        hC = self.hCp if side == "p" else self.hCq
+        hS = self.hSp if side == "p" else self.hSq
+        cur = src
+        for ps in range(passes):
+            _ws_ctranspose(ws, list(zip(cur, hC)))
+            _ws_gemm(ws, list(zip(cur, hC, self.hT1)))               # Gram  l x l
+            self._whiten(0 if ps == 0 else 1)
+            out = dst if ps == passes - 1 else hS
+            _ws_gemm(ws, list(zip(self.hT2, cur, out)))
+            cur = out
+
+    def start(self, passes, robust=False):
+        _ws_gemm(self.ws, list(zip(self.hG, self.hWh, self.hYh)))
+        self.orth(self.hYh, self.hQh, "p", passes, robust)
+
+    def iterate(self, last, robust=False):
+        ws = self.ws
+        _ws_gemm(ws, list(zip(self.hQh, self.hW, self.hZh)))
+        self.orth(self.hZh, self.hPh, "q", 1, robust)
+        _ws_gemm(ws, list(zip(self.hPh, self.hWh, self.hYh)))
+        self.orth(self.hYh, self.hQh, "p", 2 if last else 1, robust)
+
+    def check_enqueue(self, allow_host=True):
+        """B = Qh W, its Jacobi SVD, the Ritz vectors and the residual norms; results into out_host."""
+        ws, nb, dev, dt = self.ws, self.nb, self.dev, self.dt
+        code = dtype_code(dt)
+        st = _stream()
+        _ws_gemm(ws, list(zip(self.hQh, self.hW, self.hB)))
+        Wp = _ptr(ws.buf)
+        check(lib.gtn_jacobi_init(Wp, Wp, code, _ptr(self.pdev), nb, self.maxL, _ptr(self.rn2), _ptr(self.fro2),
+                                  _ptr(self.rn_off), st), "gtn_jacobi_init")
+        count()
+        self.host_sweeps = None
+        done = False
+        P = (self.maxL + 1) & ~1
+        esz = ws.buf.element_size()
+        rb = sum(2 * esz * (l * q + l * l) for l, q in zip(self.L_, self.Q_))
+        if self.persistent:
+            self._jbytes = rb * (P - 1)              # per sweep; scaled by the sweep count in read()
+            with prof_region("jacobi_persistent", 1, 0):
+                rc = lib.gtn_jacobi_persistent(Wp, Wp, code, _ptr(self.pdev), nb, self.maxL, JACOBI_TOL, _ptr(self.offd),
+                                               _ptr(self.rn2), _ptr(self.fro2), _ptr(self.rn_off), JACOBI_MAX_SWEEPS,
+                                               _ptr(self.sw), st)
+            if rc == 0:
+                done = True
+            elif rc == -2:
+                self.persistent = self.graphable = False
+            else:
+                check(rc, "gtn_jacobi_persistent")
+        if not done:
+            if not allow_host:
+                raise _cabi.GtnError("persistent Jacobi kernel unavailable inside a captured schedule")
+            sweeps = 0
+            self.offd.zero_()
+            while True:
+                with prof_region("jacobi_round", P - 1, rb * (P - 1)):
+                    check(lib.gtn_jacobi_sweep(Wp, Wp, code, _ptr(self.pdev), nb, self.maxL, self.maxQ, JACOBI_TOL,
+                                               _ptr(self.offd), _ptr(self.rn2), _ptr(self.fro2), _ptr(self.rn_off), st),
+                          "gtn_jacobi_sweep")
+                sweeps += 1
+                if float(self.offd[:nb].max().item()) <= JACOBI_TOL:
+                    break
+                if sweeps >= JACOBI_MAX_SWEEPS:
+                    raise _cabi.GtnError("Jacobi SVD did not converge in %d sweeps" % sweeps)
+            self.host_sweeps = sweeps
+        vh_ptr = C.c_void_p(ws.buf.data_ptr() + self.vh_delta * esz)
+        check(lib.gtn_jacobi_finish(Wp, Wp, Wp, vh_ptr, _ptr(self.s_dev), code, _ptr(self.pdev), _ptr(self.odev),
+                                    _ptr(self.order), _ptr(self.nscratch), nb, self.maxL, self.maxQ, st),
+              "gtn_jacobi_finish")
+        count(2)
+        _ws_ctranspose(ws, list(zip(self.hUb, self.hUbH)))
+        _ws_gemm(ws, list(zip(self.hUbH, self.hQh, self.hUh)))          # Uh = Ub^H Qh  (l x p)
+        # certificate rows:  Eh_i = v_i^H W^H - s_i u_i^H   (l x p)
+        _ws_gemm(ws, list(zip(self.hVk, self.hWh, self.hXh)))
+        for b in range(nb):
+            ws.view(self.hD[b]).diagonal().copy_(self.s_dev[self.soff[b]: self.soff[b] + self.L_[b]])
+        _ws_gemm(ws, list(zip(self.hD, self.hUh, self.hXh)), alpha=-1.0, beta=1.0)
+        for b in range(nb):
+            x = ws.view(self.hXh[b])
+            with prof_region("row_sumsq", 1, x.numel() * x.element_size()):
+                check(lib.gtn_row_sumsq(_ptr(x), _ptr(self.res2[self.soff[b]:]), self.L_[b], self.P_[b], code, st),
+                      "gtn_row_sumsq")
+        sL = self.sumL
+        self.out_dev[:sL].copy_(self.s_dev)
+        self.out_dev[sL: 2 * sL].copy_(self.res2)
+        self.out_dev[2 * sL: 2 * sL + nb].copy_(self.kept[0])
+        self.out_dev[2 * sL + nb:].copy_(self.sw[:2])
+        self.out_host.copy_(self.out_dev, non_blocking=True)
+
+    def read(self):
+        torch.cuda.current_stream().synchronize()
+        o = self.out_host.numpy()
+        sL, nb = self.sumL, self.nb
+        svals = [o[a: a + l].copy() for a, l in zip(self.soff, self.L_)]
+        res = np.sqrt(np.maximum(o[sL: 2 * sL], 0.0))
+        kept = o[2 * sL: 2 * sL + nb].astype(np.int64)
+        if self.host_sweeps is None:
+            sweeps, conv = int(o[2 * sL + nb]), int(o[2 * sL + nb + 1])
+            if not conv:
+                raise _cabi.GtnError("Jacobi SVD did not converge in %d sweeps" % sweeps)
+            if PROF.enabled:
+                for i in range(len(PROF.records) - 1, -1, -1):
+                    r = PROF.records[i]
+                    if r[0] == "jacobi_persistent":
+                        if r[4] == 0:
+                            PROF.records[i] = r[:4] + (self._jbytes * max(sweeps, 1),) + r[5:]
+                        break
+        else:
+            sweeps = self.host_sweeps
+        batched_svd.last_sweeps = sweeps
+        return svals, res, kept
+
+    def finalize(self):
+        ws = self.ws
+        _ws_ctranspose(ws, list(zip(self.hUh, self.hU)))
+        return [(ws.view(self.hU[b]), None, ws.view(self.hVk[b])) for b in range(self.nb)]
+
+    # ---- CUDA graph of the steady-state schedule -----------------------------------------------
+    def schedule(self, n):
+        self.start(2 if n == 0 else 1)
+        for it in range(1, n + 1):
+            self.iterate(it == n)
+        self.check_enqueue(allow_host=False)
+
+    def graph(self, n):
+        g = self.graphs.get(n)
+        if g is None:
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream()
+            side.wait_stream(cur)
+            c0 = _cabi.launch_count
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(side):
+                g.capture_begin()
+                try:
+                    self.schedule(n)
+                finally:
+                    g.capture_end()
+            cur.wait_stream(side)
+            self.graph_launches[n] = _cabi.launch_count - c0
+            _cabi.launch_count = c0                      # captured, not executed
+            self.graphs[n] = g
+        return g
+
+
+def _trunc_plan(key, P_, Q_, ks, L_, dt, dev):
+    plan = _trunc_plans.get(key)
+    if plan is None:
+        plan = _TruncPlan(P_, Q_, ks, L_, dt, dev)
+        plan.cached = plan.nbytes <= TRUNC_PLAN_CACHE_BYTES
+        if plan.cached:
+            if len(_trunc_plans) >= 16:
+                _trunc_plans.pop(next(iter(_trunc_plans)))
+            _trunc_plans[key] = plan
+    return plan
 
 
 def truncated_svd_batch(mats, ks, robust=False):
@@ -917,7 +1144,7 @@ def truncated_svd_batch(mats, ks, robust=False):
          Yh = G Wh ; Qh = orth_rows(Yh) ; [Zh = Qh W ; Ph = orth_rows(Zh) ; Yh = Ph Wh ; Qh = orth_rows(Yh)]*
          B = Qh W (l x q) ; B = Ub S Vh (small one-sided Jacobi) ; U = Qh^H Ub
     All products run on the DMMA GEMM kernel.  orth_rows whitens with the l x l Gram matrix
-    (gtn_small_eigh_whiten, one CTA per matrix; two passes for the final basis) -- or, with
+    (gtn_chol_whiten, one CTA per matrix; two passes for the final basis) -- or, with
     robust=True, runs the one-sided Jacobi kernels on the l rows (keeps directions that a Gram matrix
     cannot resolve).  The final small SVD of B always uses one-sided Jacobi, so the kept singular
     values do not go through a Gram matrix.  The result is accepted only with a certificate: the
@@ -925,6 +1152,8 @@ def truncated_svd_batch(mats, ks, robust=False):
     Returns None when the certificate fails after TRUNC_MAX_ITERS refinements, or when the Gram
     whitening dropped directions while fewer than k triplets were found -- the caller then retries
     with robust=True or runs the full Jacobi SVD.
+    The returned U / Vh are views into the plan's workspace: valid until the next call with the same
+    batch shape (callers unpack them into tensors straight away).
     Replaces LAPACK's full gesdd in reference SortedSVD (__init__.py:3932) when only the first
     `cutoff` singular triplets are kept (:3943-3948)."""
     dev, dt = mats[0].device, mats[0].dtype
@@ -932,97 +1161,44 @@ def truncated_svd_batch(mats, ks, robust=False):
     P_ = [m.shape[0] for m in mats]
     Q_ = [m.shape[1] for m in mats]
     L_ = [min(p, q, 2 * k + 8, TRUNC_LMAX) for p, q, k in zip(P_, Q_, ks)]
-    key = (tuple(P_), tuple(Q_), tuple(ks), str(dt))
+    key = (tuple(P_), tuple(Q_), tuple(ks), str(dt), str(dev))
     fails = _trunc_fail.get(key, 0)
     if fails >= 2 and not robust:
         # this shape keeps failing the certificate (flat spectrum): go straight to the full SVD, but
         # re-try every 16th call in case the spectrum has changed
         _trunc_fail[key] = fails + 1 if fails < 17 else 1
         return None
-    ws = _WS(dt, dev)
-    hW = [ws.add(p, q) for p, q in zip(P_, Q_)]
-    hWh = [ws.add(q, p) for p, q in zip(P_, Q_)]
-    hG = [ws.add(l, q) for l, q in zip(L_, Q_)]
-    hYh = [ws.add(l, p) for l, p in zip(L_, P_)]
-    hQh = [ws.add(l, p) for l, p in zip(L_, P_)]
-    hZh = [ws.add(l, q) for l, q in zip(L_, Q_)]
-    hPh = [ws.add(l, q) for l, q in zip(L_, Q_)]
-    hB = [ws.add(l, q) for l, q in zip(L_, Q_)]
-    hUbH = [ws.add(l, l) for l in L_]
-    hUh = [ws.add(l, p) for l, p in zip(L_, P_)]
-    hU = [ws.add(p, l) for l, p in zip(L_, P_)]
-    hVk = [ws.add(l, q) for l, q in zip(L_, Q_)]
-    hXh = [ws.add(l, p) for l, p in zip(L_, P_)]
-    hD = [ws.add(l, l) for l in L_]
-    hT1 = [ws.add(l, l) for l in L_]           # Gram / whitening scratch
-    hT2 = [ws.add(l, l) for l in L_]
-    hCp = [ws.add(p, l) for l, p in zip(L_, P_)]   # conj-transposed iterates
-    hCq = [ws.add(q, l) for l, q in zip(L_, Q_)]
-    hSp = [ws.add(l, p) for l, p in zip(L_, P_)]
-    hSq = [ws.add(l, q) for l, q in zip(L_, Q_)]
-    ws.alloc()
-    for b in range(nb):
-        ws.view(hW[b]).copy_(mats[b])
-        ws.view(hG[b]).view(-1).copy_(_randn(L_[b] * Q_[b], dt, dev))
-    _ws_ctranspose(ws, list(zip(hW, hWh)))
-    dropped = [None]
-
-    def orth(src, dst, side, passes):
-        if robust:
-            res = batched_svd([ws.view(h) for h in src])
-            for b in range(nb):
-                ws.view(dst[b]).copy_(res[b][2])
-            return
-        hC = hCp if side == "p" else hCq
-        hS = hSp if side == "p" else hSq
-        cur = src
-        for ps in range(passes):
-            _ws_ctranspose(ws, list(zip(cur, hC)))
-            _ws_gemm(ws, list(zip(cur, hC, hT1)))               # Gram  l x l
-            kept = _whiten(ws, hT1, hT2)
-            if ps == 0:
-                dropped[0] = kept
-            out = dst if ps == passes - 1 else hS
-            _ws_gemm(ws, list(zip(hT2, cur, out)))
-            cur = out
-
+    plan = _trunc_plan(key, P_, Q_, ks, L_, dt, dev)
+    plan.load(mats)
+    hint = _trunc_iters_hint.get(key)
+    start_it = max(0, (hint or 0) - 1) if not robust else 0
+    replayed = False
+    if (USE_GRAPHS and hint is not None and not robust and plan.cached and plan.graphable and not PROF.enabled):
+        try:
+            g = plan.graph(start_it)
+            g.replay()
+            count(plan.graph_launches[start_it])
+            replayed = True
+        except (RuntimeError, _cabi.GtnError):
+            plan.graphable = False
+            plan.graphs.clear()
+            torch.cuda.synchronize()
     prev_worst, prev_it, next_check = None, None, 0
-    start_it = max(0, _trunc_iters_hint.get(key, 0) - 1) if not robust else 0
-    _ws_gemm(ws, list(zip(hG, hWh, hYh)))
-    orth(hYh, hQh, "p", 2 if start_it == 0 else 1)
-    code = dtype_code(dt)
     for it in range(TRUNC_MAX_ITERS + 1):
-        if it > 0:
-            last = it >= start_it and it >= next_check
-            _ws_gemm(ws, list(zip(hQh, hW, hZh)))
-            orth(hZh, hPh, "q", 1)
-            _ws_gemm(ws, list(zip(hPh, hWh, hYh)))
-            orth(hYh, hQh, "p", 2 if last else 1)
-        if it < start_it or it < next_check:
-            continue
-        _ws_gemm(ws, list(zip(hQh, hW, hB)))
-        usv = batched_svd([ws.view(h) for h in hB])
-        svals = [u[1] for u in usv]
-        for b in range(nb):
-            ws.view(hUbH[b]).copy_(usv[b][0].conj().transpose(0, 1))
-            ws.view(hVk[b]).copy_(usv[b][2])
-        _ws_gemm(ws, list(zip(hUbH, hQh, hUh)))          # Uh = Ub^H Qh  (l x p)
-        # certificate rows:  Eh_i = v_i^H W^H - s_i u_i^H   (l x p)
-        _ws_gemm(ws, list(zip(hVk, hWh, hXh)))
-        for b in range(nb):
-            d = ws.view(hD[b])
-            d.zero_()
-            d.diagonal().copy_(torch.from_numpy(-svals[b]).to(dev).to(dt))
-        _ws_gemm(ws, list(zip(hD, hUh, hXh)), alpha=1.0, beta=1.0)
-        res2 = torch.empty(sum(L_), dtype=torch.float64, device=dev)
-        o = 0
-        for b in range(nb):
-            x = ws.view(hXh[b])
-            with prof_region("row_sumsq", 1, x.numel() * x.element_size()):
-                check(lib.gtn_row_sumsq(_ptr(x), _ptr(res2[o:]), L_[b], P_[b], code, _stream()), "gtn_row_sumsq")
-            o += L_[b]
-        res = np.sqrt(res2.cpu().numpy())
-        kept_host = None if (robust or dropped[0] is None) else dropped[0].cpu().numpy()
+        if replayed and it <= start_it:
+            if it < start_it:
+                continue                     # done inside the graph, check included
+        else:
+            if it == 0:
+                plan.start(2 if start_it == 0 else 1, robust)
+            else:
+                plan.iterate(it >= start_it and it >= next_check, robust)
+            if it < start_it or it < next_check:
+                continue
+            plan.check_enqueue()
+        svals, res, kept_host = plan.read()
+        if robust:
+            kept_host = None
         ok, o = True, 0
         worst = 0.0
         for b in range(nb):
@@ -1051,8 +1227,9 @@ def truncated_svd_batch(mats, ks, robust=False):
             o += L_[b]
         truncated_svd_batch.last_iters = it
         if DEBUG_TRUNC:
-            print("[trunc] it", it, "worst %.2e" % worst, "ok", ok, "shapes", list(zip(P_, Q_)), "k", ks, "L", L_,
-                  "s[k-2:k+3]/s0", [np.array2string(sv[max(0, k - 2):k + 3] / sv[0], precision=5) for sv, k in zip(svals, ks)], flush=True)
+            print("[trunc] it", it, "worst %.2e" % worst, "ok", ok, "graph", replayed, "shapes", list(zip(P_, Q_)), "k", ks,
+                  "L", L_, "s[k-2:k+3]/s0",
+                  [np.array2string(sv[max(0, k - 2):k + 3] / sv[0], precision=5) for sv, k in zip(svals, ks)], flush=True)
         if not ok and prev_worst is not None and it >= 2:
             rate = (worst / prev_worst) ** (1.0 / max(it - prev_it, 1)) if prev_worst > 0 else 1.0
             if rate > 0.6:
@@ -1070,8 +1247,8 @@ def truncated_svd_batch(mats, ks, robust=False):
         if ok:
             _trunc_iters_hint[key] = it
             _trunc_fail[key] = 0
-            _ws_ctranspose(ws, list(zip(hUh, hU)))
-            return [(ws.view(hU[b]), svals[b], ws.view(hVk[b])) for b in range(nb)]
+            out = plan.finalize()
+            return [(u, svals[b], v) for b, (u, _, v) in enumerate(out)]
     _trunc_fail[key] = _trunc_fail.get(key, 0) + 1
     return None
 
