@@ -237,13 +237,18 @@ def main():
     host_in = torch.from_numpy(np.ascontiguousarray(T.todense().data.cpu().numpy())).pin_memory()
     tstats = T.statistics
 
+    host_out = [None]
+
     def e2e_step():
         d = host_in.to(dev, non_blocking=True)
         Xb = gtn.dense(d, statistics=tstats).toblock()
         Y, Tn = g.trg(Xb, args.chi)
         out = Y.todense().data
-        host_out = out.cpu()
-        return host_out, Tn
+        if host_out[0] is None or host_out[0].shape != out.shape:
+            host_out[0] = torch.empty(out.shape, dtype=out.dtype).pin_memory()
+        host_out[0].copy_(out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return host_out[0], Tn
     for _ in range(max(1, args.warmup // 2)):
         e2e_step()
     barrier()

@@ -61,8 +61,10 @@ def _load():
         "gtn_jacobi_persistent": (i32, [vp, vp, i32, vp, i32, i32, dbl, vp, vp, vp, vp, i32, vp, vp]),
         "gtn_jacobi_finish": (i32, [vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, i32, i32, i32, vp]),
         "gtn_small_eigh_whiten": (i32, [vp, vp, i32, vp, vp, vp, i32, i32, dbl, vp, vp, vp, vp]),
-        "gtn_chol_whiten": (i32, [vp, vp, i32, vp, vp, vp, i32, i32, dbl, vp, vp, vp]),
+        "gtn_chol_whiten": (i32, [vp, vp, i32, vp, vp, vp, i32, i32, i32, dbl, vp, vp, vp]),
         "gtn_chol_whiten_scratch_elems": (i64, [i32]),
+        "gtn_debug_phase_clocks": (i32, [vp]),
+        "gtn_gram_rotate": (i32, [vp, vp, i32, vp, vp, vp, i32, i32, i32, dbl, dbl, i32, vp, vp]),
         "gtn_sumsq": (i32, [vp, i64, i32, vp, i32, vp]),
         "gtn_rowsum": (i32, [vp, vp, i64, i64, i32, vp]),
         "gtn_dot": (i32, [vp, vp, i64, i32, vp, vp, i32, vp]),

@@ -776,7 +776,7 @@ def batched_svd(mats):
                 check(lib.gtn_jacobi_sweep(_ptr(W), _ptr(Z), code, _ptr(pdev), nprob, maxp, maxq, JACOBI_TOL,
                                            _ptr(offd), _ptr(rn2), _ptr(fro2), _ptr(rn_off), st), "gtn_jacobi_sweep")
             sweeps += 1
-            if float(offd[:nprob].max().item()) <= JACOBI_TOL:
+            if float(offd[:nprob].max().item()) <= JACOBI_TOL ** 2:     # squared overlaps of rotated pairs
                 break
             if sweeps >= JACOBI_MAX_SWEEPS:
                 raise _cabi.GtnError("Jacobi SVD did not converge in %d sweeps" % sweeps)
@@ -884,9 +884,14 @@ def _ws_ctranspose(ws, pairs):
 DEBUG_TRUNC = bool(int(__import__("os").environ.get("GTN_DEBUG_TRUNC", "0")))
 WHITEN = "chol"            # "chol": pivoted Cholesky kernel (default); "eigh": Jacobi eigen-solver kernel
 USE_GRAPHS = bool(int(__import__("os").environ.get("GTN_GRAPHS", "1")))
+PREROTATE = bool(int(__import__("os").environ.get("GTN_PREROTATE", "1")))
+# in-kernel Jacobi tolerance of the Gram pre-rotation: the Gram matrix only determines the rows to ~1e-8
+# relative for the small ones, the global Jacobi kernel polishes the rest
+ROTATE_TOL = float(__import__("os").environ.get("GTN_ROTATE_TOL", "1e-12"))
 TRUNC_PLAN_CACHE_BYTES = 1 << 30     # plans (workspace + CUDA graphs) are kept for workspaces up to this size
 _trunc_iters_hint = {}
 _trunc_fail = {}
+_trunc_rate = {}
 _trunc_plans = {}
 
 
@@ -909,7 +914,9 @@ class _TruncPlan:
         self.hB, self.hVk = add(L_, Q_), add(L_, Q_)          # same sizes, same order: constant offset delta
         self.hZ, self.hUb, self.hUbH = add(L_, L_), add(L_, L_), add(L_, L_)
         self.hUh, self.hU, self.hXh = add(L_, P_), add(P_, L_), add(L_, P_)
-        self.hD, self.hT1, self.hT2 = add(L_, L_), add(L_, L_), add(L_, L_)
+        # split-K Gram matrices: NS partial l x l slices per problem, summed by the whitening kernels
+        self.NS = 4 if (WHITEN == "chol" and min(P_ + Q_) >= 256) else 1
+        self.hD, self.hT1, self.hT2 = add(L_, L_), add([self.NS * l for l in L_], L_), add(L_, L_)
         self.hCp, self.hCq = add(P_, L_), add(Q_, L_)         # conj-transposed iterates
         self.hSp, self.hSq = add(L_, P_), add(L_, Q_)
         ws.alloc()
@@ -948,6 +955,15 @@ class _TruncPlan:
         self.out_dev = torch.empty(2 * sumL + nb + 2, dtype=torch.float64, device=dev)
         self.out_host = torch.empty(2 * sumL + nb + 2, dtype=torch.float64).pin_memory()
         self.maxL, self.maxQ = max(L_), max(Q_)
+        # Gram pre-rotation of the projected matrix (gtn_gram_rotate): the Jacobi SVD then runs on hSq
+        self.prerotate = PREROTATE and 2 <= self.maxL <= 80
+        self.rot_sweeps = torch.zeros(nb, dtype=torch.int32, device=dev)
+        hJ = self.hSq if self.prerotate else self.hB
+        for b in range(nb):
+            parr[b].w_off = ws.off(hJ[b])
+        self.pdev = _to_dev_bytes(bytes(parr))
+        self.vh_delta = ws.off(self.hVk[0]) - ws.off(hJ[0])
+        assert all(ws.off(v) - ws.off(h) == self.vh_delta for v, h in zip(self.hVk, hJ))
         self.persistent = 2 <= self.maxL <= PERSISTENT_MAX_ROWS
         self.graphable = self.persistent and WHITEN == "chol"
         self.graphs, self.graph_launches = {}, {}
@@ -971,9 +987,27 @@ class _TruncPlan:
         else:
             with prof_region("chol_whiten", 1):
                 check(lib.gtn_chol_whiten(_ptr(ws.buf), _ptr(ws.buf), code, _ptr(self.g_off), _ptr(self.t_off),
-                                          _ptr(self.n_dev), nb, self.maxL, rel_thr, _ptr(self.kept[slot]),
+                                          _ptr(self.n_dev), nb, self.maxL, self.NS, rel_thr, _ptr(self.kept[slot]),
                                           _ptr(self.chol_scratch) if self.chol_scratch is not None else None,
                                           _stream()), "gtn_chol_whiten")
+
+    def _gram(self, cur, curH):
+        """hT1_b = sum_s cur_b[:, Ks] curH_b[Ks, :]  as NS partial slices (one grouped launch)"""
+        ws, NS = self.ws, self.NS
+        if NS == 1:
+            _ws_gemm(ws, list(zip(cur, curH, self.hT1)))
+            return
+        groups = []
+        for a, bh, c in zip(cur, curH, self.hT1):
+            _, l, K = ws.items[a]
+            kc = -(-K // NS)
+            for sp in range(NS):
+                k0 = min(sp * kc, K)
+                kk = min(kc, K - k0)
+                groups.append(dict(a_off=ws.off(a) + k0, b_off=ws.off(bh) + k0 * l, c_off=ws.off(c) + sp * l * l,
+                                   lda=K, ldb=l, ldc=l, m=l, n=l, k=kk, alpha=1.0, beta=0.0))
+        key = ("wsgram", str(ws.dtype), tuple(tuple(sorted(g.items())) for g in groups))
+        _cached(key, lambda: GemmPlan(groups, ws.dtype)).run(ws.buf, ws.buf, ws.buf)
 
     def orth(self, src, dst, side, passes, robust=False):
         ws = self.ws
@@ -987,7 +1021,7 @@ class _TruncPlan:
         cur = src
         for ps in range(passes):
             _ws_ctranspose(ws, list(zip(cur, hC)))
-            _ws_gemm(ws, list(zip(cur, hC, self.hT1)))               # Gram  l x l
+            self._gram(cur, hC)                                      # Gram  l x l
             self._whiten(0 if ps == 0 else 1)
             out = dst if ps == passes - 1 else hS
             _ws_gemm(ws, list(zip(self.hT2, cur, out)))
@@ -1011,6 +1045,19 @@ class _TruncPlan:
         st = _stream()
         _ws_gemm(ws, list(zip(self.hQh, self.hW, self.hB)))
         Wp = _ptr(ws.buf)
+        if self.prerotate:
+            # B' = T B, Qh' = T Qh with the unitary T from the Gram matrix of B: rows of B' nearly orthogonal
+            _ws_ctranspose(ws, list(zip(self.hB, self.hCq)))
+            self._gram(self.hB, self.hCq)
+            with prof_region("gram_rotate", 1):
+                check(lib.gtn_gram_rotate(Wp, Wp, code, _ptr(self.g_off), _ptr(self.t_off), _ptr(self.n_dev), nb,
+                                          self.maxL, self.NS, 1e-15, ROTATE_TOL, 30, _ptr(self.rot_sweeps), st),
+                      "gtn_gram_rotate")
+            _ws_gemm(ws, list(zip(self.hT2, self.hB, self.hSq)))
+            _ws_gemm(ws, list(zip(self.hT2, self.hQh, self.hSp)))
+            a0, a1 = ws.off(self.hQh[0]), ws.off(self.hSp[0])
+            nq = sum(l * p for l, p in zip(self.L_, self.P_))
+            ws.buf[a0: a0 + nq].copy_(ws.buf[a1: a1 + nq])
         check(lib.gtn_jacobi_init(Wp, Wp, code, _ptr(self.pdev), nb, self.maxL, _ptr(self.rn2), _ptr(self.fro2),
                                   _ptr(self.rn_off), st), "gtn_jacobi_init")
         count()
@@ -1042,7 +1089,7 @@ class _TruncPlan:
                                                _ptr(self.offd), _ptr(self.rn2), _ptr(self.fro2), _ptr(self.rn_off), st),
                           "gtn_jacobi_sweep")
                 sweeps += 1
-                if float(self.offd[:nb].max().item()) <= JACOBI_TOL:
+                if float(self.offd[:nb].max().item()) <= JACOBI_TOL ** 2:
                     break
                 if sweeps >= JACOBI_MAX_SWEEPS:
                     raise _cabi.GtnError("Jacobi SVD did not converge in %d sweeps" % sweeps)
@@ -1171,7 +1218,9 @@ def truncated_svd_batch(mats, ks, robust=False):
     plan = _trunc_plan(key, P_, Q_, ks, L_, dt, dev)
     plan.load(mats)
     hint = _trunc_iters_hint.get(key)
-    start_it = max(0, (hint or 0) - 1) if not robust else 0
+    # steady state: as many iterations as the last accepted run needed, one fewer when that run passed
+    # with a margin of one iteration's convergence factor (a failed check costs ~4 iterations' worth).
+    start_it = (hint or 0) if not robust else 0
     replayed = False
     if (USE_GRAPHS and hint is not None and not robust and plan.cached and plan.graphable and not PROF.enabled):
         try:
@@ -1230,6 +1279,8 @@ def truncated_svd_batch(mats, ks, robust=False):
             print("[trunc] it", it, "worst %.2e" % worst, "ok", ok, "graph", replayed, "shapes", list(zip(P_, Q_)), "k", ks,
                   "L", L_, "s[k-2:k+3]/s0",
                   [np.array2string(sv[max(0, k - 2):k + 3] / sv[0], precision=5) for sv, k in zip(svals, ks)], flush=True)
+        if prev_worst is not None and prev_worst > 0 and worst > 0 and it > prev_it:
+            _trunc_rate[key] = min(max((worst / prev_worst) ** (1.0 / (it - prev_it)), 1e-3), 0.9)
         if not ok and prev_worst is not None and it >= 2:
             rate = (worst / prev_worst) ** (1.0 / max(it - prev_it, 1)) if prev_worst > 0 else 1.0
             if rate > 0.6:
@@ -1245,7 +1296,8 @@ def truncated_svd_batch(mats, ks, robust=False):
                 return None
         prev_worst, prev_it = worst, it
         if ok:
-            _trunc_iters_hint[key] = it
+            margin = worst <= TRUNC_TOL * _trunc_rate.get(key, 0.2)
+            _trunc_iters_hint[key] = max(it - 1, 0) if margin else it
             _trunc_fail[key] = 0
             out = plan.finalize()
             return [(u, svals[b], v) for b, (u, _, v) in enumerate(out)]

@@ -74,6 +74,27 @@ __device__ __forceinline__ void rot(double& x, double& y, double cs, double sn, 
   y = sn * xx + cs * yy;
 }
 
+// Jacobi rotation for the row pair with squared norms a, b and inner product c = <x, y^*> = cr + i ci:
+// returns false when |c| <= tol |x||y| (no rotation).  One rsqrt for |c| (phase, zeta), one sqrt + one
+// division for t = tan(theta), one rsqrt for cos(theta): the rotation is computed by a single thread (or
+// redundantly by a lane group) on the critical path of every round, so the special-function chain is
+// kept short.  *off2 = |c|^2 / (a b).
+__device__ __forceinline__ bool jacobi_rotation(double a, double b, double cr, double ci, double tol, double& cs,
+                                                double& sn, double& phr, double& phi, double& tcabs, double* off2) {
+  const double c2 = cr * cr + ci * ci;
+  const double ab = a * b;
+  if (!(c2 > tol * tol * ab) || !(ab > 0.0)) return false;
+  const double ic = rsqrt(c2);
+  const double zeta = (b - a) * 0.5 * ic;
+  const double tt = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+  cs = rsqrt(1.0 + tt * tt);
+  sn = cs * tt;
+  phr = cr * ic; phi = ci * ic;
+  tcabs = tt * c2 * ic;
+  if (off2) *off2 = c2 / ab;
+  return true;
+}
+
 // one (round, pair) step of the one-sided Jacobi iteration for problem `prob`, executed by one CTA
 template <bool CPLX>
 __device__ __forceinline__ void jacobi_pair_step(typename Elem<CPLX>::T* __restrict__ Wb,
@@ -155,23 +176,13 @@ __device__ __forceinline__ void jacobi_pair_step(typename Elem<CPLX>::T* __restr
     double A = 0, B = 0, CR = 0, CI = 0;
 #pragma unroll
     for (int w = 0; w < JT / 32; ++w) { A += red[0][w]; B += red[1][w]; CR += red[2][w]; CI += red[3][w]; }
-    const double cabs = sqrt(CR * CR + CI * CI);
-    const double denom = sqrt(A) * sqrt(B);
-    double cs = 1.0, sn = 0.0, phr = 1.0, phi = 0.0, act = 0.0;
+    double cs = 1.0, sn = 0.0, phr = 1.0, phi = 0.0, act = 0.0, tc = 0.0, off2 = 0.0;
     rn[i] = A; rn[j] = B;
-    if (denom > 0.0 && cabs > 0.0) {
-      const double off = cabs / denom;
-      if (off > tol) {
-        atomic_max_pos(offdiag + prob, off);
-        const double zeta = (B - A) / (2.0 * cabs);
-        const double tt = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-        cs = 1.0 / sqrt(1.0 + tt * tt);
-        sn = cs * tt;
-        phr = CR / cabs; phi = CI / cabs;
-        act = 1.0;
-        rn[i] = fmax(A - tt * cabs, 0.0); rn[j] = B + tt * cabs;
-        atomic_max_pos(const_cast<double*>(fro2) + prob, fmax(rn[i], rn[j]));
-      }
+    if (jacobi_rotation(A, B, CR, CI, tol, cs, sn, phr, phi, tc, &off2)) {
+      atomic_max_pos(offdiag + prob, off2);
+      act = 1.0;
+      rn[i] = fmax(A - tc, 0.0); rn[j] = B + tc;
+      atomic_max_pos(const_cast<double*>(fro2) + prob, fmax(rn[i], rn[j]));
     }
     rotp[0] = cs; rotp[1] = sn; rotp[2] = phr; rotp[3] = phi; rotp[4] = act;
   }
@@ -640,22 +651,240 @@ extern "C" int gtn_small_eigh_whiten(const void* G, void* T, int dtype, const in
 // ------------------------------------------------------------------------------------------------
 namespace {
 
+// phase time stamps (clock64) of block 0 of the last chol_whiten / gram_rotate launch: [0..3] / [4..7]
+__device__ long long gtn_phase_clk[8];
+
 constexpr int CHOL_MAXN = 512;       // global-scratch variant
 constexpr int CHOL_T_SMALL = 256;
 constexpr int CHOL_T_LARGE = 1024;
 
-// Diagonally pivoted Cholesky of the Hermitian n x n matrix G with NO data movement for the pivoting:
-// perm[] lists the original indices in pivot order, the k-th column of L is formed in place in row
-// perm[k] of G (L_k[i] = conj(G[pk][i]) / sqrt(G[pk][pk]) for the not yet pivoted i), so a step is
-// three block barriers: pivot search (warp 0) | column scaling | rank-1 update of the remaining rows.
-// The inverse of the r x r factor is then built one warp per column (dot products across lanes) into
-// LiT (transposed), and T = [L_r^{-1} 0] P^T is written out.  GLOB=false keeps G and LiT in shared
-// memory (n <= EIG_MAXN), GLOB=true in a caller-provided global scratch (L2-resident, n <= CHOL_MAXN).
-template <bool CPLX, int NT, bool GLOB>
+// Diagonally pivoted Cholesky of the Hermitian n x n matrix G (row stride ld), ONE block barrier per
+// pivot and no data movement for the pivoting.  Every warp runs the pivot search redundantly on
+// lane-owned copies of the remaining diagonal (registers), so pivot index and 1/sqrt(pivot) are known to
+// all threads without a broadcast; the rank-1 update of the remaining rows/columns reads the pivot row
+// of G, scales it on the fly and stores column k of the factor into the SEPARATE array L:
+//     L[k*ld + i] = L_k[i]   (i = original row index, defined for the rows not pivoted before step k)
+// piv[k] = original index of the k-th pivot; in pivot order L_r[a][b] = L[b*ld + piv[a]], a >= b.
+// The pivot is the largest remaining diagonal entry up to its top 32 bits (sign, exponent, 20 mantissa
+// bits): one REDUX instead of a shuffle tree; any near-maximal pivot is as good.
+template <int NT, int MAXN>
+__device__ __forceinline__ int chol_factor(c128* G, c128* L, int n, int ld, int* piv, double rel_thr) {
+  constexpr int NW = (MAXN + 31) / 32;
+  const int tid = threadIdx.x, lane = tid & 31;
+  unsigned done[NW];
+  double dreg[NW];
+#pragma unroll
+  for (int t = 0; t < NW; ++t) {
+    done[t] = 0u;
+    const int i = lane + 32 * t;
+    dreg[t] = i < n ? G[i * ld + i].re : -1.0;
+  }
+  double first = 0.0;
+  int rank = n;
+  for (int k = 0; k < n; ++k) {
+    // ---- pivot search (identical in every warp)
+    double best = -1.0; int bidx = 0;
+#pragma unroll
+    for (int t = 0; t < NW; ++t) {
+      const bool free_ = !((done[t] >> lane) & 1u);
+      if (free_ && dreg[t] > best) { best = dreg[t]; bidx = lane + 32 * t; }
+    }
+    const unsigned key = best > 0.0 ? (unsigned)(__double_as_longlong(best) >> 32) : 0u;
+    const unsigned top = __reduce_max_sync(0xffffffffu, key);
+    const int src = __ffs(__ballot_sync(0xffffffffu, key == top)) - 1;
+    best = __shfl_sync(0xffffffffu, best, src);
+    bidx = __shfl_sync(0xffffffffu, bidx, src);
+    if (k == 0) first = best;
+    if (!(best > rel_thr * first && best > 0.0)) { rank = k; break; }
+    const int pk = bidx;
+    const double inv = rsqrt(best);
+    const double inv2 = inv * inv;
+    const c128* Gk = G + pk * ld;
+#pragma unroll
+    for (int t = 0; t < NW; ++t) {
+      if ((pk >> 5) == t) done[t] |= 1u << (pk & 31);
+      const int i = lane + 32 * t;
+      if (i < n && !((done[t] >> lane) & 1u)) {
+        const c128 g = Gk[i];
+        dreg[t] -= (g.re * g.re + g.im * g.im) * inv2;
+      }
+    }
+    c128* Lk = L + k * ld;
+    if (tid == 0) {
+      piv[k] = pk;
+      c128 d; d.re = best * inv; d.im = 0.0;
+      Lk[pk] = d;
+    }
+    // ---- G[i][j] -= L_k[i] conj(L_k[j]),  L_k[i] = conj(G[pk][i]) / sqrt(pivot), over the rows / columns
+    //      that are still free; 16 x (NT/16) thread tile, the first tile column also stores L_k
+    for (int i = tid / 16; i < n; i += NT / 16) {
+      if ((done[i >> 5] >> (i & 31)) & 1u) continue;
+      c128 a = Gk[i];
+      a.re *= inv; a.im *= -inv;
+      if ((tid & 15) == 0) Lk[i] = a;
+      for (int j = tid & 15; j < n; j += 16) {
+        if ((done[j >> 5] >> (j & 31)) & 1u) continue;
+        c128 b = Gk[j];
+        b.re *= inv; b.im *= -inv;
+        c128 g = G[i * ld + j];
+        g.re -= a.re * b.re + a.im * b.im;
+        g.im -= a.im * b.re - a.re * b.im;
+        G[i * ld + j] = g;
+      }
+    }
+    __syncthreads();
+  }
+  // the pivots stop at the numerical rank; the remaining rows keep their place behind them
+  if (tid == 0 && rank < n) {
+    int k = rank;
+    for (int i = 0; i < n; ++i)
+      if (!((done[i >> 5] >> (i & 31)) & 1u)) piv[k++] = i;
+  }
+  __syncthreads();
+  return rank;
+}
+
+// Register-tile variant for n <= 16*TS (shared-memory kernels, 256 threads as a 16 x 16 grid): thread
+// (ty, tx) keeps G[ty + 16 t][tx + 16 u], t, u < TS, in registers for the whole factorisation.  Per pivot
+// the owners of the pivot row publish it through a double-buffered shared row, everybody applies the
+// rank-1 update to its registers: ONE block barrier and no shared-memory read-modify-write per pivot.
+// Same outputs as chol_factor (L, piv, rank); G is read straight from global memory.
+template <bool CPLX, int TS>
+__device__ __forceinline__ int chol_factor_reg(const typename Elem<CPLX>::T* __restrict__ Gin, int nsplit, c128* L,
+                                               int n, int ld, int* piv, double rel_thr, c128* rowbuf) {
+  using T = typename Elem<CPLX>::T;
+  constexpr int NW = (16 * TS + 31) / 32;
+  const int tid = threadIdx.x, lane = tid & 31, tx = tid & 15, ty = tid >> 4;
+  c128 g[TS][TS];
+#pragma unroll
+  for (int t = 0; t < TS; ++t)
+#pragma unroll
+    for (int u = 0; u < TS; ++u) { g[t][u].re = 0.0; g[t][u].im = 0.0; }
+  // G = sum of the split-K partial Gram matrices; all loads of one slice are independent
+  for (int sp = 0; sp < nsplit; ++sp) {
+    const T* Gs = Gin + sp * n * n;
+#pragma unroll
+    for (int t = 0; t < TS; ++t)
+#pragma unroll
+      for (int u = 0; u < TS; ++u) {
+        const int i = ty + 16 * t, j = tx + 16 * u;
+        if (i < n && j < n) {
+          const T x = Elem<CPLX>::ld(Gs + i * n + j);
+          if constexpr (CPLX) { g[t][u].re += x.re; g[t][u].im += x.im; } else g[t][u].re += x;
+        }
+      }
+  }
+  unsigned long long done_lo = 0ull, done_hi = 0ull;      // pivoted rows (n <= 80 < 128)
+  auto is_done = [&](int i) -> bool { return ((i < 64 ? done_lo >> i : done_hi >> (i - 64)) & 1ull) != 0ull; };
+  double dreg[NW];
+#pragma unroll
+  for (int t = 0; t < NW; ++t) {
+    const int i = lane + 32 * t;
+    double d = -1.0;
+    if (i < n) {
+      d = 0.0;
+      for (int sp = 0; sp < nsplit; ++sp) {
+        if constexpr (CPLX) d += Elem<CPLX>::ld(Gin + sp * n * n + i * n + i).re;
+        else d += Elem<CPLX>::ld(Gin + sp * n * n + i * n + i);
+      }
+    }
+    dreg[t] = d;
+  }
+  double first = 0.0;
+  int rank = n;
+  for (int k = 0; k < n; ++k) {
+    double best = -1.0; int bidx = 0;
+#pragma unroll
+    for (int t = 0; t < NW; ++t) {
+      if (!is_done(lane + 32 * t) && dreg[t] > best) { best = dreg[t]; bidx = lane + 32 * t; }
+    }
+    const unsigned key = best > 0.0 ? (unsigned)(__double_as_longlong(best) >> 32) : 0u;
+    const unsigned top = __reduce_max_sync(0xffffffffu, key);
+    const int src = __ffs(__ballot_sync(0xffffffffu, key == top)) - 1;
+    best = __shfl_sync(0xffffffffu, best, src);
+    bidx = __shfl_sync(0xffffffffu, bidx, src);
+    if (k == 0) first = best;
+    if (!(best > rel_thr * first && best > 0.0)) { rank = k; break; }
+    const int pk = bidx;
+    const double inv = rsqrt(best);
+    c128* buf = rowbuf + (k & 1) * (16 * TS);
+#pragma unroll
+    for (int t = 0; t < TS; ++t) {
+      if (ty + 16 * t == pk) {               // static register slots: no dynamic indexing of g
+#pragma unroll
+        for (int u = 0; u < TS; ++u) buf[tx + 16 * u] = g[t][u];
+      }
+    }
+    __syncthreads();
+    c128 a[TS], b[TS];
+#pragma unroll
+    for (int t = 0; t < TS; ++t) {
+      a[t] = buf[ty + 16 * t]; a[t].re *= inv; a[t].im *= -inv;
+      b[t] = buf[tx + 16 * t]; b[t].re *= inv; b[t].im *= -inv;
+    }
+#pragma unroll
+    for (int t = 0; t < TS; ++t)
+#pragma unroll
+      for (int u = 0; u < TS; ++u) {
+        g[t][u].re -= a[t].re * b[u].re + a[t].im * b[u].im;
+        g[t][u].im -= a[t].im * b[u].re - a[t].re * b[u].im;
+      }
+    const double inv2 = inv * inv;
+    if (pk < 64) done_lo |= 1ull << pk; else done_hi |= 1ull << (pk - 64);
+#pragma unroll
+    for (int t = 0; t < NW; ++t) {
+      const int i = lane + 32 * t;
+      if (i < n && !is_done(i)) {
+        const c128 x = buf[i];
+        dreg[t] -= (x.re * x.re + x.im * x.im) * inv2;
+      }
+    }
+    c128* Lk = L + k * ld;
+    if (tx == 0) {
+#pragma unroll
+      for (int t = 0; t < TS; ++t) {
+        const int i = ty + 16 * t;
+        if (i < n && !is_done(i)) Lk[i] = a[t];
+      }
+    }
+    if (tid == 0) {
+      piv[k] = pk;
+      c128 d; d.re = best * inv; d.im = 0.0;
+      Lk[pk] = d;
+    }
+  }
+  if (tid == 0 && rank < n) {
+    int k = rank;
+    for (int i = 0; i < n; ++i)
+      if (!is_done(i)) piv[k++] = i;
+  }
+  __syncthreads();
+  return rank;
+}
+
+template <bool CPLX, int NT>
+__device__ __forceinline__ void load_gram(c128* G, const typename Elem<CPLX>::T* Gin, int nsplit, int n, int ld) {
+  using T = typename Elem<CPLX>::T;
+  for (int e = threadIdx.x; e < n * n; e += NT) {
+    const int i = e / n, j = e % n;
+    c128 v; v.re = 0.0; v.im = 0.0;
+    for (int sp = 0; sp < nsplit; ++sp) {
+      const T t = Elem<CPLX>::ld(Gin + sp * n * n + e);
+      if constexpr (CPLX) { v.re += t.re; v.im += t.im; } else v.re += t;
+    }
+    G[i * ld + j] = v;
+  }
+}
+
+// Whitening transform T = [L_r^{-1} 0] P^T from the pivoted Cholesky factor.  The inverse of the
+// r x r factor is built by groups of INV_G lanes per column (dot products across the group) into LiT
+// (transposed).  GLOB=false keeps G and LiT in shared memory (n <= EIG_MAXN), GLOB=true in a
+// caller-provided global scratch (L2-resident, n <= CHOL_MAXN).
+template <bool CPLX, int NT, bool GLOB, int TS>
 __global__ void __launch_bounds__(NT)
     chol_whiten_kernel(const typename Elem<CPLX>::T* __restrict__ Gb, typename Elem<CPLX>::T* __restrict__ Tb,
                        const int64_t* __restrict__ g_off, const int64_t* __restrict__ t_off,
-                       const int32_t* __restrict__ ns, double rel_thr, int32_t* __restrict__ kept,
+                       const int32_t* __restrict__ ns, int nsplit, double rel_thr, int32_t* __restrict__ kept,
                        c128* __restrict__ scratch, int64_t scratch_stride) {
   using T = typename Elem<CPLX>::T;
   extern __shared__ __align__(16) unsigned char sm_raw[];
@@ -664,96 +893,51 @@ __global__ void __launch_bounds__(NT)
   c128* G;
   if constexpr (GLOB) G = scratch + int64_t(blockIdx.x) * scratch_stride;
   else G = reinterpret_cast<c128*>(sm_raw);
-  c128* LiT = G + n * ld;
+  c128* L = G + n * ld;
   __shared__ int perm[GLOB ? CHOL_MAXN : EIG_MAXN];
-  __shared__ int rank_s, go_s;
-  __shared__ double first_s, inv_s;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const T* Gin = Gb + g_off[blockIdx.x];
-  for (int e = tid; e < n * n; e += NT) {
-    const int i = e / n, j = e % n;
-    c128 v;
-    if constexpr (CPLX) { const T t = Elem<CPLX>::ld(Gin + e); v.re = t.re; v.im = t.im; }
-    else { v.re = Elem<CPLX>::ld(Gin + e); v.im = 0.0; }
-    G[i * ld + j] = v;
+  __shared__ double invd[GLOB ? CHOL_MAXN : EIG_MAXN];
+  const int tid = threadIdx.x;
+  const bool stamp = tid == 0 && blockIdx.x == 0;
+  if (stamp) gtn_phase_clk[0] = clock64();
+  int r;
+  if constexpr (TS > 0) {
+    __shared__ c128 rowbuf[2 * 16 * (TS > 0 ? TS : 1)];
+    r = chol_factor_reg<CPLX, TS>(Gb + g_off[blockIdx.x], nsplit, L, n, ld, perm, rel_thr, rowbuf);
+  } else {
+    load_gram<CPLX, NT>(G, Gb + g_off[blockIdx.x], nsplit, n, ld);
+    __syncthreads();
+    r = chol_factor<NT, (GLOB ? CHOL_MAXN : EIG_MAXN)>(G, L, n, ld, perm, rel_thr);
   }
-  for (int i = tid; i < n; i += NT) perm[i] = i;
-  if (tid == 0) { rank_s = n; first_s = 0.0; }
+  if (stamp) gtn_phase_clk[1] = clock64();
+  for (int i = tid; i < r; i += NT) invd[i] = 1.0 / L[i * ld + perm[i]].re;
   __syncthreads();
-  for (int k = 0; k < n; ++k) {
-    if (warp == 0) {
-      // ---- pivot: arg max of the remaining diagonal (ties -> smallest original index)
-      double best = -1.0; int bpos = k, bidx = 0x7fffffff;
-      for (int pos = k + lane; pos < n; pos += 32) {
-        const int i = perm[pos];
-        const double d = G[i * ld + i].re;
-        if (d > best || (d == best && i < bidx)) { best = d; bpos = pos; bidx = i; }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-        const int op = __shfl_xor_sync(0xffffffffu, bpos, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
-        if (ob > best || (ob == best && oi < bidx)) { best = ob; bpos = op; bidx = oi; }
-      }
-      if (lane == 0) {
-        if (k == 0) first_s = best;
-        const bool ok = best > rel_thr * first_s && best > 0.0;
-        go_s = ok ? 1 : 0;
-        if (ok) {
-          const int t = perm[k]; perm[k] = perm[bpos]; perm[bpos] = t;
-          const double dkk = sqrt(best);
-          inv_s = 1.0 / dkk;
-          c128 d; d.re = dkk; d.im = 0.0;
-          G[bidx * ld + bidx] = d;
-        } else {
-          rank_s = k;
-        }
-      }
-    }
-    __syncthreads();
-    if (!go_s) break;
-    const int pk = perm[k];
-    const double inv = inv_s;
-    c128* Lk = G + pk * ld;
-    // ---- column k of L, in place in row pk:  L_k[i] = conj(G[pk][i]) / dkk
-    for (int pos = k + 1 + tid; pos < n; pos += NT) {
-      const int i = perm[pos];
-      c128 v = Lk[i];
-      v.re *= inv; v.im *= -inv;
-      Lk[i] = v;
-    }
-    __syncthreads();
-    // ---- G[i][j] -= L_k[i] conj(L_k[j]) over the remaining rows / columns
-    const int m = n - k - 1;
-    for (int e = tid; e < m * m; e += NT) {
-      const int i = perm[k + 1 + e / m], j = perm[k + 1 + e % m];
-      const c128 a = Lk[i], b = Lk[j];
-      c128 g = G[i * ld + j];
-      g.re -= a.re * b.re + a.im * b.im;
-      g.im -= a.im * b.re - a.re * b.im;
-      G[i * ld + j] = g;
-    }
-    __syncthreads();
-  }
-  __syncthreads();
-  const int r = rank_s;
-  // ---- LiT[c][i] = (L_r^{-1})[i][c]; L_r[i][j] = G[perm[j]][perm[i]] (i >= j). One warp per column.
-  for (int c = warp; c < r; c += NT / 32) {
-    c128* col = LiT + c * ld;
-    for (int i = c; i < r; ++i) {
+  // ---- LiT[c][i] = (L_r^{-1})[i][c] into the (now dead) storage of G; L_r[i][j] = L[j][perm[i]] (i >= j).
+  //      INV_G lanes per column: small n -> all columns in flight at once, large n -> longer dot products
+  c128* LiT = G;
+  constexpr int INV_G = GLOB ? 32 : 4;
+  const int sub = tid % INV_G;
+  for (int c0 = 0; c0 < r; c0 += NT / INV_G) {
+    const int c = c0 + tid / INV_G;
+    const bool live = c < r;
+    c128* col = LiT + (live ? c : 0) * ld;
+    for (int i = c0; i < r; ++i) {              // warp-uniform trip count; columns c > i just idle
       const int pi = perm[i];
       double sr = 0.0, si = 0.0;
-      for (int j = c + lane; j < i; j += 32) {
-        const c128 l = G[perm[j] * ld + pi], x = col[j];
-        sr -= l.re * x.re - l.im * x.im;
-        si -= l.re * x.im + l.im * x.re;
+      if (live && i > c) {
+        for (int j = c + sub; j < i; j += INV_G) {
+          const c128 l = L[j * ld + pi], x = col[j];
+          sr -= l.re * x.re - l.im * x.im;
+          si -= l.re * x.im + l.im * x.re;
+        }
       }
-      sr = warp_sum(sr);
-      si = warp_sum(si);
-      if (lane == 0) {
+#pragma unroll
+      for (int o = INV_G / 2; o > 0; o >>= 1) {
+        sr += __shfl_xor_sync(0xffffffffu, sr, o);
+        si += __shfl_xor_sync(0xffffffffu, si, o);
+      }
+      if (live && i >= c && sub == 0) {
         if (i == c) sr += 1.0;
-        const double d = 1.0 / G[pi * ld + pi].re;
+        const double d = invd[i];
         c128 o; o.re = sr * d; o.im = si * d;
         col[i] = o;
       }
@@ -761,6 +945,7 @@ __global__ void __launch_bounds__(NT)
     }
   }
   __syncthreads();
+  if (stamp) gtn_phase_clk[2] = clock64();
   if (tid == 0) kept[blockIdx.x] = r;
   T* Tout = Tb + t_off[blockIdx.x];
   for (int e = tid; e < n * n; e += NT) {
@@ -771,6 +956,117 @@ __global__ void __launch_bounds__(NT)
     if constexpr (CPLX) { T t; t.re = v.re; t.im = v.im; Elem<CPLX>::st(dst, t); }
     else Elem<CPLX>::st(dst, v.re);
   }
+  if (stamp) gtn_phase_clk[3] = clock64();
+}
+
+// Pre-rotation for the one-sided Jacobi SVD of a short-and-wide matrix B (n rows): from G = B B^H
+// compute a unitary T such that the rows of T B are orthogonal up to the accuracy a Gram matrix
+// allows.  G = P L L^H P^T (pivoted Cholesky, above); the rows of L are orthogonalised by one-sided
+// Jacobi entirely in shared memory (8 lanes per row pair, one block barrier per round), Z accumulates
+// the rotations and T = Z P^T.  The global Jacobi kernel then starts from T B and needs 2-3 sweeps
+// instead of 7-8; the singular values it delivers never go through G.
+constexpr int ROT_T = 256;
+template <bool CPLX, int TS>
+__global__ void __launch_bounds__(ROT_T)
+    gram_rotate_kernel(const typename Elem<CPLX>::T* __restrict__ Gb, typename Elem<CPLX>::T* __restrict__ Tb,
+                       const int64_t* __restrict__ g_off, const int64_t* __restrict__ t_off,
+                       const int32_t* __restrict__ ns, int nsplit, double rel_thr, double tol, int max_sweeps,
+                       int32_t* __restrict__ sweeps_out) {
+  using T = typename Elem<CPLX>::T;
+  constexpr int NT = ROT_T;
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  const int n = ns[blockIdx.x];
+  const int ld = n + 1;
+  c128* G = reinterpret_cast<c128*>(sm_raw);
+  c128* L = G + n * ld;
+  __shared__ int perm[EIG_MAXN];
+  __shared__ int rotated_s;
+  __shared__ double maxn_s;
+  const int tid = threadIdx.x;
+  __shared__ c128 rowbuf[2 * 16 * TS];
+  const bool stamp = tid == 0 && blockIdx.x == 0;
+  if (stamp) gtn_phase_clk[4] = clock64();
+  const int r = chol_factor_reg<CPLX, TS>(Gb + g_off[blockIdx.x], nsplit, L, n, ld, perm, rel_thr, rowbuf);
+  if (stamp) gtn_phase_clk[5] = clock64();
+  if (tid == 0) maxn_s = r > 0 ? L[perm[0]].re * L[perm[0]].re : 0.0;      // first pivot = max |row|^2
+  __syncthreads();
+  // M = L_r (n x r, rows in pivot order) into the dead storage of G
+  c128* M = G;
+  for (int e = tid; e < n * r; e += NT) {
+    const int a = e / r, b = e % r;
+    c128 v; v.re = 0.0; v.im = 0.0;
+    if (b <= a || a >= r) v = L[b * ld + perm[a]];
+    M[a * ld + b] = v;
+  }
+  __syncthreads();
+  c128* Z = L;
+  for (int e = tid; e < n * n; e += NT) {
+    c128 v; v.re = ((e / n) == (e % n)) ? 1.0 : 0.0; v.im = 0.0;
+    Z[(e / n) * ld + (e % n)] = v;
+  }
+  __syncthreads();
+  const int P = (n + 1) & ~1;
+  const int sub = tid & 7;
+  const double dead = 4e-30 * maxn_s;
+  int sweep = 0;
+  for (; sweep < max_sweeps && r > 0 && P >= 2; ++sweep) {
+    if (tid == 0) rotated_s = 0;
+    __syncthreads();
+    for (int round = 0; round < P - 1; ++round) {
+      for (int k0 = 0; k0 < P / 2; k0 += NT / 8) {
+        const int k = k0 + (tid >> 3);
+        int i = 0, j = 0;
+        bool valid = k < P / 2;
+        if (valid) {
+          if (k == 0) { i = P - 1; j = round; }
+          else { i = (round + k) % (P - 1); j = (round - k + (P - 1)) % (P - 1); }
+          valid = i < n && j < n;
+          if (i > j) { const int t = i; i = j; j = t; }
+        }
+        c128* x = M + i * ld;
+        c128* y = M + j * ld;
+        double a = 0, b = 0, cr = 0, ci = 0;
+        if (valid) {
+          for (int e = sub; e < r; e += 8) {
+            const c128 xv = x[e], yv = y[e];
+            a += xv.re * xv.re + xv.im * xv.im;
+            b += yv.re * yv.re + yv.im * yv.im;
+            cr += xv.re * yv.re + xv.im * yv.im;
+            ci += xv.im * yv.re - xv.re * yv.im;
+          }
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+          a += __shfl_xor_sync(0xffffffffu, a, o);
+          b += __shfl_xor_sync(0xffffffffu, b, o);
+          cr += __shfl_xor_sync(0xffffffffu, cr, o);
+          ci += __shfl_xor_sync(0xffffffffu, ci, o);
+        }
+        double cs, sn, phr, phi, tc;
+        if (valid && fmin(a, b) > dead && jacobi_rotation(a, b, cr, ci, tol, cs, sn, phr, phi, tc, nullptr)) {
+          for (int e = sub; e < r; e += 8) rot(x[e], y[e], cs, sn, phr, phi);
+          c128* zx = Z + i * ld;
+          c128* zy = Z + j * ld;
+          for (int e = sub; e < n; e += 8) rot(zx[e], zy[e], cs, sn, phr, phi);
+          if (sub == 0) rotated_s = 1;
+        }
+      }
+      __syncthreads();
+    }
+    if (!rotated_s) { ++sweep; break; }
+    __syncthreads();
+  }
+  if (tid == 0 && sweeps_out) sweeps_out[blockIdx.x] = sweep;
+  if (stamp) gtn_phase_clk[6] = clock64();
+  T* Tout = Tb + t_off[blockIdx.x];
+  for (int e = tid; e < n * n; e += NT) {
+    const int i = e / n, c = e % n;       // T[i][perm[c]] = Z[i][c]
+    const c128 v = Z[i * ld + c];
+    T* dst = Tout + int64_t(i) * n + perm[c];
+    if constexpr (CPLX) { T t; t.re = v.re; t.im = v.im; Elem<CPLX>::st(dst, t); }
+    else Elem<CPLX>::st(dst, v.re);
+  }
+  if (stamp) gtn_phase_clk[7] = clock64();
 }
 
 template <typename K>
@@ -785,9 +1081,10 @@ extern "C" int64_t gtn_chol_whiten_scratch_elems(int max_n) {
 }
 
 extern "C" int gtn_chol_whiten(const void* G, void* T, int dtype, const int64_t* g_off_dev,
-                               const int64_t* t_off_dev, const int32_t* n_dev, int nprob, int max_n,
+                               const int64_t* t_off_dev, const int32_t* n_dev, int nprob, int max_n, int nsplit,
                                double rel_thr, int32_t* kept_dev, void* scratch, void* stream) {
   if (nprob <= 0) return GTN_OK;
+  if (nsplit < 1) return GTN_ERR_BAD_ARG;
   if (max_n > CHOL_MAXN) return GTN_ERR_UNSUPPORTED;
   if (dtype != GTN_C128 && dtype != GTN_F64) return GTN_ERR_BAD_ARG;
   cudaStream_t s = (cudaStream_t)stream;
@@ -795,27 +1092,64 @@ extern "C" int gtn_chol_whiten(const void* G, void* T, int dtype, const int64_t*
     const size_t smem = size_t(2) * max_n * (max_n + 1) * 16 + 64;
     static size_t attr = 0;
     if (smem > attr) {
-      int e1 = set_smem(chol_whiten_kernel<true, CHOL_T_SMALL, false>, smem);
-      int e2 = set_smem(chol_whiten_kernel<false, CHOL_T_SMALL, false>, smem);
-      if (e1) return e1;
-      if (e2) return e2;
+      int e = set_smem(chol_whiten_kernel<true, CHOL_T_SMALL, false, 3>, smem);
+      if (!e) e = set_smem(chol_whiten_kernel<false, CHOL_T_SMALL, false, 3>, smem);
+      if (!e) e = set_smem(chol_whiten_kernel<true, CHOL_T_SMALL, false, 5>, smem);
+      if (!e) e = set_smem(chol_whiten_kernel<false, CHOL_T_SMALL, false, 5>, smem);
+      if (e) return e;
       attr = smem;
     }
-    if (dtype == GTN_C128)
-      chol_whiten_kernel<true, CHOL_T_SMALL, false><<<nprob, CHOL_T_SMALL, smem, s>>>(
-          (const c128*)G, (c128*)T, g_off_dev, t_off_dev, n_dev, rel_thr, kept_dev, nullptr, 0);
-    else
-      chol_whiten_kernel<false, CHOL_T_SMALL, false><<<nprob, CHOL_T_SMALL, smem, s>>>(
-          (const double*)G, (double*)T, g_off_dev, t_off_dev, n_dev, rel_thr, kept_dev, nullptr, 0);
+    const bool c = dtype == GTN_C128;
+#define GTN_CHOL_LAUNCH(CP, TS_, GT)                                                                       \
+  chol_whiten_kernel<CP, CHOL_T_SMALL, false, TS_><<<nprob, CHOL_T_SMALL, smem, s>>>(                      \
+      (const GT*)G, (GT*)T, g_off_dev, t_off_dev, n_dev, nsplit, rel_thr, kept_dev, nullptr, 0)
+    if (max_n <= 48) { if (c) GTN_CHOL_LAUNCH(true, 3, c128); else GTN_CHOL_LAUNCH(false, 3, double); }
+    else             { if (c) GTN_CHOL_LAUNCH(true, 5, c128); else GTN_CHOL_LAUNCH(false, 5, double); }
+#undef GTN_CHOL_LAUNCH
   } else {
     if (!scratch) return GTN_ERR_BAD_ARG;
     const int64_t stride = gtn_chol_whiten_scratch_elems(max_n);
     if (dtype == GTN_C128)
-      chol_whiten_kernel<true, CHOL_T_LARGE, true><<<nprob, CHOL_T_LARGE, 0, s>>>(
-          (const c128*)G, (c128*)T, g_off_dev, t_off_dev, n_dev, rel_thr, kept_dev, (c128*)scratch, stride);
+      chol_whiten_kernel<true, CHOL_T_LARGE, true, 0><<<nprob, CHOL_T_LARGE, 0, s>>>(
+          (const c128*)G, (c128*)T, g_off_dev, t_off_dev, n_dev, nsplit, rel_thr, kept_dev, (c128*)scratch, stride);
     else
-      chol_whiten_kernel<false, CHOL_T_LARGE, true><<<nprob, CHOL_T_LARGE, 0, s>>>(
-          (const double*)G, (double*)T, g_off_dev, t_off_dev, n_dev, rel_thr, kept_dev, (c128*)scratch, stride);
+      chol_whiten_kernel<false, CHOL_T_LARGE, true, 0><<<nprob, CHOL_T_LARGE, 0, s>>>(
+          (const double*)G, (double*)T, g_off_dev, t_off_dev, n_dev, nsplit, rel_thr, kept_dev, (c128*)scratch, stride);
   }
   return (int)cudaGetLastError();
 }
+
+extern "C" int gtn_gram_rotate(const void* G, void* T, int dtype, const int64_t* g_off_dev,
+                               const int64_t* t_off_dev, const int32_t* n_dev, int nprob, int max_n, int nsplit,
+                               double rel_thr, double tol, int max_sweeps, int32_t* sweeps_dev, void* stream) {
+  if (nprob <= 0) return GTN_OK;
+  if (nsplit < 1) return GTN_ERR_BAD_ARG;
+  if (max_n > EIG_MAXN) return GTN_ERR_UNSUPPORTED;
+  if (dtype != GTN_C128 && dtype != GTN_F64) return GTN_ERR_BAD_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t smem = size_t(2) * max_n * (max_n + 1) * 16 + 64;
+  static size_t attr = 0;
+  if (smem > attr) {
+    int e = set_smem(gram_rotate_kernel<true, 3>, smem);
+    if (!e) e = set_smem(gram_rotate_kernel<false, 3>, smem);
+    if (!e) e = set_smem(gram_rotate_kernel<true, 5>, smem);
+    if (!e) e = set_smem(gram_rotate_kernel<false, 5>, smem);
+    if (e) return e;
+    attr = smem;
+  }
+  const bool c = dtype == GTN_C128;
+#define GTN_ROT_LAUNCH(CP, TS_, GT)                                                                     \
+  gram_rotate_kernel<CP, TS_><<<nprob, ROT_T, smem, s>>>((const GT*)G, (GT*)T, g_off_dev, t_off_dev, n_dev, \
+                                                         nsplit, rel_thr, tol, max_sweeps, sweeps_dev)
+  if (max_n <= 48) { if (c) GTN_ROT_LAUNCH(true, 3, c128); else GTN_ROT_LAUNCH(false, 3, double); }
+  else             { if (c) GTN_ROT_LAUNCH(true, 5, c128); else GTN_ROT_LAUNCH(false, 5, double); }
+#undef GTN_ROT_LAUNCH
+  return (int)cudaGetLastError();
+}
+
+/* diagnostic: clock64 stamps of block 0 of the last gtn_chol_whiten ([0..3]: start, factorised, inverted,
+ * stored) and gtn_gram_rotate ([4..7]: start, factorised, rotated, stored) launches; synchronises. */
+extern "C" int gtn_debug_phase_clocks(long long* host_out8) {
+  return (int)cudaMemcpyFromSymbol(host_out8, gtn_phase_clk, sizeof(long long) * 8);
+}
+

@@ -133,7 +133,7 @@ int gtn_grouped_gemm(const void* A, const void* B, void* C, int dtype,
  * writes s (double), U = (Z^H permuted) (p x p) and Vh (p x q) into caller buffers.
  * The sweep loop runs on the host side of the ABI: gtn_jacobi_sweep launches the p-1 rounds of
  * one sweep for the whole batch and returns; `offdiag` (device double[batch]) receives
- * max |<w_i,w_j>| / (|w_i||w_j|) seen in that sweep.
+ * max |<w_i,w_j>|^2 / (|w_i|^2 |w_j|^2) over the pairs that were rotated in that sweep (0 = converged).
  * ------------------------------------------------------------------------------------------ */
 typedef struct {
   int64_t w_off; /* element offset of W_b inside W */
@@ -188,11 +188,28 @@ int gtn_small_eigh_whiten(const void* G, void* T, int dtype, const int64_t* g_of
  * P^T G P = L L^H (stopped at numerical rank r: remaining diagonal <= rel_thr * first pivot):
  * T = [L_r^{-1} 0] P^T, rows >= r zero, kept_dev[b] = r.  Three block barriers per pivot.
  * max_n <= 80: everything in shared memory (scratch may be NULL); 80 < max_n <= 512: the working
- * copies live in `scratch` (complex128 elements, nprob * gtn_chol_whiten_scratch_elems(max_n)). */
+ * copies live in `scratch` (complex128 elements, nprob * gtn_chol_whiten_scratch_elems(max_n)).
+ * nsplit >= 1: G_b is the SUM of nsplit consecutive n_b x n_b slices at g_off (split-K partial Gram
+ * matrices of the grouped GEMM, summed in a fixed order while loading). */
 int64_t gtn_chol_whiten_scratch_elems(int max_n);
 int gtn_chol_whiten(const void* G, void* T, int dtype, const int64_t* g_off_dev,
-                    const int64_t* t_off_dev, const int32_t* n_dev, int nprob, int max_n,
+                    const int64_t* t_off_dev, const int32_t* n_dev, int nprob, int max_n, int nsplit,
                     double rel_thr, int32_t* kept_dev, void* scratch, void* stream);
+
+/* Pre-rotation for the one-sided Jacobi SVD of a short-and-wide matrix B (n_b <= 80 rows): from the
+ * Gram matrix G_b = B B^H compute a UNITARY T_b (n_b x n_b) such that the rows of T_b B are orthogonal
+ * up to the accuracy a Gram matrix allows (pivoted Cholesky G = P L L^H P^T, one-sided Jacobi on the
+ * rows of L in shared memory, T = Z P^T; one CTA per matrix).  gtn_jacobi_persistent started from
+ * T_b B then needs 2-3 sweeps instead of 7-8, and the singular values it returns never go through G.
+ * sweeps_dev: int32[nprob] (may be NULL) receives the in-kernel sweep counts. */
+int gtn_gram_rotate(const void* G, void* T, int dtype, const int64_t* g_off_dev,
+                    const int64_t* t_off_dev, const int32_t* n_dev, int nprob, int max_n, int nsplit,
+                    double rel_thr, double tol, int max_sweeps, int32_t* sweeps_dev, void* stream);
+
+/* Diagnostic: clock64 stamps of CTA 0 of the last gtn_chol_whiten ([0..3]: start, factorised,
+ * inverted, stored) and gtn_gram_rotate ([4..7]: start, factorised, rotated, stored) launches.
+ * Synchronises the device; host_out8 is a HOST array of 8 int64. */
+int gtn_debug_phase_clocks(long long* host_out8);
 
 /* ------------------------------------------------------------------------------------------
  * Small element-wise / reduction helpers.
