@@ -746,8 +746,8 @@ def _svd_local(mats, ctxs, cutoff, kind, rule):
 def _svd_core(mats, ks, cutoff, kind):
     usv = None
     if cutoff is not None and kind == "svd" and TRUNCATED_SVD:
-        from ._engine import TRUNC_LMAX as LM
-        if all(k >= 1 and 3 * k // 2 + 8 <= LM and 4 * min(2 * k + 8, LM) <= min(m.shape) for k, m in zip(ks, mats)):
+        from ._engine import TRUNC_LMAX as LM, subspace_rows
+        if all(k >= 1 and 3 * k // 2 + 8 <= LM and 4 * min(subspace_rows(k), LM) <= min(m.shape) for k, m in zip(ks, mats)):
             usv = truncated_svd_batch(mats, ks)
             SVD_PATH_STATS["truncated" if usv is not None else "truncated_rejected"] += 1
     if usv is None:
