@@ -648,8 +648,11 @@ class GroupLayout:
 # ------------------------------------------------------------------------------------------------
 #  grouped GEMM
 # ------------------------------------------------------------------------------------------------
+SKINNY_MAX = int(__import__("os").environ.get("GTN_SKINNY_MAX", "128"))
+
+
 class GemmPlan:
-    def __init__(self, groups, dtype):
+    def __init__(self, groups, dtype, config=None):
         self.n = len(groups)
         self.tiles = 0
         self.flops = 0
@@ -672,7 +675,9 @@ class GemmPlan:
             a.m, a.n, a.k, a.batch = g["m"], g["n"], g["k"], g.get("batch", 1)
             a.alpha, a.beta = g.get("alpha", 1.0), g.get("beta", 0.0)
         # skinny problems (a side <= 48) get the 32x32 / deep-K configuration
-        self.config = 1 if all(min(g["m"], g["n"]) <= 48 for g in groups) else 0
+        if config is None:
+            config = 1 if all(min(g["m"], g["n"]) <= SKINNY_MAX for g in groups) else 0
+        self.config = config
         self.tiles = int(lib.gtn_gemm_plan_host(arr, self.n, dtype_code(dtype), self.config))
         self.dev = _to_dev_bytes(bytes(arr))
 

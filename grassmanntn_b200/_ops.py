@@ -386,10 +386,14 @@ def _plan_pair(inputs, output, ops, prog):
             key = (parallel.rank(), parallel.world())
             if key not in shard_cache:
                 sg, pieces = parallel.shard_groups(groups, key[0], key[1])
-                shard_cache[key] = (GemmPlan([g for g in sg if g["m"] > 0], A_.dtype), pieces)
+                shard_cache[key] = (GemmPlan([g for g in sg if g["m"] > 0], A_.dtype, config=0), pieces)
             splan, pieces = shard_cache[key]
-            splan.run(bufL, bufR, r.buf)
-            parallel.gather_blocks(r.buf, pieces)
+            # fused: the GEMM epilogue stores the tiles into every rank's output over NVLink peer memory;
+            # otherwise GEMM, then one in-place NCCL all-gather per block
+            if not (parallel.fused() and all(g.get("beta", 0.0) == 0.0 for g in groups)
+                    and parallel.gemm_allgather_fused(splan, bufL, bufR, r.buf)):
+                splan.run(bufL, bufR, r.buf)
+                parallel.gather_blocks(r.buf, pieces)
         else:
             plan.run(bufL, bufR, r.buf)
         if output is None:

@@ -72,11 +72,18 @@ __device__ __forceinline__ int find_group(const gtn_gemm_group* g, int ng, int64
   return lo;
 }
 
-template <bool CPLX, int BM, int BN, int AROW>
+// peer output buffers of the fused GEMM + all-gather (multi-GPU output-tile sharding): every rank's
+// copy of C, mapped into this process (NVLink peer memory)
+struct PeerBufs {
+  int n;
+  char* p[GTN_MAX_PEERS];
+};
+
+template <bool CPLX, int BM, int BN, int AROW, bool BCAST>
 __global__ void __launch_bounds__(NTHREADS)
     grouped_gemm_kernel(const char* __restrict__ Abase, const char* __restrict__ Bbase,
                         char* __restrict__ Cbase, const gtn_gemm_group* __restrict__ groups,
-                        int ngroups) {
+                        int ngroups, const PeerBufs peers) {
   using C = Cfg<CPLX, BM, BN, AROW>;
   constexpr int MT = C::MT, NT = C::NT, WM = BM / 2, WN = BN / 2;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -97,7 +104,8 @@ __global__ void __launch_bounds__(NTHREADS)
   const int m0 = tm * BM, n0 = tn * BN;
   const char* A = Abase + (grp.a_off + int64_t(bidx) * grp.batch_stride_a) * C::ELEM;
   const char* B = Bbase + (grp.b_off + int64_t(bidx) * grp.batch_stride_b) * C::ELEM;
-  char* Cp = Cbase + (grp.c_off + int64_t(bidx) * grp.batch_stride_c) * C::ELEM;
+  const int64_t c_byte_off = (grp.c_off + int64_t(bidx) * grp.batch_stride_c) * C::ELEM;
+  char* Cp = Cbase + c_byte_off;
   const int64_t lda = grp.lda, ldb = grp.ldb, ldc = grp.ldc;
 
   const int tid = threadIdx.x;
@@ -213,37 +221,52 @@ __global__ void __launch_bounds__(NTHREADS)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         if (c + e >= N) continue;
-        char* dst = Cp + (int64_t(r) * ldc + (c + e)) * C::ELEM;
+        const int64_t eoff = (int64_t(r) * ldc + (c + e)) * C::ELEM;
+        char* dst = Cp + eoff;
         if (CPLX) {
           double2 v = make_double2(alpha * cre[i][j][e], alpha * cim[CPLX ? i : 0][CPLX ? j : 0][e]);
-          if (beta != 0.0) {
-            const double2 o = *reinterpret_cast<const double2*>(dst);
-            v.x += beta * o.x; v.y += beta * o.y;
+          if constexpr (BCAST) {
+            // the result tile goes straight into every rank's copy of C: the NVLink stores overlap the
+            // DMMA work of the other resident CTAs, no separate all-gather pass over the output
+#pragma unroll 1
+            for (int pr = 0; pr < peers.n; ++pr)
+              *reinterpret_cast<double2*>(peers.p[pr] + c_byte_off + eoff) = v;
+          } else {
+            if (beta != 0.0) {
+              const double2 o = *reinterpret_cast<const double2*>(dst);
+              v.x += beta * o.x; v.y += beta * o.y;
+            }
+            *reinterpret_cast<double2*>(dst) = v;
           }
-          *reinterpret_cast<double2*>(dst) = v;
         } else {
           double v = alpha * cre[i][j][e];
-          if (beta != 0.0) v += beta * *reinterpret_cast<const double*>(dst);
-          *reinterpret_cast<double*>(dst) = v;
+          if constexpr (BCAST) {
+#pragma unroll 1
+            for (int pr = 0; pr < peers.n; ++pr)
+              *reinterpret_cast<double*>(peers.p[pr] + c_byte_off + eoff) = v;
+          } else {
+            if (beta != 0.0) v += beta * *reinterpret_cast<const double*>(dst);
+            *reinterpret_cast<double*>(dst) = v;
+          }
         }
       }
     }
   }
 }
 
-template <bool CPLX, int BM, int BN, int AROW>
+template <bool CPLX, int BM, int BN, int AROW, bool BCAST>
 int launch_cfg(const void* A, const void* B, void* C, const gtn_gemm_group* groups_dev, int ngroups,
-               int64_t total_tiles, cudaStream_t s) {
+               int64_t total_tiles, const PeerBufs& peers, cudaStream_t s) {
   using K = Cfg<CPLX, BM, BN, AROW>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(grouped_gemm_kernel<CPLX, BM, BN, AROW>,
+    cudaError_t e = cudaFuncSetAttribute(grouped_gemm_kernel<CPLX, BM, BN, AROW, BCAST>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  grouped_gemm_kernel<CPLX, BM, BN, AROW><<<dim3((unsigned)total_tiles), dim3(NTHREADS), K::SMEM, s>>>(
-      (const char*)A, (const char*)B, (char*)C, groups_dev, ngroups);
+  grouped_gemm_kernel<CPLX, BM, BN, AROW, BCAST><<<dim3((unsigned)total_tiles), dim3(NTHREADS), K::SMEM, s>>>(
+      (const char*)A, (const char*)B, (char*)C, groups_dev, ngroups, peers);
   return (int)cudaGetLastError();
 }
 
@@ -268,12 +291,28 @@ extern "C" int gtn_grouped_gemm(const void* A, const void* B, void* C, int dtype
   if (ngroups <= 0 || total_tiles <= 0) return GTN_OK;
   if (total_tiles > 2147483647LL) return GTN_ERR_BAD_ARG;
   cudaStream_t s = (cudaStream_t)stream;
+  PeerBufs none; none.n = 0;
   if (dtype == GTN_C128) {
-    if (config == 1) return launch_cfg<true, 32, 32, 512>(A, B, C, groups_dev, ngroups, total_tiles, s);
-    return launch_cfg<true, 64, 64, 128>(A, B, C, groups_dev, ngroups, total_tiles, s);
+    if (config == 1) return launch_cfg<true, 32, 32, 512, false>(A, B, C, groups_dev, ngroups, total_tiles, none, s);
+    return launch_cfg<true, 64, 64, 128, false>(A, B, C, groups_dev, ngroups, total_tiles, none, s);
   } else if (dtype == GTN_F64) {
-    if (config == 1) return launch_cfg<false, 32, 32, 512>(A, B, C, groups_dev, ngroups, total_tiles, s);
-    return launch_cfg<false, 64, 64, 128>(A, B, C, groups_dev, ngroups, total_tiles, s);
+    if (config == 1) return launch_cfg<false, 32, 32, 512, false>(A, B, C, groups_dev, ngroups, total_tiles, none, s);
+    return launch_cfg<false, 64, 64, 128, false>(A, B, C, groups_dev, ngroups, total_tiles, none, s);
   }
+  return GTN_ERR_BAD_ARG;
+}
+
+extern "C" int gtn_grouped_gemm_bcast(const void* A, const void* B, void* const* C_peers, int npeers, int dtype,
+                                      const gtn_gemm_group* groups_dev, int ngroups, int64_t total_tiles,
+                                      void* stream) {
+  if (ngroups <= 0 || total_tiles <= 0) return GTN_OK;
+  if (total_tiles > 2147483647LL || npeers < 1 || npeers > GTN_MAX_PEERS) return GTN_ERR_BAD_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  PeerBufs peers; peers.n = npeers;
+  for (int i = 0; i < npeers; ++i) peers.p[i] = (char*)C_peers[i];
+  if (dtype == GTN_C128)
+    return launch_cfg<true, 64, 64, 128, true>(A, B, nullptr, groups_dev, ngroups, total_tiles, peers, s);
+  if (dtype == GTN_F64)
+    return launch_cfg<false, 64, 64, 128, true>(A, B, nullptr, groups_dev, ngroups, total_tiles, peers, s);
   return GTN_ERR_BAD_ARG;
 }

@@ -19,17 +19,71 @@ GPU (replicas).  The reference has no distributed mode at all (SURVEY.md section
 import torch
 import torch.distributed as dist
 
-_state = {"on": False, "min_flops": 2.0e9, "gemm": True, "svd": True}
+_state = {"on": False, "min_flops": 2.0e9, "gemm": True, "svd": True, "fused": False}
+_symm = {}          # nbytes -> (symmetric uint8 tensor, handle, ctypes array of peer pointers)
+MAX_PEERS = 8       # GTN_MAX_PEERS of include/gtn_b200.h
 
 
-def enable(min_flops=2.0e9, gemm=True, svd=True):
-    """shard contractions with at least `min_flops` algorithmic flops and all sector decompositions"""
+def enable(min_flops=2.0e9, gemm=True, svd=True, fused=True):
+    """shard contractions with at least `min_flops` algorithmic flops and all sector decompositions.
+    fused=True (NCCL backend, <= 8 ranks, peer access): the sharded GEMM stores its result tiles straight
+    into every rank's output buffer over NVLink (gtn_grouped_gemm_bcast on torch symmetric memory) instead
+    of running an all-gather after the GEMM; falls back to the all-gather if symmetric memory is unavailable."""
     if not dist.is_available() or not dist.is_initialized():
         raise RuntimeError("grassmanntn_b200.parallel.enable(): torch.distributed is not initialised")
     _state["on"] = dist.get_world_size() > 1
     _state["min_flops"] = float(min_flops)
     _state["gemm"], _state["svd"] = bool(gemm), bool(svd)
+    _state["fused"] = bool(fused and _state["on"] and dist.get_backend() == "nccl"
+                           and dist.get_world_size() <= MAX_PEERS and torch.cuda.is_available())
     return _state["on"]
+
+
+def fused():
+    return _state["on"] and _state["fused"]
+
+
+def _symm_output(nbytes, device):
+    """symmetric (peer-mapped) staging buffer of the sharded contraction output, cached by size"""
+    ent = _symm.get(nbytes)
+    if ent is None:
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm_mem
+        group = dist.group.WORLD
+        try:
+            symm_mem.enable_symm_mem_for_group(group.group_name)
+        except Exception:
+            pass
+        t = symm_mem.empty(nbytes, dtype=torch.uint8, device=device)
+        hdl = symm_mem.rendezvous(t, group)
+        w = dist.get_world_size()
+        ptrs = (C.c_void_p * w)(*[int(p) for p in hdl.buffer_ptrs])
+        ent = _symm[nbytes] = (t, hdl, ptrs)
+    return ent
+
+
+def gemm_allgather_fused(splan, A, B, out):
+    """this rank's row tiles of every output block, stored by the GEMM epilogue into ALL ranks' copies of
+    the output (peer memory); `out` receives the complete result.  Returns False (nothing done) when the
+    symmetric buffer cannot be set up -- the caller then uses GEMM + all-gather."""
+    from ._cabi import check, lib
+    from ._engine import _ptr, _stream, dtype_code, prof_region
+    nbytes = out.numel() * out.element_size()
+    try:
+        t, hdl, ptrs = _symm_output(nbytes, out.device)
+    except Exception as exc:                      # no peer access / symmetric memory on this system
+        _state["fused"] = False
+        import warnings
+        warnings.warn("grassmanntn_b200.parallel: fused GEMM+all-gather unavailable (%s); using NCCL all-gather" % exc)
+        return False
+    hdl.barrier(channel=0)                        # every peer has copied the previous result out of its buffer
+    if splan.n and splan.tiles:
+        with prof_region("grouped_gemm_bcast", 1, splan.bytes, splan.flops):
+            check(lib.gtn_grouped_gemm_bcast(_ptr(A), _ptr(B), ptrs, dist.get_world_size(), dtype_code(A.dtype),
+                                             _ptr(splan.dev), splan.n, splan.tiles, _stream()), "gtn_grouped_gemm_bcast")
+    hdl.barrier(channel=1)                        # every rank's tiles have landed in this rank's buffer
+    out.view(torch.uint8).copy_(t[:nbytes])
+    return True
 
 
 def disable():

@@ -119,6 +119,16 @@ int gtn_grouped_gemm(const void* A, const void* B, void* C, int dtype,
                      const gtn_gemm_group* groups_dev, int ngroups, int64_t total_tiles,
                      int config, void* stream);
 
+/* Fused GEMM + all-gather for the multi-GPU output-tile sharding: same product as
+ * gtn_grouped_gemm (64x64 tiles, beta = 0), but every result element is stored at the same offset into
+ * EACH of the npeers output buffers C_peers[0..npeers) -- all ranks' copies of C mapped into this process
+ * (NVLink peer memory, e.g. torch symmetric memory), own copy included.  C_peers is a HOST array of
+ * device pointers.  The caller brackets the launch with cross-rank barriers. */
+#define GTN_MAX_PEERS 8
+int gtn_grouped_gemm_bcast(const void* A, const void* B, void* const* C_peers, int npeers, int dtype,
+                           const gtn_gemm_group* groups_dev, int ngroups, int64_t total_tiles,
+                           void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Batched one-sided Jacobi SVD (Hestenes) of the parity-sector matrices.
  *
