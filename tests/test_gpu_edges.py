@@ -1,0 +1,208 @@
+"""GPU edge cases and size-independent properties of the hot path (through the C ABI).
+
+Small cases are compared with the CPU oracle; cases at the bench sizes (chi = 32 ... 64 sector
+matrices, D = 32 tensors) use properties that do not need the oracle to finish: involutions of the
+sign+permute kernel (bit-exact), join/split and hconjugate round trips (bit-exact), linearity of the
+contraction, Eckart-Young for the truncated SVD (reference SortedSVD keeps the LARGEST singular values,
+__init__.py:3931-3951), Hermitian eig reconstruction."""
+import numpy as np
+import pytest
+
+import gtn_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(gtn, shape, stats, rng, cplx=True, trim=True):
+    o = O.random_dense(shape, stats, dtype=complex if cplx else float, rng=rng, skip_trimming=not trim)
+    return o, gtn.dense(o.data, statistics=stats)
+
+
+def _np(x):
+    return x.data.cpu().numpy()
+
+
+# ---------------------------------------------------------------- small / ragged shapes vs the oracle
+SMALL = [
+    ('ab->ba', [((2, 2), (1, -1))]),
+    ('ab->ba', [((1, 1), (1, -1))]),                       # one-element legs (index 0 only: even)
+    ('a,a', [((4,), (1,)), ((4,), (-1,))]),                # vector . vector -> scalar
+    ('ab,b->a', [((4, 8), (1, 1)), ((8,), (-1,))]),        # matrix . vector
+    ('ij,jk->ik', [((3, 5), (0, 0)), ((5, 2), (0, 0))]),   # purely bosonic, ragged dims
+    ('iaj,jbk->iabk', [((3, 2, 5), (0, 1, 0)), ((5, 4, 2), (0, -1, 0))]),   # fermions between bosons
+    ('abcdefgh->hgfedcba', [((2,) * 8, (1, -1, 1, -1, 1, -1, 1, -1))]),     # 8 legs (maximum super-axes)
+    ('abcdef,fedcba', [((2, 2, 2, 2, 2, 2), (1, 1, 1, -1, -1, -1)), ((2, 2, 2, 2, 2, 2), (1, 1, 1, -1, -1, -1))]),
+]
+
+
+@pytest.mark.parametrize("case", range(len(SMALL)))
+def test_small_and_ragged_einsum(gtn, case):
+    sub, ops = SMALL[case]
+    rng = np.random.RandomState(500 + case)
+    pairs = [_mk(gtn, s, st, rng, trim=False) for s, st in ops]
+    ref = O.einsum(sub, *[p[0] for p in pairs])
+    got = gtn.einsum(sub, *[p[1] for p in pairs])
+    if isinstance(ref, O.Dense):
+        assert got.shape == ref.shape and tuple(got.statistics) == tuple(ref.statistics)
+        assert np.abs(_np(got) - ref.data).max() <= 1e-12 * max(np.abs(ref.data).max(), 1.0)
+    else:
+        assert abs(got - ref) <= 1e-12 * max(abs(ref), 1.0)
+
+
+def test_einsum_errors(gtn):
+    rng = np.random.RandomState(3)
+    _, A = _mk(gtn, (4, 4), (1, -1), rng)
+    _, B = _mk(gtn, (2, 4), (1, -1), rng)
+    with pytest.raises(ValueError):
+        gtn.einsum('ab,bc->ac', A, B)            # contracted dimensions differ
+    with pytest.raises(ValueError):
+        gtn.einsum('ab,bc->ac', A)               # operand count
+    with pytest.raises(ValueError):
+        gtn.einsum('abc->cba', A)                # leg count
+    _, C = _mk(gtn, (4, 4), (-1, 1), rng)
+    with pytest.raises(ValueError):
+        gtn.einsum('ab,bc->ac', A, C)            # contraction of two non-conjugated legs (reference :1700-1740)
+
+
+def test_eig_rejects_non_hermitian(gtn):
+    rng = np.random.RandomState(4)
+    _, A = _mk(gtn, (4, 4, 4, 4), (1, 1, -1, -1), rng)
+    with pytest.raises(ValueError):
+        A.eig('ab|cd')
+
+
+def test_svd_cutoff_larger_than_rank_and_full(gtn):
+    rng = np.random.RandomState(5)
+    a, A = _mk(gtn, (4, 4, 4, 4), (1, 1, -1, -1), rng)
+    for cut in (None, 64, 3):
+        Ur, Sr, Vr = O.svd(a, 'ab|cd', cut)
+        U, S, V = A.svd('ab|cd', cut)
+        assert S.shape == Sr.shape
+        sg = np.sort(np.abs(np.diag(_np(S))))[::-1]
+        sr = np.sort(np.abs(np.diag(Sr.data)))[::-1]
+        assert np.abs(sg - sr).max() <= 1e-10 * sr[0]
+        if cut != 3:
+            rec = gtn.einsum('abx,xy,ycd->abcd', U, S, V)
+            assert np.abs(_np(rec) - a.data).max() <= 1e-12 * np.abs(a.data).max()
+
+
+def test_svd_of_zero_sector_and_rank_one(gtn):
+    """a tensor whose odd sector vanishes, and a rank-one tensor: rank rule s_i/(s_0+1e-14) > 1e-14
+    (reference __init__.py:3939-3941) must give the oracle's bond dimension"""
+    rng = np.random.RandomState(6)
+    a, _ = _mk(gtn, (4, 4, 4, 4), (1, 1, -1, -1), rng)
+    d = a.data.copy()
+    par = np.array([bin(i).count('1') & 1 for i in range(4)])
+    odd_rows = (par[:, None] ^ par[None, :]).astype(bool)
+    d[odd_rows] = 0.0                                       # kill every element with odd (a,b) parity
+    v = rng.rand(4, 4) + 1j * rng.rand(4, 4)
+    v[odd_rows] = 0.0
+    r1 = np.einsum('ab,cd->abcd', v, v.conj())
+    for data in (d, r1):
+        o = O.Dense(data, (1, 1, -1, -1))
+        A = gtn.dense(data, statistics=(1, 1, -1, -1))
+        Ur, Sr, Vr = O.svd(o, 'ab|cd', 16)         # int(16/2) = 8 per sector = the even sector's full rank
+        U, S, V = A.svd('ab|cd', 16)
+        assert S.shape == Sr.shape
+        sg = np.sort(np.abs(np.diag(_np(S))))[::-1]
+        sr = np.sort(np.abs(np.diag(Sr.data)))[::-1]
+        assert np.abs(sg - sr).max() <= 1e-10 * max(sr[0], 1e-300)
+        rec = gtn.einsum('abx,xy,ycd->abcd', U, S, V)
+        assert np.abs(_np(rec) - data).max() <= 1e-10 * np.abs(data).max()
+
+
+def test_block_non_power_of_two(gtn):
+    """block tensors with ragged even/odd extents (reference block format, __init__.py:242-344)"""
+    np.random.seed(7)
+    R0 = gtn.random_block((5, 6, 3, 4), (1, 1, -1, -1), dtype=complex)     # not trimmed (like the reference)
+    with pytest.raises(ValueError):
+        R0.svd('ij|kl')                                                    # Error[BlockSVD]: not Grassmann-even
+    A = gtn.trim_grassmann_odd(R0)
+    even = [b for b in np.ndindex(2, 2, 2, 2) if sum(b) % 2 == 0]
+    # transposition is an involution and preserves the norm
+    B = gtn.einsum('ijkl->lkji', A)
+    C = gtn.einsum('lkji->ijkl', B)
+    assert abs(B.norm - A.norm) <= 1e-13 * A.norm
+    for blk in even:
+        assert np.array_equal(C.data[blk].cpu().numpy(), A.data[blk].cpu().numpy())
+    # svd without cutoff reconstructs the tensor
+    U, S, V = A.svd('ij|kl')
+    R = gtn.einsum('ijx,xy,ykl->ijkl', U, S, V)
+    for blk in even:
+        x, y = R.data[blk].cpu().numpy(), A.data[blk].cpu().numpy()
+        assert np.abs(x - y).max() <= 1e-12 * max(A.norm, 1.0)
+
+
+# ---------------------------------------------------------------- properties at the bench sizes
+def test_permute_involution_bit_exact_D32(gtn):
+    rng = np.random.RandomState(8)
+    _, A = _mk(gtn, (32, 32, 32, 32), (1, 1, -1, -1), rng, trim=False)
+    for fwd, back in (('ijkl->jkli', 'jkli->ijkl'), ('ijkl->lkji', 'lkji->ijkl'), ('ijkl->kilj', 'kilj->ijkl')):
+        B = gtn.einsum(fwd, A)
+        C = gtn.einsum(back, B)
+        assert np.array_equal(_np(C), _np(A)), fwd
+        assert not np.array_equal(_np(B).ravel(), _np(A).ravel())
+
+
+def test_switch_round_trips_bit_exact_D32(gtn):
+    rng = np.random.RandomState(9)
+    _, A = _mk(gtn, (32, 32, 32, 32), (1, -1, -1, 1), rng, trim=False)
+    B = A.switch_format().switch_encoder().switch_encoder().switch_format()
+    assert np.array_equal(_np(B), _np(A))
+    H = A.hconjugate('ij|kl').hconjugate('ij|kl')
+    assert np.array_equal(_np(H), _np(A))
+    J = A.join_legs('(ij)(kl)', 'matrix', (1, -1))
+    K = J.split_legs('(ij)(kl)', (1, -1, -1, 1), (32, 32, 32, 32), (1, -1)).force_format('standard').force_encoder('canonical')
+    assert np.array_equal(_np(K), _np(A))
+
+
+def test_contraction_linearity_D32(gtn):
+    """einsum is bilinear: (A1 + 2 A2) . B == A1 . B + 2 A2 . B  to rounding, at D = chi = 32"""
+    rng = np.random.RandomState(10)
+    _, A1 = _mk(gtn, (32, 16, 16, 32), (1, 1, -1, 1), rng)
+    _, A2 = _mk(gtn, (32, 16, 16, 32), (1, 1, -1, 1), rng)
+    _, B = _mk(gtn, (32, 16, 16, 32), (-1, 1, -1, 1), rng)
+    lhs = gtn.einsum('lxzk,jzxi->ijkl', A1 + A2 * 2.0, B)
+    rhs = gtn.einsum('lxzk,jzxi->ijkl', A1, B) + gtn.einsum('lxzk,jzxi->ijkl', A2, B) * 2.0
+    assert np.abs(_np(lhs) - _np(rhs)).max() <= 1e-12 * np.abs(_np(rhs)).max()
+
+
+@pytest.mark.parametrize("chi,fmt", [(32, "dense"), (32, "block"), (64, "block"), (25, "block")])
+def test_truncated_svd_eckart_young(gtn, chi, fmt):
+    """|| T - U S V ||_F^2 == sum of the discarded s_i^2 of the sector matrices, and the kept values are
+    the largest ones of each sector (full LAPACK SVD of the two sector matrices as the yard-stick)"""
+    rng = np.random.RandomState(12)
+    D = 32
+    a = O.random_dense((D, D, D, D), (1, 1, -1, -1), dtype=complex, rng=rng)
+    # graded spectrum (physical tensors decay): damp the tensor along a diagonal direction
+    w = np.exp(-0.25 * np.arange(D))
+    data = a.data * w[:, None, None, None] * w[None, :, None, None] * w[None, None, :, None] * w[None, None, None, :]
+    A = gtn.dense(data, statistics=(1, 1, -1, -1))
+    X = A if fmt == "dense" else A.toblock()
+    U, S, V = X.svd('ab|cd', chi)
+    R = gtn.einsum('abx,xy,ycd->abcd', U, S, V)
+    Rd = _np(R if fmt == "dense" else R.todense())
+    err2 = float(np.sum(np.abs(Rd - data) ** 2))
+    # sector matrices in the parity-preserving order: rows (a,b) with p(a)+p(b) even / odd
+    par = np.array([bin(i).count('1') & 1 for i in range(D)])
+    rp = (par[:, None] ^ par[None, :]).ravel()
+    M = data.reshape(D * D, D * D)
+    disc = 0.0
+    kE = chi // 2 if fmt == "dense" else -(-chi // 2)
+    kO = chi // 2
+    for sec, k in ((0, kE), (1, kO)):
+        sub = M[np.ix_(rp == sec, rp == sec)]
+        s = np.linalg.svd(sub, compute_uv=False)
+        disc += float(np.sum(s[k:] ** 2))
+    tot = float(np.sum(np.abs(data) ** 2))
+    assert abs(err2 - disc) <= 1e-9 * tot, (err2, disc)
+
+
+def test_eig_reconstruction_D16(gtn):
+    rng = np.random.RandomState(13)
+    a, A = _mk(gtn, (16, 16, 16, 16), (1, 1, -1, -1), rng)
+    Ah = A.hconjugate('ab|cd')
+    Hm = gtn.einsum('abxy,xycd->abcd', A, Ah)            # Hermitian positive
+    U, L, V = Hm.eig('ab|cd')
+    R = gtn.einsum('abx,xy,ycd->abcd', U, L, V)
+    assert np.abs(_np(R) - _np(Hm)).max() <= 1e-10 * np.abs(_np(Hm)).max()

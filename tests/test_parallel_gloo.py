@@ -27,6 +27,7 @@ def _worker(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         assert parallel.enable(min_flops=0.0)
+        assert not parallel.fused()          # peer-store fusion needs NCCL + CUDA; gloo uses GEMM + all-gather
         rng = np.random.RandomState(0)                      # same data on every rank
         # two output blocks (m x n) = A (m x k) B (k x n) inside shared buffers, odd sizes on purpose
         shapes = [(7, 5, 6), (4, 3, 8)]
