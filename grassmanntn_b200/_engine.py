@@ -914,6 +914,7 @@ def subspace_rows(k):
 
 _trunc_fail = {}
 _trunc_rate = {}
+SVD_SITE = [None]          # call site of the decomposition being run (set by _ops.decompose_many)
 _trunc_plans = {}
 
 
@@ -1230,14 +1231,15 @@ def truncated_svd_batch(mats, ks, robust=False):
     P_ = [m.shape[0] for m in mats]
     Q_ = [m.shape[1] for m in mats]
     L_ = [min(p, q, subspace_rows(k), TRUNC_LMAX) for p, q, k in zip(P_, Q_, ks)]
-    key = (tuple(P_), tuple(Q_), tuple(ks), str(dt), str(dev))
+    pkey = (tuple(P_), tuple(Q_), tuple(ks), str(dt), str(dev))
+    key = (pkey, SVD_SITE[0])               # iteration hints / failure memory are per call site
     fails = _trunc_fail.get(key, 0)
     if fails >= 2 and not robust:
         # this shape keeps failing the certificate (flat spectrum): go straight to the full SVD, but
         # re-try every 16th call in case the spectrum has changed
         _trunc_fail[key] = fails + 1 if fails < 17 else 1
         return None
-    plan = _trunc_plan(key, P_, Q_, ks, L_, dt, dev)
+    plan = _trunc_plan(pkey, P_, Q_, ks, L_, dt, dev)
     plan.load(mats)
     hint = _trunc_iters_hint.get(key)
     # steady state: as many iterations as the last accepted run needed, one fewer when that run passed
@@ -1316,10 +1318,17 @@ def truncated_svd_batch(mats, ks, robust=False):
             if next_check > TRUNC_MAX_ITERS:
                 _trunc_fail[key] = _trunc_fail.get(key, 0) + 1
                 return None
+        if not ok and prev_worst is None and key in _trunc_rate and worst > 0:
+            # first failed check of this call: schedule the next one with the convergence factor measured on
+            # earlier calls from this site instead of checking again after a single iteration
+            need = math.log(max(TRUNC_TOL * 0.3, 1e-300) / worst) / math.log(_trunc_rate[key])
+            next_check = it + max(1, min(int(math.ceil(need)), 6))
         prev_worst, prev_it = worst, it
         if ok:
-            margin = worst <= TRUNC_TOL * _trunc_rate.get(key, 0.2)
-            _trunc_iters_hint[key] = max(it - 1, 0) if margin else it
+            # passed with a margin of d convergence factors: d - 1 fewer iterations next time (at most half)
+            rate = _trunc_rate.get(key, 0.2)
+            d = int(math.log(max(worst, 1e-16) / TRUNC_TOL) / math.log(rate)) if worst < TRUNC_TOL else 0
+            _trunc_iters_hint[key] = max(it - min(max(d - 1, 0), (it + 1) // 2), 0)
             _trunc_fail[key] = 0
             out = plan.finalize()
             return [(u, svals[b], v) for b, (u, _, v) in enumerate(out)]

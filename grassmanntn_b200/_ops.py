@@ -11,6 +11,8 @@ References: einsum_ds / einsum_block (reference __init__.py:1633-2306, :2346-294
 decompose_block (:4033-4308, :4425-4698, :4704-5289), hconjugate(_block) (:5300-5493, :5495-5955).
 """
 import math
+import os
+import sys
 
 import numpy as np
 import torch
@@ -21,6 +23,10 @@ from ._engine import (BT, FERMI, GemmPlan, GroupLayout, group_layout, PermutePla
                       batched_svd, truncated_svd_batch, bt_force_standard, bt_switch_format, build_job, dtype_code, gemm, lin_leg,
                       require_cuda, sigma_bits)
 from ._cabi import check, count, lib
+from . import _engine as _engine_mod
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+_CORE_FILES = ("__init__.py", "_ops.py", "_engine.py")
 from ._engine import prof_region
 
 NUMER_CUTOFF = 1.0e-14      # reference __init__.py:30 (module global numer_cutoff)
@@ -708,6 +714,14 @@ def decompose_many(items, cutoff, kind, rule):
     run (the two SVDs of a TRG step share their sweeps)."""
     ctxs = [_decompose_prepare(bt, nl, kind) for bt, nl in items]
     mats = [m for c in ctxs for m in c["mats"]]
+    # call site (first frame outside the package core): the truncated SVD remembers its converged iteration
+    # count per (batch shape, call site) -- the three SVDs of an ATRG step have the same shapes but very
+    # different spectra
+    f = sys._getframe(1)
+    while f is not None and os.path.basename(f.f_code.co_filename) in _CORE_FILES \
+            and os.path.dirname(f.f_code.co_filename) == _PKG_DIR:
+        f = f.f_back
+    _engine_mod.SVD_SITE[0] = (f.f_code.co_filename, f.f_lineno) if f is not None else None
     if parallel.active():
         # always through the owner/broadcast path in multi-GPU mode: the replicated operands of the
         # sharded contractions must be bit-identical on every rank (SVD gauges are not unique)
