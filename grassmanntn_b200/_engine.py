@@ -1322,7 +1322,7 @@ def truncated_svd_batch(mats, ks, robust=False):
             # first failed check of this call: schedule the next one with the convergence factor measured on
             # earlier calls from this site instead of checking again after a single iteration
             need = math.log(max(TRUNC_TOL * 0.3, 1e-300) / worst) / math.log(_trunc_rate[key])
-            next_check = it + max(1, min(int(math.ceil(need)), 6))
+            next_check = min(it + max(1, min(int(math.ceil(need)), 6)), TRUNC_MAX_ITERS)
         prev_worst, prev_it = worst, it
         if ok:
             # passed with a margin of d convergence factors: d - 1 fewer iterations next time (at most half)
