@@ -206,3 +206,28 @@ def test_eig_reconstruction_D16(gtn):
     U, L, V = Hm.eig('ab|cd')
     R = gtn.einsum('abx,xy,ycd->abcd', U, L, V)
     assert np.abs(_np(R) - _np(Hm)).max() <= 1e-10 * np.abs(_np(Hm)).max()
+
+
+def test_graph_replay_equals_eager_launches(gtn):
+    """the steady-state truncated-SVD schedule replayed as a CUDA graph must give what the same launches
+    give one by one (same kernels, same order): Tnorm of a TRG chain on the Z2 tensor, both ways"""
+    from grassmanntn_b200 import _engine as E, gauge2d as g
+    def chain(use_graphs):
+        old = E.USE_GRAPHS
+        E.USE_GRAPHS = use_graphs
+        E._trunc_iters_hint.clear(); E._trunc_rate.clear(); E._trunc_fail.clear()
+        try:
+            T = g.zcap(g.load_initial_tensor()).toblock()
+            out = []
+            for _ in range(6):
+                T, n = g.trg(T, 32)[:2]
+                out.append(float(n))
+            return out
+        finally:
+            E.USE_GRAPHS = old
+    a, b = chain(False), chain(True)
+    assert any(p.graphs for p in E._trunc_plans.values()), "no CUDA graph was captured"
+    for x, y in zip(a[:3], b[:3]):
+        assert abs(x - y) <= 1e-10 * abs(x), (a, b)          # the north-star tolerance on Tnorm
+    for x, y in zip(a[3:], b[3:]):                   # from the 4th step on the cut goes through exact multiplets (DESIGN section 7)
+        assert abs(x - y) <= 1e-6 * abs(x), (a, b)
