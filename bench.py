@@ -400,6 +400,9 @@ def other_workloads(gtn, torch, data, stats, args):
     # flavour-direction HOTRG step (example.py --Nf 2): 6-leg tensors with bosonic legs, eig, hconjugate
     T6 = gtn.dense(data, statistics=stats)
     out["hotrg3dz_dense_Zcut%d_ms" % args.chi] = timed(lambda X: g.hotrg3dz(T6, T6, args.chi)[0], T6, n=2, warm=1)
+    # BASELINE.json configs[2] "HOTRG chi=64": the same step at Zcut = 64 (parity with the reference to 1e-10 in
+    # tests/test_z2_golden.py::test_gpu_hotrg3dz_z2_chi64_vs_reference; the reference takes 372 s for it on one core)
+    out["hotrg3dz_z2_Zcut64_ms"] = timed(lambda X: g.hotrg3dz(T6, T6, 64)[0], T6, n=2, warm=1)
     out["einsum_sweep"] = einsum_sweep(gtn, torch, O)
     return out
 

@@ -287,11 +287,21 @@ class PermutePlan:
 # ------------------------------------------------------------------------------------------------
 #  block tensor
 # ------------------------------------------------------------------------------------------------
+_sigma_cache = {}
+
+
 def sigma_bits(pi, n):
     """sigma exponent bit of block element (pi, s), s < n: bit 1 of popcount(canonical index)
-    (reference sgn[blck][axis][sub_i] = param.sgn(param.encoder(i)), __init__.py:300-303)."""
-    c = canonical_of_block(pi, np.arange(n, dtype=np.int64))
-    return ((_popcount_vec(c) >> 1) & 1).astype(np.uint32)
+    (reference sgn[blck][axis][sub_i] = param.sgn(param.encoder(i)), __init__.py:300-303).
+    Returns a cached read-only array."""
+    v = _sigma_cache.get((pi, n))
+    if v is None:
+        c = canonical_of_block(pi, np.arange(n, dtype=np.int64))
+        v = ((_popcount_vec(c) >> 1) & 1).astype(np.uint32)
+        v.setflags(write=False)
+        if len(_sigma_cache) < 4096:
+            _sigma_cache[(pi, n)] = v
+    return v
 
 
 class BT:

@@ -183,3 +183,20 @@ def test_gpu_hotrg3dz_z2_loose(gtn, cut):
     for i in range(3):
         assert np.isfinite(rec[i][0]) and np.isfinite(abs(rec[i][2]))
         assert abs(rec[i][2] - complex(ref[i, 2], ref[i, 3])) <= 5e-2 * abs(rec[i][2])
+
+
+@pytest.mark.gpu
+def test_gpu_hotrg3dz_z2_chi64_vs_reference(gtn):
+    """'HOTRG chi=64' configuration (SURVEY 8d config 3 = flavour HOTRG hotrg3dz with --Dcutz 64, as in
+    example.py:144-154 with --Nf 2) on the Z2 tensor against the real reference
+    (tests/golden/make_z2_hotrg64.py).  At Zcut = 64 = 8*8 no multiplet is cut, so Tnorm and the free
+    energy must agree to the north-star tolerance 1e-10."""
+    ref = np.load(os.path.join(G, "z2_hotrg64.npz"))["rec"]
+    g = gtn.gauge2d
+    T0 = g.load_initial_tensor()
+    T, Tn, err = g.hotrg3dz(T0, T0, 64, error_test=True)
+    F = g.logZ(g.zcap(T), BC) + math.log(Tn)
+    assert T.shape == tuple(int(x) for x in ref[4:])
+    assert abs(Tn - ref[0]) <= 1e-10 * ref[0], (Tn, ref[0])
+    assert err <= 1e-12
+    assert abs(F - complex(ref[2], ref[3])) <= 1e-10 * abs(F), (F, ref[2], ref[3])
