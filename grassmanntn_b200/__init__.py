@@ -831,20 +831,29 @@ def _decompose_bond1(obj, bt, nl, left_is_bond):
     return tuple(outs)
 
 
-def svd_many(objs, string, cutoff=None):
+def svd_many(objs, string, cutoff=None, speculative=False, resume=None):
     """SVD of several tensors with the same partition string in ONE batched Jacobi run (not in the
     reference; used by gauge2d.trg / atrg2dy for the two independent decompositions of a step).
-    Returns [(U, S, V), ...] identical to [o.svd(string, cutoff) for o in objs]."""
+    Returns [(U, S, V), ...] identical to [o.svd(string, cutoff) for o in objs].
+    speculative=True returns ([(U, S, V), ...], pending): see _ops.decompose_many -- the results may rest on
+    an unverified truncated SVD; enqueue the dependent work, then call pending.verify() (pending may be None)
+    and repeat with resume=pending if it returns False."""
     left, right = _planner.split_partition(string, "svd")
     nl = len(left)
     bts = [(o._bt if isinstance(o, block) else o._get_bt()) for o in objs]
     for o, bt in zip(objs, bts):
         eff = [(bt.e[a] + bt.o[a]) if bt.stats[a] in fermi_type else bt.e[a] for a in range(bt.ndim)]
         if (list(bt.stats[:nl]) in ([-1], [1]) and eff[:nl] == [1]) or (list(bt.stats[nl:]) in ([-1], [1]) and eff[nl:] == [1]):
-            return [o.svd(string, cutoff) for o in objs]
+            res = [o.svd(string, cutoff) for o in objs]
+            return (res, None) if speculative else res
     rule = "block" if isinstance(objs[0], block) else "dense"
-    res = _ops.decompose_many([(bt, nl) for bt in bts], cutoff, "svd", rule)
-    return [tuple(_wrap_like(x, o) for x in r[:3]) for r, o in zip(res, objs)]
+    pending = None
+    if speculative:
+        res, pending = _ops.decompose_many([(bt, nl) for bt in bts], cutoff, "svd", rule, speculative=True)
+    else:
+        res = _ops.decompose_many([(bt, nl) for bt in bts], cutoff, "svd", rule, resume=resume)
+    out = [tuple(_wrap_like(x, o) for x in r[:3]) for r, o in zip(res, objs)]
+    return (out, pending) if speculative else out
 
 
 def svd(InpObj, string, cutoff=None, save_memory=False):

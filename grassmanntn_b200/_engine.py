@@ -1001,10 +1001,13 @@ class _TruncPlan:
         self.graphable = self.persistent and WHITEN == "chol"
         self.graphs, self.graph_launches = {}, {}
         self.host_sweeps = None
+        self.pending = None
+        self.epoch = 0                  # number of load() calls: identifies the run whose state the workspace holds
         torch.cuda.current_stream().synchronize()       # metadata uploads done before any capture
 
     # ---- launch sequences (enqueue only) -------------------------------------------------------
     def load(self, mats):
+        self.epoch += 1
         for b in range(self.nb):
             self.ws.view(self.hW[b]).copy_(mats[b])
         _ws_ctranspose(self.ws, list(zip(self.hW, self.hWh)))
@@ -1219,7 +1222,88 @@ def _trunc_plan(key, P_, Q_, ks, L_, dt, dev):
     return plan
 
 
-def truncated_svd_batch(mats, ks, robust=False):
+def _trunc_certificate(svals, res, kept_host, ks, L_):
+    """(ok, worst, reject) for the Ritz values `svals`, residual norms `res` and whitening ranks `kept_host`
+    of one check: ok = every kept triplet has residual <= TRUNC_TOL * s_0 AND the kept ones are the largest;
+    reject = the subspace lost directions while fewer than k triplets were found (count not trustworthy)."""
+    ok, o, worst = True, 0, 0.0
+    for b in range(len(svals)):
+        s = svals[b]
+        s0 = s[0] if len(s) else 0.0
+        nnz = int(np.sum(np.abs(s / (abs(s0) + 1e-14)) > 1e-14)) if len(s) else 0
+        kk = min(ks[b], nnz)
+        if kk > 0:
+            worst = max(worst, float(np.max(res[o: o + kk])) / max(s0, 1e-300))
+        if kk > 0 and np.max(res[o: o + kk]) > TRUNC_TOL * s0:
+            ok = False
+        if 0 < kk < len(s):
+            # the accepted triplets must also be the LARGEST ones: a Ritz pair j > kk with residual
+            # r_j stands for an exact singular value within r_j of it, so none of them may reach
+            # above the smallest accepted value (a direction that is still poorly represented in
+            # the subspace shows up here as a low Ritz value with a large residual)
+            hi = s[kk:] + res[o + kk: o + len(s)]
+            if np.max(hi) > s[kk - 1] + max(TRUNC_TOL * s0, res[o + kk - 1]):
+                ok = False
+                worst = max(worst, float(np.max(hi) - s[kk - 1]) / max(s0, 1e-300))
+        if nnz < ks[b] and kept_host is not None and kept_host[b] < L_[b] and nnz >= kept_host[b]:
+            # fewer triplets than requested AND the Gram whitening could not resolve every direction:
+            # a small-but-valid singular direction may have been dropped -> do not trust the count
+            return False, worst, True
+        o += L_[b]
+    return ok, worst, False
+
+
+def _trunc_accept(key, it, worst, spare=1):
+    """bookkeeping of an accepted run: remember the iteration count for this (shape, call site), lowered when
+    the run passed with a margin of d convergence factors (d - spare fewer next time, at most half).
+    Speculative runs keep two spare factors: a failed speculation costs the tail of the caller's step."""
+    rate = _trunc_rate.get(key, 0.2)
+    d = int(math.log(max(worst, 1e-16) / TRUNC_TOL) / math.log(rate)) if worst < TRUNC_TOL else 0
+    _trunc_iters_hint[key] = max(it - min(max(d - spare, 0), (it + 1) // 2), 0)
+    _trunc_fail[key] = 0
+
+
+class SpeculativeSVD:
+    """Result of a truncated SVD whose certificate has NOT been read back yet (the steady-state schedule
+    was replayed as a CUDA graph and nothing was synchronised).  `outs[b] = (U, s_dev, Vh)` are device
+    views valid until the next run of the same batch shape; the caller may enqueue dependent work and must
+    call verify() before trusting any of it: verify() synchronises, evaluates the certificate and the
+    assumption that every sector has at least k_b non-zero singular values, and returns True/False."""
+
+    def __init__(self, plan, key, it, ks, L_):
+        self.plan, self.key, self.it, self.ks, self.L_ = plan, key, it, ks, L_
+        fin = plan.finalize()
+        self.outs = [(u, plan.s_dev[o: o + l], v) for (u, _, v), o, l in zip(fin, plan.soff, plan.L_)]
+        self.svals = None
+        self.readback = None
+        self.ok = None
+        self.epoch = plan.epoch
+        plan.pending = self
+
+    def verify(self):
+        if self.ok is not None:
+            return self.ok
+        plan = self.plan
+        plan.pending = None
+        try:
+            svals, res, kept_host = plan.read()
+        except _cabi.GtnError:
+            self.ok = False
+            return False
+        ok, worst, reject = _trunc_certificate(svals, res, kept_host, self.ks, self.L_)
+        full = all(int(np.sum(np.abs(s / (abs(s[0]) + 1e-14)) > 1e-14)) >= k for s, k in zip(svals, self.ks))
+        truncated_svd_batch.last_iters = self.it
+        if DEBUG_TRUNC:
+            print("[trunc] speculative it", self.it, "worst %.2e" % worst, "ok", ok, "full rank", full, flush=True)
+        self.svals = svals
+        self.readback = (svals, res, kept_host)
+        self.ok = bool(ok and full and not reject)
+        if self.ok:
+            _trunc_accept(self.key, self.it, worst, spare=2)
+        return self.ok
+
+
+def truncated_svd_batch(mats, ks, robust=False, speculative=False, resume=None):
     """Top-k_b singular triplets of every matrix in `mats` by randomized subspace iteration:
          Yh = G Wh ; Qh = orth_rows(Yh) ; [Zh = Qh W ; Ph = orth_rows(Zh) ; Yh = Ph Wh ; Qh = orth_rows(Yh)]*
          B = Qh W (l x q) ; B = Ub S Vh (small one-sided Jacobi) ; U = Qh^H Ub
@@ -1250,22 +1334,37 @@ def truncated_svd_batch(mats, ks, robust=False):
         _trunc_fail[key] = fails + 1 if fails < 17 else 1
         return None
     plan = _trunc_plan(pkey, P_, Q_, ks, L_, dt, dev)
-    plan.load(mats)
+    if getattr(plan, "pending", None) is not None:
+        plan.pending.verify()               # an unverified speculative run still owns the read-back buffer
+    resumed = (resume is not None and resume.plan is plan and resume.readback is not None
+               and resume.epoch == plan.epoch and not robust)
+    if resumed:
+        # continue a speculative run whose certificate failed: the workspace still holds its iterate, the
+        # check has been read back already; bookkeeping goes to the speculative call site
+        key = resume.key
+    else:
+        plan.load(mats)
     hint = _trunc_iters_hint.get(key)
     # steady state: as many iterations as the last accepted run needed, one fewer when that run passed
     # with a margin of one iteration's convergence factor (a failed check costs ~4 iterations' worth).
     start_it = (hint or 0) if not robust else 0
     replayed = False
-    if (USE_GRAPHS and hint is not None and not robust and plan.cached and plan.graphable and not PROF.enabled):
+    if resumed:
+        replayed, start_it = True, resume.it
+    elif (USE_GRAPHS and hint is not None and not robust and plan.cached and plan.graphable and not PROF.enabled):
         try:
             g = plan.graph(start_it)
             g.replay()
             count(plan.graph_launches[start_it])
             replayed = True
-        except (RuntimeError, _cabi.GtnError):
+        except (RuntimeError, _cabi.GtnError) as exc:
+            if DEBUG_TRUNC:
+                print("[trunc] CUDA graph capture/replay failed, falling back to eager launches:", repr(exc)[:300], flush=True)
             plan.graphable = False
             plan.graphs.clear()
             torch.cuda.synchronize()
+    if speculative and replayed:
+        return SpeculativeSVD(plan, key, start_it, ks, L_)
     prev_worst, prev_it, next_check = None, None, 0
     for it in range(TRUNC_MAX_ITERS + 1):
         if replayed and it <= start_it:
@@ -1279,35 +1378,16 @@ def truncated_svd_batch(mats, ks, robust=False):
             if it < start_it or it < next_check:
                 continue
             plan.check_enqueue()
-        svals, res, kept_host = plan.read()
+        if resumed and it == start_it:
+            svals, res, kept_host = resume.readback
+        else:
+            svals, res, kept_host = plan.read()
         if robust:
             kept_host = None
-        ok, o = True, 0
-        worst = 0.0
-        for b in range(nb):
-            s = svals[b]
-            s0 = s[0] if len(s) else 0.0
-            nnz = int(np.sum(np.abs(s / (abs(s0) + 1e-14)) > 1e-14)) if len(s) else 0
-            kk = min(ks[b], nnz)
-            if kk > 0:
-                worst = max(worst, float(np.max(res[o: o + kk])) / max(s0, 1e-300))
-            if kk > 0 and np.max(res[o: o + kk]) > TRUNC_TOL * s0:
-                ok = False
-            if 0 < kk < len(s):
-                # the accepted triplets must also be the LARGEST ones: a Ritz pair j > kk with residual
-                # r_j stands for an exact singular value within r_j of it, so none of them may reach
-                # above the smallest accepted value (a direction that is still poorly represented in
-                # the subspace shows up here as a low Ritz value with a large residual)
-                hi = s[kk:] + res[o + kk: o + len(s)]
-                if np.max(hi) > s[kk - 1] + max(TRUNC_TOL * s0, res[o + kk - 1]):
-                    ok = False
-                    worst = max(worst, float(np.max(hi) - s[kk - 1]) / max(s0, 1e-300))
-            if nnz < ks[b] and kept_host is not None and kept_host[b] < L_[b] and nnz >= kept_host[b]:
-                # fewer triplets than requested AND the Gram whitening could not resolve every direction:
-                # a small-but-valid singular direction may have been dropped -> do not trust the count
-                truncated_svd_batch.last_iters = it
-                return None
-            o += L_[b]
+        ok, worst, reject = _trunc_certificate(svals, res, kept_host, ks, L_)
+        if reject:
+            truncated_svd_batch.last_iters = it
+            return None
         truncated_svd_batch.last_iters = it
         if DEBUG_TRUNC:
             print("[trunc] it", it, "worst %.2e" % worst, "ok", ok, "graph", replayed, "shapes", list(zip(P_, Q_)), "k", ks,
@@ -1335,11 +1415,7 @@ def truncated_svd_batch(mats, ks, robust=False):
             next_check = min(it + max(1, min(int(math.ceil(need)), 6)), TRUNC_MAX_ITERS)
         prev_worst, prev_it = worst, it
         if ok:
-            # passed with a margin of d convergence factors: d - 1 fewer iterations next time (at most half)
-            rate = _trunc_rate.get(key, 0.2)
-            d = int(math.log(max(worst, 1e-16) / TRUNC_TOL) / math.log(rate)) if worst < TRUNC_TOL else 0
-            _trunc_iters_hint[key] = max(it - min(max(d - 1, 0), (it + 1) // 2), 0)
-            _trunc_fail[key] = 0
+            _trunc_accept(key, it + (1 if resumed else 0), worst, spare=2 if resumed else 1)
             out = plan.finalize()
             return [(u, svals[b], v) for b, (u, _, v) in enumerate(out)]
     _trunc_fail[key] = _trunc_fail.get(key, 0) + 1

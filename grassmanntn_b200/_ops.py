@@ -555,7 +555,7 @@ def _decompose_prepare(bt, nl, kind):
     return dict(locals())
 
 
-def _decompose_finish(ctx, usv, cutoff, kind, rule):
+def _decompose_finish(ctx, usv, cutoff, kind, rule, spec=False):
     bt, nl, this_fmt = ctx["bt"], ctx["nl"], ctx["this_fmt"]
     Rl, Cl, fR, fC = ctx["Rl"], ctx["Cl"], ctx["fR"], ctx["fC"]
     layR, layC, sectors, rows, cols = ctx["layR"], ctx["layC"], ctx["sectors"], ctx["rows"], ctx["cols"]
@@ -570,7 +570,8 @@ def _decompose_finish(ctx, usv, cutoff, kind, rule):
             cuts = [None, None] if cutoff is None else [int(math.ceil(cutoff / 2)), int(math.floor(cutoff / 2))]
     else:
         cuts = [cutoff]
-    keep = [_rank_rule(usv[i][1], cuts[i]) for i in range(len(sectors))]
+    # spec: the singular values are still on the device -- assume every sector keeps its full cut (verified later)
+    keep = list(cuts) if spec else [_rank_rule(usv[i][1], cuts[i]) for i in range(len(sectors))]
     if len(sectors) == 2:
         d = max(keep)
         if rule == "dense":
@@ -686,8 +687,23 @@ def _decompose_finish(ctx, usv, cutoff, kind, rule):
     Sbt = BT((bond_stat[1], bond_stat[0]), (dims_x[0],) * 2, (dims_x[1],) * 2, bt.dtype)
     spats = [(0, 0), (1, 1)] if two else [()]
     Sbt.alloc([p for p in spats if Sbt.block_size(p) > 0], zero=True)
-    host = np.zeros(max(Sbt.buf.numel(), 1), dtype=np.complex128 if bt.dtype == torch.complex128 else np.float64)
-    for i, s in enumerate(sectors):
+    if spec:
+        # diag(sigma(x) * s) scattered on the device from the device-resident Ritz values
+        for i, s in enumerate(sectors):
+            k = keep[i]
+            p = (s, s) if two else ()
+            if k == 0 or p not in Sbt.off:
+                continue
+            dd = dims_x[s] if two else dims_x[0]
+
+            def build_idx(s=s, k=k, dd=dd, p=p):
+                sg = (1 - 2 * sigma_bits(s, k).astype(np.int64)) if two else np.ones(k, dtype=np.int64)
+                return (torch.from_numpy(Sbt.off[p] + np.arange(k, dtype=np.int64) * (dd + 1)).to(dev),
+                        torch.from_numpy(sg.astype(np.float64)).to(dev))
+            idx, sgd = _cached(("specS", two, s, k, dd, Sbt.off[p], str(dev)), build_idx)
+            Sbt.buf.index_copy_(0, idx, (usv[i][1][:k] * sgd).to(Sbt.buf.dtype))
+    host = np.zeros(max(Sbt.buf.numel(), 1) if not spec else 0, dtype=np.complex128 if bt.dtype == torch.complex128 else np.float64)
+    for i, s in enumerate(sectors if not spec else []):
         k = keep[i]
         p = (s, s) if two else ()
         if k == 0 or p not in Sbt.off:
@@ -699,7 +715,7 @@ def _decompose_finish(ctx, usv, cutoff, kind, rule):
             vals = np.real(vals)
         idx = Sbt.off[p] + np.arange(k) * (dd + 1)
         host[idx] = vals
-    if Sbt.buf.numel() > 0 and host.size > 0:
+    if not spec and Sbt.buf.numel() > 0 and host.size > 0:
         Sbt.buf.copy_(torch.from_numpy(host[: Sbt.buf.numel()]))
     outs = [Ubt, Sbt, Vbt]
     if this_fmt == "matrix":
@@ -709,9 +725,14 @@ def _decompose_finish(ctx, usv, cutoff, kind, rule):
 
 
 
-def decompose_many(items, cutoff, kind, rule):
+def decompose_many(items, cutoff, kind, rule, speculative=False, resume=None):
     """items: list of (bt, nl).  All sector matrices of all items go through ONE batched Jacobi
-    run (the two SVDs of a TRG step share their sweeps)."""
+    run (the two SVDs of a TRG step share their sweeps).
+    speculative=True returns (outs, pending): when the truncated SVD could replay its steady-state CUDA graph,
+    U, S, V are assembled on the device under the assumption 'certificate passes, every sector keeps its full
+    cut' WITHOUT synchronising; the caller enqueues the rest of its step and must call pending.verify()
+    (False -> repeat the decomposition with resume=pending: the iteration continues from the workspace state
+    of the failed run).  pending is None when nothing was speculated."""
     ctxs = [_decompose_prepare(bt, nl, kind) for bt, nl in items]
     mats = [m for c in ctxs for m in c["mats"]]
     # call site (first frame outside the package core): the truncated SVD remembers its converged iteration
@@ -731,14 +752,14 @@ def decompose_many(items, cutoff, kind, rule):
             n = len(c["mats"])
             outs.append(_decompose_finish(c, usv[k:k + n], cutoff, kind, rule))
             k += n
-        return outs
-    usv = _svd_local(mats, ctxs, cutoff, kind, rule)
+        return (outs, None) if speculative else outs
+    usv, pending = _svd_local(mats, ctxs, cutoff, kind, rule, speculative, resume)
     outs, k = [], 0
     for c in ctxs:
         n = len(c["mats"])
-        outs.append(_decompose_finish(c, usv[k:k + n], cutoff, kind, rule))
+        outs.append(_decompose_finish(c, usv[k:k + n], cutoff, kind, rule, spec=pending is not None))
         k += n
-    return outs
+    return (outs, pending) if speculative else outs
 
 
 def _sector_cuts(ctxs, cutoff, rule):
@@ -760,27 +781,32 @@ def _svd_distributed(mats, ctxs, cutoff, kind, rule):
     mine = [i for i in range(len(mats)) if i % w == r]
     res = {}
     if mine:
-        sub = _svd_core([mats[i] for i in mine], [ks[i] for i in mine], cutoff, kind)
+        sub, _ = _svd_core([mats[i] for i in mine], [ks[i] for i in mine], cutoff, kind)
         res = {i: sub[j] for j, i in enumerate(mine)}
     return parallel.broadcast_usv(res, len(mats), mats[0].device, mats[0].dtype)
 
 
-def _svd_local(mats, ctxs, cutoff, kind, rule):
+def _svd_local(mats, ctxs, cutoff, kind, rule, speculative=False, resume=None):
     ks = _sector_cuts(ctxs, cutoff, rule) if cutoff is not None else [None] * len(mats)
-    return _svd_core(mats, ks, cutoff, kind)
+    return _svd_core(mats, ks, cutoff, kind, speculative, resume)
 
 
-def _svd_core(mats, ks, cutoff, kind):
+def _svd_core(mats, ks, cutoff, kind, speculative=False, resume=None):
+    """returns (usv, pending): pending is an _engine.SpeculativeSVD when the truncated path was replayed
+    without reading its certificate back (usv[b][1] is then a DEVICE vector of Ritz values)"""
     usv = None
     if cutoff is not None and kind == "svd" and TRUNCATED_SVD:
         from ._engine import TRUNC_LMAX as LM, subspace_rows
         if all(k >= 1 and 3 * k // 2 + 8 <= LM and 4 * min(subspace_rows(k), LM) <= min(m.shape) for k, m in zip(ks, mats)):
-            usv = truncated_svd_batch(mats, ks)
+            usv = truncated_svd_batch(mats, ks, speculative=speculative, resume=resume)
+            if isinstance(usv, _engine_mod.SpeculativeSVD):
+                SVD_PATH_STATS["truncated"] += 1
+                return usv.outs, usv
             SVD_PATH_STATS["truncated" if usv is not None else "truncated_rejected"] += 1
     if usv is None:
         usv = batched_svd(mats)
         SVD_PATH_STATS["full"] += 1
-    return usv
+    return usv, None
 
 
 def decompose_bt(bt, nl, cutoff, kind, rule):

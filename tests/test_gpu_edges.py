@@ -231,3 +231,32 @@ def test_graph_replay_equals_eager_launches(gtn):
         assert abs(x - y) <= 1e-10 * abs(x), (a, b)          # the north-star tolerance on Tnorm
     for x, y in zip(a[3:], b[3:]):                   # from the 4th step on the cut goes through exact multiplets
         assert abs(x - y) <= 1e-6 * abs(x), (a, b)
+
+
+def test_speculative_trg_step_and_misspeculation(gtn):
+    """gauge2d.trg enqueues the rest of the step behind the replayed SVD graph and verifies the certificate
+    at the end.  (a) same Tnorm as the non-speculative step; (b) a wrong iteration hint (certificate must
+    fail) is caught by verify() and the step is repeated: results unchanged."""
+    from grassmanntn_b200 import _engine as E, gauge2d as g
+    def chain(spec, sabotage=False):
+        old = g.SPECULATE
+        g.SPECULATE = spec
+        E._trunc_iters_hint.clear(); E._trunc_rate.clear(); E._trunc_fail.clear()
+        try:
+            T = g.zcap(g.load_initial_tensor()).toblock()
+            out = []
+            for i in range(5):
+                if sabotage and i >= 3:
+                    for k in list(E._trunc_iters_hint):
+                        E._trunc_iters_hint[k] = 0           # far too few iterations: the certificate fails
+                T, n = g.trg(T, 32)[:2]
+                out.append(float(n))
+            return out
+        finally:
+            g.SPECULATE = old
+    ref = chain(False)
+    for other in (chain(True), chain(True, sabotage=True)):
+        for x, y in zip(ref[:3], other[:3]):
+            assert abs(x - y) <= 1e-10 * abs(x), (ref, other)
+        for x, y in zip(ref[3:], other[3:]):             # from the 4th step on the cut goes through exact multiplets
+            assert abs(x - y) <= 1e-6 * abs(x), (ref, other)
