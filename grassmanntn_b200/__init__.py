@@ -831,13 +831,14 @@ def _decompose_bond1(obj, bt, nl, left_is_bond):
     return tuple(outs)
 
 
-def svd_many(objs, string, cutoff=None, speculative=False, resume=None):
+def svd_many(objs, string, cutoff=None, speculative=False, resume=None, site=None):
     """SVD of several tensors with the same partition string in ONE batched Jacobi run (not in the
     reference; used by gauge2d.trg / atrg2dy for the two independent decompositions of a step).
     Returns [(U, S, V), ...] identical to [o.svd(string, cutoff) for o in objs].
     speculative=True returns ([(U, S, V), ...], pending): see _ops.decompose_many -- the results may rest on
     an unverified truncated SVD; enqueue the dependent work, then call pending.verify() (pending may be None)
-    and repeat with resume=pending if it returns False."""
+    and repeat with resume=pending if it returns False.  `site` tags the call for the truncated SVD's per-site
+    memory (iteration hints, speculative workspace) when several decompositions share one calling line."""
     left, right = _planner.split_partition(string, "svd")
     nl = len(left)
     bts = [(o._bt if isinstance(o, block) else o._get_bt()) for o in objs]
@@ -849,9 +850,9 @@ def svd_many(objs, string, cutoff=None, speculative=False, resume=None):
     rule = "block" if isinstance(objs[0], block) else "dense"
     pending = None
     if speculative:
-        res, pending = _ops.decompose_many([(bt, nl) for bt in bts], cutoff, "svd", rule, speculative=True)
+        res, pending = _ops.decompose_many([(bt, nl) for bt in bts], cutoff, "svd", rule, speculative=True, site=site)
     else:
-        res = _ops.decompose_many([(bt, nl) for bt in bts], cutoff, "svd", rule, resume=resume)
+        res = _ops.decompose_many([(bt, nl) for bt in bts], cutoff, "svd", rule, resume=resume, site=site)
     out = [tuple(_wrap_like(x, o) for x in r[:3]) for r, o in zip(res, objs)]
     return (out, pending) if speculative else out
 

@@ -1270,8 +1270,8 @@ class SpeculativeSVD:
     call verify() before trusting any of it: verify() synchronises, evaluates the certificate and the
     assumption that every sector has at least k_b non-zero singular values, and returns True/False."""
 
-    def __init__(self, plan, key, it, ks, L_):
-        self.plan, self.key, self.it, self.ks, self.L_ = plan, key, it, ks, L_
+    def __init__(self, plan, key, it, ks, L_, pkey=None):
+        self.plan, self.key, self.it, self.ks, self.L_, self.pkey = plan, key, it, ks, L_, pkey
         fin = plan.finalize()
         self.outs = [(u, plan.s_dev[o: o + l], v) for (u, _, v), o, l in zip(fin, plan.soff, plan.L_)]
         self.svals = None
@@ -1279,6 +1279,14 @@ class SpeculativeSVD:
         self.ok = None
         self.epoch = plan.epoch
         plan.pending = self
+
+    def discard(self):
+        """Drop a run whose INPUT turned out to be unverified (an earlier decomposition of the same step failed
+        its certificate): no read-back, no bookkeeping."""
+        if self.ok is None:
+            self.ok = False
+            if self.plan.pending is self:
+                self.plan.pending = None
 
     def verify(self):
         if self.ok is not None:
@@ -1333,7 +1341,12 @@ def truncated_svd_batch(mats, ks, robust=False, speculative=False, resume=None):
         # re-try every 16th call in case the spectrum has changed
         _trunc_fail[key] = fails + 1 if fails < 17 else 1
         return None
-    plan = _trunc_plan(pkey, P_, Q_, ks, L_, dt, dev)
+    # speculative callers get a workspace of their own per call site: the three same-shape SVDs of an ATRG step
+    # are then in flight behind each other without waiting for one another's certificate
+    if resume is not None and resume.pkey == pkey and not robust:
+        plan = resume.plan
+    else:
+        plan = _trunc_plan((pkey, SVD_SITE[0]) if speculative else pkey, P_, Q_, ks, L_, dt, dev)
     if getattr(plan, "pending", None) is not None:
         plan.pending.verify()               # an unverified speculative run still owns the read-back buffer
     resumed = (resume is not None and resume.plan is plan and resume.readback is not None
@@ -1364,7 +1377,7 @@ def truncated_svd_batch(mats, ks, robust=False, speculative=False, resume=None):
             plan.graphs.clear()
             torch.cuda.synchronize()
     if speculative and replayed:
-        return SpeculativeSVD(plan, key, start_it, ks, L_)
+        return SpeculativeSVD(plan, key, start_it, ks, L_, pkey)
     prev_worst, prev_it, next_check = None, None, 0
     for it in range(TRUNC_MAX_ITERS + 1):
         if replayed and it <= start_it:

@@ -725,7 +725,7 @@ def _decompose_finish(ctx, usv, cutoff, kind, rule, spec=False):
 
 
 
-def decompose_many(items, cutoff, kind, rule, speculative=False, resume=None):
+def decompose_many(items, cutoff, kind, rule, speculative=False, resume=None, site=None):
     """items: list of (bt, nl).  All sector matrices of all items go through ONE batched Jacobi
     run (the two SVDs of a TRG step share their sweeps).
     speculative=True returns (outs, pending): when the truncated SVD could replay its steady-state CUDA graph,
@@ -743,6 +743,8 @@ def decompose_many(items, cutoff, kind, rule, speculative=False, resume=None):
             and os.path.dirname(f.f_code.co_filename) == _PKG_DIR:
         f = f.f_back
     _engine_mod.SVD_SITE[0] = (f.f_code.co_filename, f.f_lineno) if f is not None else None
+    if site is not None:
+        _engine_mod.SVD_SITE[0] = site          # explicit tag (a driver with several decompositions behind one helper)
     if parallel.active():
         # always through the owner/broadcast path in multi-GPU mode: the replicated operands of the
         # sharded contractions must be bit-identical on every rank (SVD gauges are not unique)

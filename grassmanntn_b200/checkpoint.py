@@ -1,0 +1,147 @@
+"""On-disk format for long coarse-graining runs: tensor checkpoints and a per-step observable log.
+
+The reference keeps nothing on disk (no checkpoint / resume; example.py prints one line
+per step and loses the tensor when the process ends).  SURVEY.md section 8(f) row 4 asks for a format that makes
+chi = 128..256 runs resumable and comparable:
+
+* `save_tensor` / `load_tensor` -- one `.npz` per tensor holding the parity-blocked device buffer exactly as it
+  lives in HBM (`_engine.BT`: one contiguous buffer + block offsets; only the stored, i.e. even-parity, blocks),
+  its statistics / even / odd dimensions / format, the container kind (dense | block, encoder) and free-form
+  metadata.  Loading restores the same bits: a resumed run continues bit-identically.
+* `RunLog` -- JSON-lines file, one record per coarse-graining step with the columns example.py prints
+  (reference example.py:158-196): process, volume, F (real, imag), shape, trace error, Tnorm, seconds.
+* `gauge2d.coarse_grain(..., log=, checkpoint_dir=, resume=)` uses both.
+
+Host-side plumbing only (numpy + json); nothing here launches a kernel.
+"""
+import json
+import os
+import time
+
+import numpy as np
+import torch
+
+from . import _engine
+
+FORMAT_VERSION = 1
+
+
+def _bt_of(T):
+    from . import block, dense
+    if isinstance(T, block):
+        return T._bt, "block", None
+    if isinstance(T, dense):
+        return T._get_bt(), "dense", T.encoder
+    raise TypeError("save_tensor: expected a grassmanntn_b200 dense or block tensor")
+
+
+def pack_bt(bt):
+    """BT -> dict of numpy arrays (the .npz members)."""
+    pats = list(bt.off)
+    nf = len(bt.faxes)
+    return dict(
+        version=np.int64(FORMAT_VERSION),
+        stats=np.asarray(bt.stats, dtype=np.int64),
+        e=np.asarray(bt.e, dtype=np.int64),
+        o=np.asarray(bt.o, dtype=np.int64),
+        fmt=np.str_(bt.fmt),
+        dtype=np.str_("complex128" if bt.dtype == torch.complex128 else "float64"),
+        patterns=np.asarray(pats, dtype=np.int8).reshape(len(pats), nf),
+        offsets=np.asarray([bt.off[p] for p in pats], dtype=np.int64),
+        zero=np.asarray(sorted(bt.zero), dtype=np.int8).reshape(len(bt.zero), nf),
+        buf=bt.buf.detach().cpu().numpy(),
+    )
+
+
+def unpack_bt(z, device=None):
+    """inverse of pack_bt; the buffer goes to `device` (default: the current CUDA device)."""
+    if int(z["version"]) != FORMAT_VERSION:
+        raise ValueError("checkpoint format version %d is not supported" % int(z["version"]))
+    dt = torch.complex128 if str(z["dtype"]) == "complex128" else torch.float64
+    bt = _engine.BT(tuple(int(s) for s in z["stats"]), [int(x) for x in z["e"]], [int(x) for x in z["o"]], dt, str(z["fmt"]))
+    for p, off in zip(z["patterns"], z["offsets"]):
+        bt.off[tuple(int(x) for x in p)] = int(off)
+    bt.zero = {tuple(int(x) for x in p) for p in z["zero"]}
+    dev = device if device is not None else _engine.require_cuda()
+    bt.buf = torch.from_numpy(np.ascontiguousarray(z["buf"])).to(dev)
+    if bt.buf.dtype != dt:
+        raise ValueError("checkpoint buffer dtype %s does not match its header %s" % (bt.buf.dtype, dt))
+    need = max([o_ + bt.block_size(p) for p, o_ in bt.off.items()] + [0])
+    if bt.buf.numel() < need:
+        raise ValueError("checkpoint buffer is shorter (%d) than its block table needs (%d)" % (bt.buf.numel(), need))
+    return bt
+
+
+def save_tensor(path, T, **meta):
+    """Write T (dense or block) and JSON-serialisable metadata to `path` (.npz), atomically."""
+    bt, kind, encoder = _bt_of(T)
+    arrays = pack_bt(bt)
+    arrays["kind"] = np.str_(kind)
+    arrays["encoder"] = np.str_(encoder or "")
+    arrays["shape"] = np.asarray(T.shape, dtype=np.int64)
+    arrays["meta"] = np.str_(json.dumps(meta))
+    tmp = path + ".tmp.npz"
+    with open(tmp, "wb") as f:
+        np.savez(f, **arrays)
+    os.replace(tmp, path)
+    return path
+
+
+def load_tensor(path, device=None):
+    """-> (T, meta): the tensor as the container kind it was saved from, bit-identical."""
+    from . import block, dense
+    with np.load(path, allow_pickle=False) as z:
+        bt = unpack_bt(z, device)
+        kind, encoder = str(z["kind"]), str(z["encoder"])
+        shape = tuple(int(x) for x in z["shape"])
+        meta = json.loads(str(z["meta"]))
+    if kind == "block":
+        return block._from_bt(bt, shape), meta
+    return dense._from_bt(bt, encoder or "canonical"), meta
+
+
+class RunLog:
+    """Append-only JSON-lines log of a coarse-graining run."""
+
+    def __init__(self, path, truncate=False):
+        self.path = path
+        if truncate and os.path.exists(path):
+            os.remove(path)
+
+    def write(self, **rec):
+        rec.setdefault("time", time.time())
+        for k, v in list(rec.items()):
+            if isinstance(v, complex):
+                rec[k] = [v.real, v.imag]
+            elif isinstance(v, (np.floating, np.integer)):
+                rec[k] = v.item()
+            elif isinstance(v, tuple):
+                rec[k] = list(v)
+        with open(self.path, "a") as f:
+            f.write(json.dumps(rec) + "\n")
+
+    def read(self):
+        if not os.path.exists(self.path):
+            return []
+        with open(self.path) as f:
+            return [json.loads(line) for line in f if line.strip()]
+
+
+def step_path(directory, step):
+    return os.path.join(directory, "step_%04d.npz" % step)
+
+
+def latest_step(directory):
+    """-> (step, path) of the newest complete checkpoint in `directory`, or (None, None)."""
+    best = (None, None)
+    if not os.path.isdir(directory):
+        return best
+    for name in os.listdir(directory):
+        if name.startswith("step_") and name.endswith(".npz") and ".tmp" not in name:
+            try:
+                s = int(name[5:-4])
+            except ValueError:
+                continue
+            if best[0] is None or s > best[0]:
+                best = (s, os.path.join(directory, name))
+    return best

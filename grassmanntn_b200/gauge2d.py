@@ -30,6 +30,7 @@ def load_initial_tensor(path=None):
 
 
 SPECULATE = bool(int(os.environ.get("GTN_SPECULATE", "1")))
+SPEC_STATS = {"speculated": 0, "failed": 0}       # decompositions run speculatively / whose certificate then failed
 
 
 def _normalised(T):
@@ -105,48 +106,91 @@ def trg(T, dcut=64, iternum=None, error_test=False):
     else:
         res, pending = gtn.svd_many([T1, T2], "ab|cd", dcut), None
     Tn, Tnorm, err = tail(res)
-    if pending is not None and not pending.verify():
-        Tn, Tnorm, err = tail(gtn.svd_many([T1, T2], "ab|cd", dcut, resume=pending))
+    if pending is not None:
+        SPEC_STATS["speculated"] += 1
+        if not pending.verify():
+            SPEC_STATS["failed"] += 1
+            Tn, Tnorm, err = tail(gtn.svd_many([T1, T2], "ab|cd", dcut, resume=pending))
     return (Tn, Tnorm, err) if error_test else (Tn, Tnorm)
 
 
+def _svd_stage(objs, string, cut, site, resume, pend):
+    """One decomposition of a multi-stage step.  Steady state: speculative (the replayed SVD graph is only
+    enqueued; `pend[site]` holds the unverified run).  `resume`: continue a run whose certificate failed."""
+    if resume is not None:
+        return gtn.svd_many(objs, string, cut, resume=resume, site=site)
+    if SPECULATE:
+        res, pend[site] = gtn.svd_many(objs, string, cut, speculative=True, site=site)
+        return res
+    return gtn.svd_many(objs, string, cut, site=site)
+
+
 def atrg2dy(T1, T2, dcut=64, intermediate_dcut=None, iternum=None, error_test=False, alignment="y"):
-    """One ATRG step along y (reference gauge2d.py:1761-1869)."""
+    """One ATRG step along y (reference gauge2d.py:1761-1869).
+    The three decompositions depend on each other; in steady state each replays its truncated-SVD graph without
+    reading the certificate back, the next stage is enqueued behind it, and the step synchronises once (its
+    norm).  The certificates are then verified in order; the first stage that fails is resumed from its
+    workspace state and everything after it is repeated."""
     if intermediate_dcut is None:
         intermediate_dcut = dcut
     T1o, T2o = T1, T2
+    same = T1o is T2o
     T1 = gtn.einsum("ijkl->lijk", T1)
-    T2 = T1 if T1o is T2o else gtn.einsum("ijkl->lijk", T2)
-    if T1o is T2o:
-        U1, S1, V1 = T1.svd("li|jk", intermediate_dcut)
-        U2, S2, V2 = U1, S1, V1
-    else:
-        (U1, S1, V1), (U2, S2, V2) = gtn.svd_many([T1, T2], "li|jk", intermediate_dcut)
-    A = V1
-    B = gtn.einsum("lia,ab->lib", U1, S1)
-    C = gtn.einsum("ab,bjk->ajk", S2, V2)
-    D = U2
-    M = gtn.einsum("ajk,jib->aibk", C, B)
-    U, S, V = M.svd("ai|bk", intermediate_dcut)
-    sq = gtn.sqrt(S)
-    Y = gtn.einsum("abx,xc->abc", U, sq)
-    X = gtn.einsum("ax,xbc->abc", sq, V)
-    Q1 = gtn.einsum("iax,xbj->ijab", D, Y)
-    Q2 = gtn.einsum("kya,ylb->abkl", X, A)
-    Q = gtn.einsum("ijab,abkl->ijkl", Q1, Q2)
-    U, S, V = Q.svd("ij|kl", dcut)
-    sq = gtn.sqrt(S)
-    H = gtn.einsum("abx,xc->abc", U, sq)
-    G = gtn.einsum("ax,xbc->abc", sq, V)
-    H = gtn.einsum("lai->ila", H)
-    G = gtn.einsum("kaj->ajk", G)
-    T = gtn.einsum("ila,ajk->ijkl", H, G)
-    err = None
-    if error_test:
-        Z1 = gtn.einsum("IJIK,iKiJ", T1o, T2o)
-        Z2 = gtn.einsum("IJIJ", T)
-        err = np.abs(1 - Z2 / Z1)
-    T, Tnorm = _normalised(T)
+    T2 = T1 if same else gtn.einsum("ijkl->lijk", T2)
+    sites = [("atrg", alignment, i) for i in (1, 2, 3)]
+    st, start, resume = {}, 0, None
+    while True:
+        pend = {}
+        if start <= 0:
+            st["a"] = _svd_stage([T1] if same else [T1, T2], "li|jk", intermediate_dcut, sites[0],
+                                 resume if start == 0 else None, pend)
+        (U1, S1, V1), (U2, S2, V2) = st["a"][0], st["a"][-1]
+        if start <= 1:
+            A = V1
+            B = gtn.einsum("lia,ab->lib", U1, S1)
+            C = gtn.einsum("ab,bjk->ajk", S2, V2)
+            D = U2
+            M = gtn.einsum("ajk,jib->aibk", C, B)
+            st["b"] = _svd_stage([M], "ai|bk", intermediate_dcut, sites[1], resume if start == 1 else None, pend)
+            st["AD"] = (A, D)
+        A, D = st["AD"]
+        U, S, V = st["b"][0]
+        if start <= 2:
+            sq = gtn.sqrt(S)
+            Y = gtn.einsum("abx,xc->abc", U, sq)
+            X = gtn.einsum("ax,xbc->abc", sq, V)
+            Q1 = gtn.einsum("iax,xbj->ijab", D, Y)
+            Q2 = gtn.einsum("kya,ylb->abkl", X, A)
+            Q = gtn.einsum("ijab,abkl->ijkl", Q1, Q2)
+            st["c"] = _svd_stage([Q], "ij|kl", dcut, sites[2], resume if start == 2 else None, pend)
+        U, S, V = st["c"][0]
+        sq = gtn.sqrt(S)
+        H = gtn.einsum("abx,xc->abc", U, sq)
+        G = gtn.einsum("ax,xbc->abc", sq, V)
+        H = gtn.einsum("lai->ila", H)
+        G = gtn.einsum("kaj->ajk", G)
+        T = gtn.einsum("ila,ajk->ijkl", H, G)
+        err = None
+        if error_test:
+            Z1 = gtn.einsum("IJIK,iKiJ", T1o, T2o)
+            Z2 = gtn.einsum("IJIJ", T)
+            err = np.abs(1 - Z2 / Z1)
+        T, Tnorm = _normalised(T)
+        # verify the speculated stages in order; stages behind a failed one worked on unverified input
+        bad = None
+        for i, site in enumerate(sites):
+            p = pend.get(site)
+            if p is None:
+                continue
+            SPEC_STATS["speculated"] += 1
+            if bad is not None:
+                p.discard()
+            elif not p.verify():
+                SPEC_STATS["failed"] += 1
+                bad = i
+        if bad is None:
+            break
+        start, resume = bad, pend[sites[bad]]
     return (T, Tnorm, err) if error_test else (T, Tnorm)
 
 
@@ -245,25 +289,56 @@ def logZhotrg3dz(T1, T2, boundary_conditions="periodic"):
     return np.log(gtn.einsum('IJIJmn,KLKLmn', T1, T2))
 
 
-def coarse_grain(T, cgsteps=5, dcut=32, method="atrg", boundary_conditions="anti-periodic", error_test=False):
-    """The 2D loop of example.py:156-196 (after zcap): returns the list of per-step records
-    (volume, F, Tnorm, err, shape)."""
-    logNorm = 0.0
+def coarse_grain(T, cgsteps=5, dcut=32, method="atrg", boundary_conditions="anti-periodic", error_test=False,
+                 log=None, checkpoint_dir=None, resume=False, checkpoint_every=1, logNorm0=0.0):
+    """The 2D loop of example.py:156-196 (after zcap): returns (T, records) with one record per step
+    (volume, F, Tnorm, err, shape).
+    log: path of a JSON-lines run log (checkpoint.RunLog), one line per step.
+    checkpoint_dir: the tensor and the accumulated log-norm are saved after every `checkpoint_every` steps;
+    with resume=True the loop continues bit-identically from the newest checkpoint found there (the reference has
+    neither).  logNorm0: log-norm accumulated before the 2D loop (flavour coarse-graining,
+    example.py:144-150)."""
+    import time as _time
+    from . import checkpoint as ck
+    logNorm = float(logNorm0)
     records = []
-    F = logZ(T, boundary_conditions) + logNorm
-    records.append(dict(vol=1, F=complex(F), Tnorm=None, err=None, shape=T.shape[:2]))
+    runlog = ck.RunLog(log, truncate=not resume) if log else None
+    first = 0
     cgxfirst = T.shape[0] > T.shape[1]
-    for i in range(cgsteps):
+    if checkpoint_dir:
+        os.makedirs(checkpoint_dir, exist_ok=True)
+        step, path = ck.latest_step(checkpoint_dir) if resume else (None, None)
+        if step is not None:
+            T, meta = ck.load_tensor(path)
+            if (meta["dcut"], meta["method"], meta["boundary_conditions"]) != (dcut, method, boundary_conditions):
+                gtn.error("Error[coarse_grain]: the checkpoint was written with different run parameters.")
+            logNorm, first, cgxfirst, records = meta["logNorm"], step, meta["cgxfirst"], meta["records"]
+            for r in records:
+                r["F"], r["shape"] = complex(*r["F"]), tuple(r["shape"])
+    if first == 0:
+        F = logZ(T, boundary_conditions) + logNorm
+        records.append(dict(vol=1, F=complex(F), Tnorm=None, err=None, shape=tuple(getattr(T, "effective_shape", T.shape)[:2])))
+        if runlog:
+            runlog.write(process="_ini", **records[-1])
+    for i in range(first, cgsteps):
+        t0 = _time.time()
         if method == "trg":
+            process = "_trg"
             out = trg(T, dcut, iternum=i, error_test=error_test)
         else:
             use_x = (i % 2 == 0) == cgxfirst
-            fn = atrg2dx if use_x else atrg2dy
+            fn, process = (atrg2dx, "_atrgx") if use_x else (atrg2dy, "_atrgy")
             out = fn(T, T, dcut, iternum=i, error_test=error_test)
         T, Tnorm = out[0], out[1]
         vol = 2 ** (i + 1)
         logNorm = 2 * logNorm + math.log(Tnorm)
         F = (logZ(T, boundary_conditions) + logNorm) / vol
-        records.append(dict(vol=vol, F=complex(F), Tnorm=float(Tnorm), err=(out[2] if error_test else None),
-                            shape=T.shape[:2]))
+        records.append(dict(vol=vol, F=complex(F), Tnorm=float(Tnorm), err=(float(out[2]) if error_test else None),
+                            shape=tuple(getattr(T, "effective_shape", T.shape)[:2])))
+        if runlog:
+            runlog.write(process=process, seconds=_time.time() - t0, **records[-1])
+        if checkpoint_dir and ((i + 1) % checkpoint_every == 0 or i + 1 == cgsteps):
+            meta_records = [dict(r, F=[r["F"].real, r["F"].imag], shape=list(r["shape"])) for r in records]
+            ck.save_tensor(ck.step_path(checkpoint_dir, i + 1), T, logNorm=logNorm, dcut=dcut, method=method,
+                           boundary_conditions=boundary_conditions, cgxfirst=bool(cgxfirst), records=meta_records)
     return T, records

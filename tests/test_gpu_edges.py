@@ -260,3 +260,44 @@ def test_speculative_trg_step_and_misspeculation(gtn):
             assert abs(x - y) <= 1e-10 * abs(x), (ref, other)
         for x, y in zip(ref[3:], other[3:]):             # from the 4th step on the cut goes through exact multiplets
             assert abs(x - y) <= 1e-6 * abs(x), (ref, other)
+
+
+@pytest.mark.gpu
+def test_speculative_atrg_chain_and_misspeculation(gtn):
+    """gauge2d.atrg2dy keeps its three dependent decompositions in flight behind each other (one workspace per
+    call site) and verifies the certificates in order at the end of the step.  (a) same Tnorm as the
+    non-speculative step; (b) too few iterations at ONE stage (its certificate must fail) are caught, that stage
+    is resumed, the stages behind it are repeated; (c) same with every stage sabotaged."""
+    from grassmanntn_b200 import _engine as E, gauge2d as g
+    T0 = g.zcap(g.load_initial_tensor()).toblock()
+    for _ in range(2):
+        T0, _ = g.trg(T0, 32)                                  # 32^4 site tensor: the truncated path is taken
+    def chain(spec, sabotage=None):
+        old = g.SPECULATE
+        g.SPECULATE = spec
+        E._trunc_iters_hint.clear(); E._trunc_rate.clear(); E._trunc_fail.clear()
+        g.SPEC_STATS["speculated"] = g.SPEC_STATS["failed"] = 0
+        try:
+            T, out = T0, []
+            for i in range(6):
+                if sabotage is not None and i >= 4:
+                    for k in list(E._trunc_iters_hint):
+                        site = k[1]
+                        if isinstance(site, tuple) and site[0] == "atrg" and (sabotage == "all" or site[2] == sabotage):
+                            E._trunc_iters_hint[k] = 0           # far too few iterations: the certificate fails
+                fn = g.atrg2dx if i % 2 == 0 else g.atrg2dy
+                T, n = fn(T, T, 32)[:2]
+                out.append(float(n))
+            return out, dict(g.SPEC_STATS)
+        finally:
+            g.SPECULATE = old
+    ref, st0 = chain(False)
+    assert st0["speculated"] == 0
+    runs = [chain(True), chain(True, sabotage=2), chain(True, sabotage="all")]
+    assert runs[0][1]["speculated"] > 0, runs[0][1]
+    assert runs[1][1]["failed"] >= 1 and runs[2][1]["failed"] >= 2, (runs[1][1], runs[2][1])
+    for other, _ in runs:
+        for i, (x, y) in enumerate(zip(ref, other)):
+            # the cut goes through exact multiplets of the Z2 spectrum after the first steps (DESIGN section 7)
+            tol = 1e-10 if i < 1 else 1e-6
+            assert abs(x - y) <= tol * abs(x), (i, ref, other)
