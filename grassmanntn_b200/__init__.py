@@ -391,6 +391,7 @@ class block:
 
     def __init__(self, data=None, is_zero=False):
         self.marked_as_joined = False
+        self._joined_sigma = None        # {axis: (sigma bits even, odd)} of legs made by join_legs (reference .sgn)
         if data is None:
             self._bt = None
             self.statistics = None
@@ -401,6 +402,7 @@ class block:
             self._bt = data._bt.clone()
             self.statistics, self.format, self.shape = data.statistics, data.format, data.shape
             self.marked_as_joined = data.marked_as_joined
+            self._joined_sigma = data._joined_sigma
             return
         if not isinstance(data, dense):
             error("Error[block]: a block tensor is constructed from a dense tensor only.")
@@ -451,7 +453,10 @@ class block:
             for a in range(bt.ndim):
                 if bt.stats[a] in fermi_type:
                     n = bt.e[a] if pi == 0 else bt.o[a]
-                    v = 1 - 2 * _engine.sigma_bits(pi, n).astype(np.int64)
+                    if self._joined_sigma and a in self._joined_sigma:
+                        v = 1 - 2 * self._joined_sigma[a][pi][:n].astype(np.int64)
+                    else:
+                        v = 1 - 2 * _engine.sigma_bits(pi, n).astype(np.int64)
                     if n == 0:
                         v = np.zeros(1, dtype=np.int64)
                 else:
@@ -552,8 +557,8 @@ class block:
         return self * other
 
     def switch_format(self):
-        r = block._from_bt(bt_switch_format(self._bt), self.shape)
-        r.marked_as_joined = self.marked_as_joined
+        r = block._from_bt(bt_switch_format(self._bt, sigma=self._joined_sigma), self.shape)
+        r.marked_as_joined, r._joined_sigma = self.marked_as_joined, self._joined_sigma
         return r
 
     def force_format(self, format):
@@ -574,6 +579,12 @@ class block:
 
     def eig(self, string, cutoff=None, save_memory=False):
         return eig(self, string, cutoff, False, save_memory)
+
+    def join_legs(self, string_inp, final_stat):
+        return join_legs_block(self, string_inp, final_stat)
+
+    def split_legs(self, string_inp, final_stat, final_shape, final_even_shape, final_odd_shape):
+        return split_legs_block(self, string_inp, final_stat, final_shape, final_even_shape, final_odd_shape)
 
 
 def todense(obj, encoder="canonical", skip_joined_check=False):
@@ -722,6 +733,55 @@ def split_legs(InpObj, string_inp, final_stat, final_shape, intermediate_stat=No
     return out
 
 
+def _block_group_axes(string_inp, ndim, fn):
+    groups, loc = [], 0
+    for ind in _planner.parse_groups(denumerate(string_inp.replace(" ", ""))):
+        groups.append(list(range(loc, loc + len(ind))))
+        loc += len(ind)
+    if loc != ndim:
+        error("Error[%s]: The number of indices is not consistent with the object's shape." % fn)
+    return groups
+
+
+def join_legs_block(InpObj, string_inp, final_stat):
+    """reference join_legs_block (__init__.py:3376-3621): join the legs of a block tensor group by group.  The
+    parity blocks of a group's members become sub-blocks of the joined leg's even / odd block, in the reference's
+    enumeration order; the data gets (-1)^p for +1 members of a -1 group and NO sigma factors -- the joined legs
+    carry their own sigma vectors instead (`.sgn`), which `switch_format` and `split_legs` use.  The result is
+    `marked_as_joined`: split it before contracting or decomposing it."""
+    if not isinstance(InpObj, block):
+        error("Error[join_legs_block]: This function only works with block data format.")
+    if InpObj.marked_as_joined:
+        error("Error[join_legs_block]: The tensor can only be joined once!")
+    final_stat = make_tuple(final_stat)
+    groups = _block_group_axes(string_inp, InpObj.ndim, "join_legs_block")
+    bt, sigma = _ops.join_block_bt(InpObj._bt, groups, final_stat)
+    r = block._from_bt(bt)               # total shape: next power of two of every joined leg (zero_block_eo :646-648)
+    r.marked_as_joined, r._joined_sigma = True, sigma
+    return r
+
+
+def split_legs_block(InpObj, string_inp, final_stat, final_shape, final_even_shape, final_odd_shape):
+    """reference split_legs_block (__init__.py:3623-3859), inverse of join_legs_block for a standard-format tensor.
+    (For a matrix-format tensor the reference switches to the standard format with the joined legs' sigma vectors,
+    splits, and switches back with the split legs' standard sigma vectors; reproduced.)"""
+    if not isinstance(InpObj, block):
+        error("Error[split_legs_block]: This function only works with block data format.")
+    if not InpObj.marked_as_joined:
+        error("Error[split_legs_block]: You can only split the joined tensor!")
+    final_stat, final_shape = make_tuple(final_stat), make_tuple(final_shape)
+    e = [int(x) for x in make_tuple(final_even_shape)]
+    o = [int(x) for x in make_tuple(final_odd_shape)]
+    for a, st in enumerate(final_stat):
+        if st in bose_type:
+            e[a] = int(final_shape[a])
+    groups = _block_group_axes(string_inp, len(final_stat), "split_legs_block")
+    if len(groups) != InpObj.ndim:
+        error("Error[split_legs_block]: The number of groups is not consistent with the object's shape.")
+    bt = _ops.split_block_bt(InpObj._bt, InpObj._joined_sigma, groups, final_stat, e, o)
+    return block._from_bt(bt, tuple(int(x) for x in final_shape))
+
+
 # sign helpers of the reference's "Parity Calculation (internal tools)" section (__init__.py:1483-1604),
 # kept for API parity; the kernels never call them (the planner derives the same signs as one GF(2)
 # quadratic form, _planner.einsum_sign_program).
@@ -766,6 +826,8 @@ def einsum(*args, ignore_anticommutation=False):
             error("Error[einsum]: operands must be grassmanntn_b200.dense or .block objects")
         if isinstance(o, block) != isinstance(first, block):
             error("Error[einsum_block]: This function only works with block data format.")
+        if getattr(o, "marked_as_joined", False):
+            error("Error[einsum_block]: Split the legs first!")
     this_format = first.format
     bts = [(o._bt if isinstance(o, block) else o._get_bt()) for o in objs]
     res = _ops.einsum_bt(subscripts, bts, ignore_anticommutation)
@@ -781,6 +843,8 @@ def _decompose(obj, string, cutoff, kind):
     left, right = _planner.split_partition(string, "svd" if kind == "svd" else "eig")
     nl = len(left)
     is_block = isinstance(obj, block)
+    if getattr(obj, "marked_as_joined", False):
+        error("Error[%s]: Split the legs first!" % kind)
     bt = obj._bt if is_block else obj._get_bt()
     if nl + len(right) != bt.ndim:
         error("Error[%s]: The number of indices is not consistent with the object's shape." % kind)
@@ -874,6 +938,8 @@ eig_block = eig
 def hconjugate(InpObj, string, save_memory=False):
     """Hermitian conjugate (reference hconjugate :5300-5493, hconjugate_block :5495-5955)."""
     left, right = _planner.split_partition(string, "hconjugate")
+    if getattr(InpObj, "marked_as_joined", False):
+        error("Error[hconjugate]: Split the legs first!")
     bt = InpObj._bt if isinstance(InpObj, block) else InpObj._get_bt()
     if len(left) + len(right) != bt.ndim:
         error("Error[hconjugate]: The number of indices is not consistent with the object's shape.")

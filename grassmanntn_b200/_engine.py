@@ -567,9 +567,11 @@ def dense_sign_permute(data, perm, alpha_axes=()):
 
 
 # ---- in-place style elementwise sign passes (format switch) -----------------------------------
-def bt_switch_format(bt):
+def bt_switch_format(bt, sigma=None):
     """sigma on every conjugated (-1) leg: reference dense.switch_format (__init__.py:1011-1068) /
-    block.switch_format (:537-571).  One launch, new buffer."""
+    block.switch_format (:537-571).  One launch, new buffer.
+    sigma: {axis: (bits of the even block, bits of the odd block)} for legs whose sigma vector is not the standard
+    one (legs made by join_legs_block carry their own sgn, reference :3588-3610)."""
     out = BT(bt.stats, bt.e, bt.o, bt.dtype, "matrix" if bt.fmt == "standard" else "standard")
     out.off = dict(bt.off)
     out.zero = set(bt.zero)
@@ -587,7 +589,8 @@ def bt_switch_format(bt):
             legs, beta = [], []
             for a in range(bt.ndim):
                 if a in pis and bt.stats[a] == -1:
-                    legs.append(lin_leg(bshape[a], bstr[a], bstr[a], q=sigma_bits(pis[a], bshape[a])))
+                    q = sigma[a][pis[a]][:bshape[a]] if (sigma and a in sigma) else sigma_bits(pis[a], bshape[a])
+                    legs.append(lin_leg(bshape[a], bstr[a], bstr[a], q=q))
                     beta.append(1)
                 else:
                     legs.append(lin_leg(bshape[a], bstr[a], bstr[a]))
@@ -595,7 +598,8 @@ def bt_switch_format(bt):
             order = list(range(bt.ndim))
             jobs.append(build_job(legs, beta=beta, in_base=bt.off[p], out_base=bt.off[p], in_order=order, out_order=order))
         return PermutePlan(jobs)
-    _cached(("fmt", bt.key()), build).run(bt.buf, out.buf)
+    skey = None if not sigma else tuple((a, v[0].tobytes(), v[1].tobytes()) for a, v in sorted(sigma.items()))
+    _cached(("fmt", bt.key(), skey), build).run(bt.buf, out.buf)
     return out
 
 
@@ -609,13 +613,13 @@ def bt_force_standard(bt):
 _layout_cache = {}
 
 
-def group_layout(legs):
-    k = tuple(legs)
+def group_layout(legs, order="lex"):
+    k = (tuple(legs), order)
     g = _layout_cache.get(k)
     if g is None:
         if len(_layout_cache) > 4096:
             _layout_cache.clear()
-        g = GroupLayout(k)
+        g = GroupLayout(k[0], order)
         _layout_cache[k] = g
     return g
 
@@ -623,13 +627,21 @@ def group_layout(legs):
 class GroupLayout:
     """Index space of a list of legs joined together.  Patterns (parities of the fermionic
     members) are ordered with even total parity first; inside a pattern the members form a
-    row-major mixed-radix index."""
+    row-major mixed-radix index.
+    order='lex': patterns of one total parity in lexicographic order (internal packing: any fixed order
+    serves a decomposition or a contraction).  order='ref': the order the reference's join_index walks the
+    sub-blocks (__init__.py:3339-3355 through param.to_bin_parity_preserving, param.py:25-47): by
+    (p_1, p_2, ...) read as a little-endian number, p_0 fixed by the total parity -- the user-visible layout
+    of join_legs_block."""
 
-    def __init__(self, legs):
+    def __init__(self, legs, order="lex"):
         self.legs = list(legs)                      # (stat, e, o)
         self.fpos = [k for k, L in enumerate(self.legs) if L[0] in FERMI]
         pats = list(itertools.product((0, 1), repeat=len(self.fpos)))
-        pats.sort(key=lambda p: (sum(p) % 2, p))
+        if order == "ref":
+            pats.sort(key=lambda p: (sum(p) % 2, tuple(reversed(p[1:]))))
+        else:
+            pats.sort(key=lambda p: (sum(p) % 2, p))
         self.pats, self.offset, self.size, self.shape = [], {}, {}, {}
         acc = 0
         self.even_total = 0

@@ -864,3 +864,121 @@ def power_bt(bt, p, rcond=1e-10):
           "gtn_pow_rcond")
     count()
     return m if this_fmt == "matrix" else bt_switch_format(m)
+
+
+# ------------------------------------------------------------------------------------------------
+#  user-level join / split of block tensors (reference join_legs_block / split_legs_block)
+# ------------------------------------------------------------------------------------------------
+def _joined_sigma_bits(lay):
+    """sigma exponent bits of a joined fermionic leg, per total parity: sub-block v carries
+    prod_{i<j} (-1)^{v_i v_j} * outer(member sigma) (reference join_index :3357-3366)."""
+    bits = {0: np.zeros(lay.even_total, dtype=np.uint32), 1: np.zeros(lay.total - lay.even_total, dtype=np.uint32)}
+    for v in lay.pats:
+        par = sum(v) % 2
+        b = np.zeros(1, dtype=np.uint32)
+        for pi, d in zip(v, lay.shape[v]):
+            b = (b[:, None] ^ sigma_bits(pi, d)[None, :]).ravel()
+        perm = sum(v[i] * v[j] for i in range(len(v)) for j in range(i + 1, len(v))) & 1
+        o = lay.offset[v] - lay.sector(par)[0]
+        bits[par][o: o + lay.size[v]] = b ^ np.uint32(perm)
+    return bits[0], bits[1]
+
+
+def _check_block_groups(groups, stats, final_stat, fn):
+    if "*" in tuple(final_stat):
+        _err("Error[%s]: Hybrid joining is not allowed for block format." % fn)
+    if len(final_stat) != len(groups):
+        _err("Error[%s]: Inconsistent number of final statistics and groupings!" % fn)
+    for ax, fs in zip(groups, final_stat):
+        st = [stats[a] for a in ax]
+        f = [s in FERMI for s in st]
+        if any(f) and not all(f):
+            _err("Error[%s]: Hybrid joining is not allowed for block format." % fn)
+        if (fs in FERMI) != all(f):
+            _err("Error[%s]: The final statistics are not consistent with the groups." % fn)
+
+
+def join_block_bt(bt, groups, final_stat):
+    """reference join_legs_block (__init__.py:3376-3621): ONE sign+permute launch.  Every parity block goes, as a
+    (prod of members) sub-block per group, into block (total parities) at the offset of its sub-block in the
+    reference's enumeration order, times (-1)^p for every +1 member of a group whose final statistic is -1
+    (:3574-3580); the data carries no sigma factors, the format is kept.
+    Returns (joined BT, {joined axis: (sigma bits even, sigma bits odd)})."""
+    _check_block_groups(groups, bt.stats, final_stat, "join_legs_block")
+    lays = [group_layout([bt.leg(a) for a in ax], "ref") for ax in groups]
+    fg = [bt.stats[ax[0]] in FERMI for ax in groups]
+    ne = [lay.even_total if f else lay.total for lay, f in zip(lays, fg)]
+    no = [lay.total - lay.even_total if f else 0 for lay, f in zip(lays, fg)]
+    out = BT(tuple(final_stat), ne, no, bt.dtype, bt.fmt)
+    live = bt.live()
+
+    def vpat(pis, ax):
+        return tuple(pis[a] for a in ax if a in pis)
+
+    def opat_of(pat):
+        pis = dict(zip(bt.faxes, pat))
+        return tuple(sum(vpat(pis, ax)) % 2 for ax, f in zip(groups, fg) if f)
+    out.alloc(sorted({opat_of(p) for p in live}), zero=True)
+    alpha = {a for k, ax in enumerate(groups) if final_stat[k] == -1 for a in ax if bt.stats[a] == 1}
+
+    def build():
+        def place(pat, bshape):
+            pis = dict(zip(bt.faxes, pat))
+            op = opat_of(pat)
+            oblk = _row_strides(out.block_shape(op))
+            base, ostr = out.off[op], [0] * bt.ndim
+            for k, (ax, lay) in enumerate(zip(groups, lays)):
+                v = vpat(pis, ax)
+                base += (lay.offset[v] - lay.sector(sum(v) % 2)[0]) * oblk[k]
+                for j, a in enumerate(ax):
+                    ostr[a] = lay.strides(v)[j] * oblk[k]
+            return base, ostr, False
+        return PermutePlan(_block_jobs(bt, live, alpha, set(), set(), place))
+    _cached(("joinblk", bt.key(), tuple(map(tuple, groups)), tuple(final_stat)), build).run(bt.buf, out.buf)
+    sigma = {k: _joined_sigma_bits(lay) for k, (lay, f) in enumerate(zip(lays, fg)) if f}
+    return out, sigma
+
+
+def split_block_bt(bt, sigma, groups, final_stat, e, o):
+    """reference split_legs_block (__init__.py:3623-3859): standard format first -- with the joined legs' own sigma
+    vectors (:3644) --, every joined block cut into its sub-blocks with the (-1)^p correction undone (:3838-3846),
+    one sign+permute launch, then back to the caller's format with the STANDARD sigma of the split legs (:3857)."""
+    this_fmt = bt.fmt
+    S = bt if bt.fmt == "standard" else bt_switch_format(bt, sigma=sigma)
+    _check_block_groups(groups, final_stat, S.stats, "split_legs_block")
+    res = BT(tuple(final_stat), e, o, bt.dtype, "standard")
+    lays = [group_layout([res.leg(a) for a in ax], "ref") for ax in groups]
+    fg = [final_stat[ax[0]] in FERMI for ax in groups]
+    for k, (lay, f) in enumerate(zip(lays, fg)):
+        want = (lay.even_total, lay.total - lay.even_total) if f else (lay.total, 0)
+        if (S.e[k], S.o[k]) != want:
+            _err("Error[split_legs_block]: The final shape is not consistent with the joined leg %d." % k)
+
+    def jpat_of(pat):
+        pis = dict(zip(res.faxes, pat))
+        return tuple(sum(pis[a] for a in ax) % 2 for ax, f in zip(groups, fg) if f)
+    live_j = set(S.live())
+    pats = [p for p in res.patterns() if jpat_of(p) in live_j and res.block_size(p) > 0]
+    res.alloc(pats)
+
+    def build():
+        jobs = []
+        for p in pats:
+            pis = dict(zip(res.faxes, p))
+            jp = jpat_of(p)
+            iblk = _row_strides(S.block_shape(jp))
+            oblk = _row_strides(res.block_shape(p))
+            base, const, legs = S.off[jp], 0, [None] * res.ndim
+            for k, (ax, lay) in enumerate(zip(groups, lays)):
+                v = tuple(pis[a] for a in ax if a in pis)
+                base += (lay.offset[v] - lay.sector(sum(v) % 2)[0]) * iblk[k]
+                st = lay.strides(v)
+                for j, a in enumerate(ax):
+                    legs[a] = lin_leg(lay.shape[v][j], st[j] * iblk[k], oblk[a])
+                    if S.stats[k] == -1 and final_stat[a] == 1:
+                        const ^= pis[a]
+            jobs.append(build_job(legs, const=const, in_base=base, out_base=res.off[p]))
+        return PermutePlan(jobs)
+    key = ("splitblk", S.key(), tuple(map(tuple, groups)), tuple(final_stat), tuple(res.e), tuple(res.o))
+    _cached(key, build).run(S.buf, res.buf)
+    return res if this_fmt == "standard" else bt_switch_format(res)

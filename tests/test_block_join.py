@@ -85,3 +85,113 @@ def test_oracle_join_block_errors():
     B = O.Blocks(st, ev, [2, 1, 3, 2], _input_blocks(6, st), fmt)
     with pytest.raises(ValueError):
         O.join_legs_block(B, "(ijk)(l)", (1, 0))                  # hybrid group
+
+
+# ---------------------------------------------------------------------------------------------------------------
+#  product: host-built launch tables (CPU, kernel emulated by tests/test_tables_cpu.emulate) and the GPU itself
+# ---------------------------------------------------------------------------------------------------------------
+def _product_case(gtn, k, device):
+    """the golden case as a product block tensor (all parity blocks stored)"""
+    import torch
+    from grassmanntn_b200 import _engine as E
+    ev, od, st, fmt, string, fstat = CASES[k]
+    bt = E.BT(st, ev, od, torch.complex128, fmt)
+    total = 0
+    for p in bt.patterns():
+        bt.off[p] = total
+        total += bt.block_size(p)
+    buf = np.zeros(max(total, 1), dtype=np.complex128)
+    for p in bt.patterns():
+        buf[bt.off[p]: bt.off[p] + bt.block_size(p)] = Z[_key(k, "in", p)].ravel()
+    bt.buf = torch.from_numpy(buf).to(device)
+    return gtn.block._from_bt(bt, tuple(int(x) for x in Z["c%d_shape" % k]))
+
+
+def _check_product_case(gtn, k, device):
+    ev, od, st, fmt, string, fstat = CASES[k]
+    B = _product_case(gtn, k, device)
+    J = B.join_legs(string, fstat)
+    assert J.marked_as_joined and J.format == fmt and J.statistics == tuple(fstat)
+    fj = [a for a, s in enumerate(fstat) if s in (1, -1)]
+    assert [J.even_shape[a] for a in fj] == [int(Z["c%d_join_even" % k][a]) for a in fj]
+    assert [J.odd_shape[a] for a in fj] == [int(Z["c%d_join_odd" % k][a]) for a in fj]
+    assert tuple(J.shape) == tuple(int(x) for x in Z["c%d_join_shape" % k])
+    data = J.data
+    for p in _pats(fstat):
+        assert np.array_equal(data[p].cpu().numpy(), Z[_key(k, "join", p)]), (k, p)
+    sgn = J.sgn
+    for a in fj:
+        for pi in (0, 1):
+            n = J.even_shape[a] if pi == 0 else J.odd_shape[a]
+            assert np.array_equal(sgn[pi][a][:n], Z["c%d_sgn_%d_%d" % (k, pi, a)][:n]), (k, pi, a)
+    dsw = J.switch_format().data
+    for p in _pats(fstat):
+        assert np.array_equal(dsw[p].cpu().numpy(), Z[_key(k, "joinsw", p)]), (k, p)
+    S = J.split_legs(string, st, tuple(int(x) for x in Z["c%d_shape" % k]), ev, od)
+    assert not S.marked_as_joined and S.format == fmt and S.statistics == tuple(st)
+    assert tuple(S.even_shape) == tuple(ev)
+    ds = S.data
+    for p in _pats(st):
+        assert np.array_equal(ds[p].cpu().numpy(), Z[_key(k, "split", p)]), (k, p)
+    # errors: joined once, split only joined, no contraction / decomposition of a joined tensor
+    with pytest.raises(ValueError):
+        J.join_legs("(i)" * J.ndim, fstat)
+    with pytest.raises(ValueError):
+        B.split_legs(string, st, B.shape, ev, od)
+    with pytest.raises(ValueError):
+        gtn.einsum("".join("abcdef"[:J.ndim]) + "->" + "".join("abcdef"[:J.ndim]), J)
+
+
+@pytest.fixture
+def host_tables(monkeypatch):
+    """run the product's host code without a GPU: buffers on the host, every sign+permute launch replaced by the
+    numpy emulation of the kernel's addressing / sign rule"""
+    import torch
+    from test_tables_cpu import emulate
+    from grassmanntn_b200 import _engine as E, _ops
+
+    class HostPlan:
+        def __init__(self, jobs):
+            self.jobs = jobs
+
+        def run(self, src, dst, scale=1.0):
+            s, d = src.numpy(), dst.numpy()
+            for f, tabs in self.jobs:
+                emulate(f, tabs, s, d, scale)
+    saved = dict(E._plan_cache)
+    E._plan_cache.clear()
+    monkeypatch.setattr(E, "PermutePlan", HostPlan)
+    monkeypatch.setattr(_ops, "PermutePlan", HostPlan)
+    monkeypatch.setattr(E, "require_cuda", lambda: torch.device("cpu"))
+    monkeypatch.setattr(_ops, "require_cuda", lambda: torch.device("cpu"))
+    yield
+    E._plan_cache.clear()
+    E._plan_cache.update(saved)
+
+
+@pytest.mark.parametrize("k", range(len(CASES)))
+def test_product_tables_join_split_block_vs_reference(host_tables, k):
+    import grassmanntn_b200 as gtn
+    _check_product_case(gtn, k, "cpu")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k", range(len(CASES)))
+def test_gpu_join_split_block_vs_reference(gtn, k):
+    _check_product_case(gtn, k, "cuda")
+
+
+@pytest.mark.gpu
+def test_gpu_join_split_block_roundtrip_at_size(gtn):
+    """size-independent property at the bench size: split(join(T)) == T bit-exactly for a standard-format
+    32^4 block tensor, and the joined matrix has the norm of T"""
+    g = gtn.gauge2d
+    T = g.zcap(g.load_initial_tensor()).toblock()
+    for _ in range(2):
+        T, _ = g.trg(T, 32)
+    J = T.join_legs("(ij)(kl)", (1, -1))
+    assert J.even_shape == (512, 512) and abs(J.norm - T.norm) <= 1e-14 * T.norm
+    S = J.split_legs("(ij)(kl)", T.statistics, T.shape, T.even_shape, T.odd_shape)
+    a, b = T.data, S.data
+    for p in T._bt.patterns():
+        assert bool((a[p] == b[p]).all()), p
