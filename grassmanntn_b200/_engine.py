@@ -937,6 +937,12 @@ def subspace_rows(k):
 _trunc_fail = {}
 _trunc_rate = {}
 SVD_SITE = [None]          # call site of the decomposition being run (set by _ops.decompose_many)
+FORCE_VERIFY_FAIL = [None]  # test hook: callable(SpeculativeSVD) -> True makes verify() report a failed certificate
+CAPTURING_STEP = [False]   # a caller is capturing a whole coarse-graining step: enqueue the steady-state schedule inline
+
+
+class NotCapturable(RuntimeError):
+    """raised inside a whole-step capture when a decomposition is not in its replayable steady state"""
 _trunc_plans = {}
 
 
@@ -1012,6 +1018,8 @@ class _TruncPlan:
         self.persistent = 2 <= self.maxL <= PERSISTENT_MAX_ROWS
         self.graphable = self.persistent and WHITEN == "chol"
         self.graphs, self.graph_launches = {}, {}
+        self.warmed = set()             # iteration counts whose schedule has run eagerly (its launch tables are cached)
+        self.graph_failures = 0
         self.host_sweeps = None
         self.pending = None
         self.epoch = 0                  # number of load() calls: identifies the run whose state the workspace holds
@@ -1300,6 +1308,12 @@ class SpeculativeSVD:
             if self.plan.pending is self:
                 self.plan.pending = None
 
+    def reverify(self):
+        """certificate of a NEW execution of the same enqueued schedule (whole-step graph replay)"""
+        self.ok = None
+        self.plan.pending = self
+        return self.verify()
+
     def verify(self):
         if self.ok is not None:
             return self.ok
@@ -1318,6 +1332,9 @@ class SpeculativeSVD:
         self.svals = svals
         self.readback = (svals, res, kept_host)
         self.ok = bool(ok and full and not reject)
+        if self.ok and FORCE_VERIFY_FAIL[0] is not None and FORCE_VERIFY_FAIL[0](self):
+            self.ok = False             # test hook: exercise the callers' mis-speculation paths on a sound result
+            return False
         if self.ok:
             _trunc_accept(self.key, self.it, worst, spare=2)
         return self.ok
@@ -1374,9 +1391,20 @@ def truncated_svd_batch(mats, ks, robust=False, speculative=False, resume=None):
     # with a margin of one iteration's convergence factor (a failed check costs ~4 iterations' worth).
     start_it = (hint or 0) if not robust else 0
     replayed = False
+    if CAPTURING_STEP[0]:
+        # the caller records its whole step as ONE CUDA graph: the schedule 'start, n iterations, check' is enqueued
+        # inline (no nested replay, no read-back); the caller verifies the certificate after every replay
+        if not (speculative and hint is not None and not robust and not resumed and plan.cached and plan.graphable
+                and (start_it in plan.graphs or start_it in plan.warmed)):
+            raise NotCapturable("truncated SVD of shape %s is not in its steady state" % (pkey[:3],))
+        plan.schedule(start_it)
+        return SpeculativeSVD(plan, key, start_it, ks, L_, pkey)
     if resumed:
         replayed, start_it = True, resume.it
-    elif (USE_GRAPHS and hint is not None and not robust and plan.cached and plan.graphable and not PROF.enabled):
+    elif (USE_GRAPHS and hint is not None and not robust and plan.cached and plan.graphable and not PROF.enabled
+          and (start_it in plan.graphs or start_it in plan.warmed)):
+        # a schedule is recorded only after it has run eagerly once: building a launch table uploads it from
+        # pageable host memory, which a capturing stream refuses
         try:
             g = plan.graph(start_it)
             g.replay()
@@ -1385,8 +1413,11 @@ def truncated_svd_batch(mats, ks, robust=False, speculative=False, resume=None):
         except (RuntimeError, _cabi.GtnError) as exc:
             if DEBUG_TRUNC:
                 print("[trunc] CUDA graph capture/replay failed, falling back to eager launches:", repr(exc)[:300], flush=True)
-            plan.graphable = False
-            plan.graphs.clear()
+            plan.graph_failures += 1
+            plan.warmed.discard(start_it)
+            if plan.graph_failures >= 3:
+                plan.graphable = False
+            plan.graphs.pop(start_it, None)
             torch.cuda.synchronize()
     if speculative and replayed:
         return SpeculativeSVD(plan, key, start_it, ks, L_, pkey)
@@ -1403,6 +1434,8 @@ def truncated_svd_batch(mats, ks, robust=False, speculative=False, resume=None):
             if it < start_it or it < next_check:
                 continue
             plan.check_enqueue()
+            if it == start_it and not robust:
+                plan.warmed.add(start_it)        # exactly the launches of schedule(start_it) have now been built
         if resumed and it == start_it:
             svals, res, kept_host = resume.readback
         else:

@@ -806,6 +806,8 @@ def _svd_core(mats, ks, cutoff, kind, speculative=False, resume=None):
                 return usv.outs, usv
             SVD_PATH_STATS["truncated" if usv is not None else "truncated_rejected"] += 1
     if usv is None:
+        if _engine_mod.CAPTURING_STEP[0]:
+            raise _engine_mod.NotCapturable("the full Jacobi SVD synchronises with the host")
         usv = batched_svd(mats)
         SVD_PATH_STATS["full"] += 1
     return usv, None

@@ -71,46 +71,202 @@ def _flip_leg_parity(T, leg):
     return gtn.dense._from_bt(bt, T.encoder)
 
 
+# ------------------------------------------------------------------------------------------------
+#  whole-step CUDA graphs
+# ------------------------------------------------------------------------------------------------
+STEP_GRAPH = bool(int(os.environ.get("GTN_STEP_GRAPH", "1")))
+STEP_GRAPH_MAX_BYTES = 160 << 20          # site tensors up to chi = 64 (the graph's pool keeps a step's intermediates)
+STEP_GRAPH_STATS = {"captured": 0, "replayed": 0, "failed_capture": 0, "failed_certificate": 0}
+_step_graphs = {}                         # key -> _StepGraph, or False after a failed capture
+_steady = {}                              # key -> (consecutive verified speculative eager steps, hints then)
+
+
+def _bt_of(T):
+    return T._bt if isinstance(T, gtn.block) else T._get_bt()
+
+
+def _wrap_bt(bt, like):
+    return gtn.block._from_bt(bt, like.shape) if isinstance(like, gtn.block) else gtn.dense._from_bt(bt, like.encoder)
+
+
+def _step_key(name, T, *params):
+    return (name, type(T).__name__, getattr(T, "encoder", None), _bt_of(T).key()) + params
+
+
+class _StepGraph:
+    """One coarse-graining step, from the site tensor to the un-normalised result and its squared norm, recorded
+    as ONE CUDA graph: permutes, packs, the truncated SVD schedules (enqueued inline), unpacks, contractions.
+    Bond dimensions are data dependent in general (rank rule), so the graph encodes the steady state 'every
+    sector keeps its full cut'; after every replay the certificates of its decompositions and that assumption
+    are verified from the pinned read-backs (one synchronisation per step), and the caller falls back to the
+    eager path when they fail.  Normalisation (one scale launch) happens outside: the norm is known to the host
+    only after the synchronisation."""
+
+    def __init__(self, T, body):
+        import torch
+        from . import _cabi, _engine as E
+        self.static = _bt_of(T).clone()
+        self.key = self.static.key()
+        Tin = _wrap_bt(self.static, T)
+        self.norm_host = torch.zeros(1, dtype=torch.float64).pin_memory()
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        c0 = _cabi.launch_count
+        g = torch.cuda.CUDAGraph()
+        E.CAPTURING_STEP[0] = True
+        try:
+            with torch.cuda.stream(side):
+                g.capture_begin()
+                try:
+                    out, pend, norm_of = body(Tin)
+                    self.obt = _bt_of(out)
+                    self.acc = _bt_of(norm_of).sumsq()
+                    self.norm_host.copy_(self.acc, non_blocking=True)
+                finally:
+                    g.capture_end()
+        finally:
+            E.CAPTURING_STEP[0] = False
+        cur.wait_stream(side)
+        self.launches = _cabi.launch_count - c0
+        _cabi.launch_count = c0                       # captured, not executed
+        self.g, self.like = g, out
+        self.pend = [p for p in pend if p is not None]
+        self.its = [p.it for p in self.pend]
+        self.replays = 0
+
+    def replay(self, T):
+        from . import _cabi
+        bt = _bt_of(T)
+        if bt.key() != self.key:
+            return None
+        self.static.buf.copy_(bt.buf)
+        self.g.replay()
+        _cabi.count(self.launches)
+        self.replays += 1
+        for p in self.pend:
+            SPEC_STATS["speculated"] += 1
+            if not p.reverify():                      # the first one synchronises the stream
+                SPEC_STATS["failed"] += 1
+                return None
+        Tnorm = math.sqrt(float(self.norm_host[0]))
+        new = self.obt.clone()
+        new.scale_(1.0 / Tnorm)
+        return _wrap_bt(new, self.like), Tnorm
+
+    def stale(self):
+        """the decompositions now need clearly fewer iterations than were recorded"""
+        from . import _engine as E
+        slack = sum(max(it - E._trunc_iters_hint.get(p.key, it), 0) for p, it in zip(self.pend, self.its))
+        return slack >= 2 and self.replays >= 8
+
+
+def _graph_step(key, T, body):
+    """the step through its recorded graph, or None (not in steady state / capture impossible / certificate failed)"""
+    import torch
+    from . import _engine as E
+    sg = _step_graphs.get(key)
+    if sg is False or E.PROF.enabled:
+        return None
+    if sg is None:
+        n, _ = _steady.get(key, (0, None))
+        bt = _bt_of(T)
+        if n < 2 or bt.buf.numel() * bt.buf.element_size() > STEP_GRAPH_MAX_BYTES:
+            return None
+        try:
+            sg = _StepGraph(T, body)
+        except Exception as exc:                      # NotCapturable, or CUDA refusing an operation during capture
+            STEP_GRAPH_STATS["failed_capture"] += 1
+            STEP_GRAPH_STATS["last_error"] = repr(exc)[:300]
+            torch.cuda.synchronize()
+            _step_graphs[key] = False
+            return None
+        STEP_GRAPH_STATS["captured"] += 1
+        if len(_step_graphs) >= 8:
+            _step_graphs.pop(next(iter(_step_graphs)))
+        _step_graphs[key] = sg
+    r = sg.replay(T)
+    if r is None:
+        STEP_GRAPH_STATS["failed_certificate"] += 1
+        _step_graphs.pop(key, None)
+        _steady[key] = (0, None)
+        return None
+    STEP_GRAPH_STATS["replayed"] += 1
+    if sg.stale():
+        _step_graphs.pop(key, None)                   # record it again with the shorter schedules
+    return r
+
+
+def _note_eager(key, pendings):
+    """bookkeeping after an eager step: it counts towards the steady state when every decomposition was
+    speculated and verified and the iteration hints did not move"""
+    from . import _engine as E
+    ok = bool(pendings) and all(p is not None and p.ok for p in pendings)
+    hints = tuple(E._trunc_iters_hint.get(p.key) for p in pendings) if ok else None
+    n, last = _steady.get(key, (0, None))
+    _steady[key] = ((n + 1) if (ok and (last is None or last == hints)) else (1 if ok else 0), hints)
+
+
+def _trg_enqueue(T, dcut, resume=None, error_test=False):
+    """enqueue one TRG step; returns (un-normalised T', pending decomposition or None, trace error or None)"""
+    T1 = gtn.einsum("ijkl->jkli", T)
+    T2 = gtn.einsum("ijkl->klij", T)
+    pending = None
+    if resume is not None:
+        res = gtn.svd_many([T1, T2], "ab|cd", dcut, resume=resume, site=("trg",))
+    elif SPECULATE:
+        # steady state: the truncated SVD replays its CUDA graph and the rest of the step is enqueued behind it
+        # without waiting for the certificate (one synchronisation per step); verified by the caller
+        res, pending = gtn.svd_many([T1, T2], "ab|cd", dcut, speculative=True, site=("trg",))
+    else:
+        res = gtn.svd_many([T1, T2], "ab|cd", dcut, site=("trg",))
+    (U1, S1, V1), (U2, S2, V2) = res
+    sq = gtn.sqrt(S1)
+    U1 = gtn.einsum("abx,xc->abc", U1, sq)
+    V1 = gtn.einsum("ax,xbc->abc", sq, V1)
+    sq = gtn.sqrt(S2)
+    U2 = gtn.einsum("abx,xc->abc", U2, sq)
+    V2 = gtn.einsum("ax,xbc->abc", sq, V2)
+    VV = gtn.einsum("kwz,lxw->lxzk", V1, V2)
+    UU = gtn.einsum("yxi,zyj->jzxi", U1, U2)
+    Tn = gtn.einsum("lxzk,jzxi->ijkl", VV, UU)
+    err = None
+    if error_test:
+        Z1 = gtn.einsum("ijkl,klij", T, T)
+        Z2 = gtn.einsum("ijij", Tn)
+        err = np.abs(1 - Z2 / Z1)
+    return Tn, pending, err
+
+
 def trg(T, dcut=64, iternum=None, error_test=False):
     """One Levin-Nave TRG step (reference gauge2d.py:1647-1755).  T: shape (m,n,m,n), statistics
-    (1,1,-1,-1).  Returns (T', Tnorm[, err])."""
+    (1,1,-1,-1).  Returns (T', Tnorm[, err]).
+    Steady state (same layout as the last steps, every sector at its full cut): the whole step replays as one
+    CUDA graph (_StepGraph); otherwise it is enqueued eagerly with a speculative truncated SVD."""
     if [T.shape[0], T.shape[1]] != [T.shape[2], T.shape[3]]:
         gtn.error("Error[trg]: The shape must be of the form (m,n,m,n)!")
     if gtn.make_list(T.statistics) != [1, 1, -1, -1]:
         gtn.error("Error[trg]: The statistics must be (1,1,-1,-1)!")
-    T1 = gtn.einsum("ijkl->jkli", T)
-    T2 = gtn.einsum("ijkl->klij", T)
+    use_graph = STEP_GRAPH and SPECULATE and not error_test
+    if use_graph:
+        key = _step_key("trg", T, dcut)
 
-    def tail(res):
-        (U1, S1, V1), (U2, S2, V2) = res
-        sq = gtn.sqrt(S1)
-        U1 = gtn.einsum("abx,xc->abc", U1, sq)
-        V1 = gtn.einsum("ax,xbc->abc", sq, V1)
-        sq = gtn.sqrt(S2)
-        U2 = gtn.einsum("abx,xc->abc", U2, sq)
-        V2 = gtn.einsum("ax,xbc->abc", sq, V2)
-        VV = gtn.einsum("kwz,lxw->lxzk", V1, V2)
-        UU = gtn.einsum("yxi,zyj->jzxi", U1, U2)
-        Tn = gtn.einsum("lxzk,jzxi->ijkl", VV, UU)
-        err = None
-        if error_test:
-            Z1 = gtn.einsum("ijkl,klij", T, T)
-            Z2 = gtn.einsum("ijij", Tn)
-            err = np.abs(1 - Z2 / Z1)
-        Tn, Tnorm = _normalised(Tn)
-        return Tn, Tnorm, err
-    # steady state: the truncated SVD replays its CUDA graph and the rest of the step is enqueued behind it
-    # without waiting for the certificate (one synchronisation per step); verified before returning
-    if SPECULATE:
-        res, pending = gtn.svd_many([T1, T2], "ab|cd", dcut, speculative=True)
-    else:
-        res, pending = gtn.svd_many([T1, T2], "ab|cd", dcut), None
-    Tn, Tnorm, err = tail(res)
+        def body(X):
+            Tn, pending, _ = _trg_enqueue(X, dcut)
+            return Tn, [pending], Tn
+        r = _graph_step(key, T, body)
+        if r is not None:
+            return r
+    Tn, pending, err = _trg_enqueue(T, dcut, error_test=error_test)
+    Tn, Tnorm = _normalised(Tn)
     if pending is not None:
         SPEC_STATS["speculated"] += 1
         if not pending.verify():
             SPEC_STATS["failed"] += 1
-            Tn, Tnorm, err = tail(gtn.svd_many([T1, T2], "ab|cd", dcut, resume=pending))
+            Tn, _, err = _trg_enqueue(T, dcut, resume=pending, error_test=error_test)
+            Tn, Tnorm = _normalised(Tn)
+    if use_graph:
+        _note_eager(key, [pending])
     return (Tn, Tnorm, err) if error_test else (Tn, Tnorm)
 
 
@@ -125,51 +281,69 @@ def _svd_stage(objs, string, cut, site, resume, pend):
     return gtn.svd_many(objs, string, cut, site=site)
 
 
+def _atrg_pass(T1, T2, same, dcut, intermediate_dcut, sites, st, start, resume):
+    """enqueue the stages >= start of one ATRG step (earlier stages: results kept in `st`); returns the
+    un-normalised T' and {site: unverified decomposition}"""
+    pend = {}
+    if start <= 0:
+        st["a"] = _svd_stage([T1] if same else [T1, T2], "li|jk", intermediate_dcut, sites[0],
+                             resume if start == 0 else None, pend)
+    (U1, S1, V1), (U2, S2, V2) = st["a"][0], st["a"][-1]
+    if start <= 1:
+        A = V1
+        B = gtn.einsum("lia,ab->lib", U1, S1)
+        C = gtn.einsum("ab,bjk->ajk", S2, V2)
+        D = U2
+        M = gtn.einsum("ajk,jib->aibk", C, B)
+        st["b"] = _svd_stage([M], "ai|bk", intermediate_dcut, sites[1], resume if start == 1 else None, pend)
+        st["AD"] = (A, D)
+    A, D = st["AD"]
+    U, S, V = st["b"][0]
+    if start <= 2:
+        sq = gtn.sqrt(S)
+        Y = gtn.einsum("abx,xc->abc", U, sq)
+        X = gtn.einsum("ax,xbc->abc", sq, V)
+        Q1 = gtn.einsum("iax,xbj->ijab", D, Y)
+        Q2 = gtn.einsum("kya,ylb->abkl", X, A)
+        Q = gtn.einsum("ijab,abkl->ijkl", Q1, Q2)
+        st["c"] = _svd_stage([Q], "ij|kl", dcut, sites[2], resume if start == 2 else None, pend)
+    U, S, V = st["c"][0]
+    sq = gtn.sqrt(S)
+    H = gtn.einsum("abx,xc->abc", U, sq)
+    G = gtn.einsum("ax,xbc->abc", sq, V)
+    H = gtn.einsum("lai->ila", H)
+    G = gtn.einsum("kaj->ajk", G)
+    return gtn.einsum("ila,ajk->ijkl", H, G), pend
+
+
 def atrg2dy(T1, T2, dcut=64, intermediate_dcut=None, iternum=None, error_test=False, alignment="y"):
     """One ATRG step along y (reference gauge2d.py:1761-1869).
     The three decompositions depend on each other; in steady state each replays its truncated-SVD graph without
     reading the certificate back, the next stage is enqueued behind it, and the step synchronises once (its
     norm).  The certificates are then verified in order; the first stage that fails is resumed from its
-    workspace state and everything after it is repeated."""
+    workspace state and everything after it is repeated.  Once that has worked twice in a row on the same layout
+    the whole step (T1 is T2) is recorded as one CUDA graph (_StepGraph)."""
     if intermediate_dcut is None:
         intermediate_dcut = dcut
+    same = T1 is T2
+    sites = [("atrg", alignment, i) for i in (1, 2, 3)]
+    use_graph = STEP_GRAPH and SPECULATE and same and not error_test
+    if use_graph:
+        key = _step_key("atrg" + alignment, T1, dcut, intermediate_dcut)
+
+        def body(X):
+            Xr = gtn.einsum("ijkl->lijk", X)
+            Tn, pend = _atrg_pass(Xr, Xr, True, dcut, intermediate_dcut, sites, {}, 0, None)
+            return Tn, [pend.get(s_) for s_ in sites], Tn
+        r = _graph_step(key, T1, body)
+        if r is not None:
+            return r
     T1o, T2o = T1, T2
-    same = T1o is T2o
     T1 = gtn.einsum("ijkl->lijk", T1)
     T2 = T1 if same else gtn.einsum("ijkl->lijk", T2)
-    sites = [("atrg", alignment, i) for i in (1, 2, 3)]
-    st, start, resume = {}, 0, None
+    st, start, resume, clean = {}, 0, None, True
     while True:
-        pend = {}
-        if start <= 0:
-            st["a"] = _svd_stage([T1] if same else [T1, T2], "li|jk", intermediate_dcut, sites[0],
-                                 resume if start == 0 else None, pend)
-        (U1, S1, V1), (U2, S2, V2) = st["a"][0], st["a"][-1]
-        if start <= 1:
-            A = V1
-            B = gtn.einsum("lia,ab->lib", U1, S1)
-            C = gtn.einsum("ab,bjk->ajk", S2, V2)
-            D = U2
-            M = gtn.einsum("ajk,jib->aibk", C, B)
-            st["b"] = _svd_stage([M], "ai|bk", intermediate_dcut, sites[1], resume if start == 1 else None, pend)
-            st["AD"] = (A, D)
-        A, D = st["AD"]
-        U, S, V = st["b"][0]
-        if start <= 2:
-            sq = gtn.sqrt(S)
-            Y = gtn.einsum("abx,xc->abc", U, sq)
-            X = gtn.einsum("ax,xbc->abc", sq, V)
-            Q1 = gtn.einsum("iax,xbj->ijab", D, Y)
-            Q2 = gtn.einsum("kya,ylb->abkl", X, A)
-            Q = gtn.einsum("ijab,abkl->ijkl", Q1, Q2)
-            st["c"] = _svd_stage([Q], "ij|kl", dcut, sites[2], resume if start == 2 else None, pend)
-        U, S, V = st["c"][0]
-        sq = gtn.sqrt(S)
-        H = gtn.einsum("abx,xc->abc", U, sq)
-        G = gtn.einsum("ax,xbc->abc", sq, V)
-        H = gtn.einsum("lai->ila", H)
-        G = gtn.einsum("kaj->ajk", G)
-        T = gtn.einsum("ila,ajk->ijkl", H, G)
+        T, pend = _atrg_pass(T1, T2, same, dcut, intermediate_dcut, sites, st, start, resume)
         err = None
         if error_test:
             Z1 = gtn.einsum("IJIK,iKiJ", T1o, T2o)
@@ -190,7 +364,9 @@ def atrg2dy(T1, T2, dcut=64, intermediate_dcut=None, iternum=None, error_test=Fa
                 bad = i
         if bad is None:
             break
-        start, resume = bad, pend[sites[bad]]
+        start, resume, clean = bad, pend[sites[bad]], False
+    if use_graph:
+        _note_eager(key, [pend.get(s_) for s_ in sites] if clean else [])
     return (T, Tnorm, err) if error_test else (T, Tnorm)
 
 

@@ -48,6 +48,7 @@ def _run(monkeypatch, fail_plan, speculate=True):
     monkeypatch.setattr(gtn, "svd_many", svd_many)
     monkeypatch.setattr(g, "_normalised", lambda T: (T, 1.0))
     monkeypatch.setattr(g, "SPECULATE", speculate)
+    monkeypatch.setattr(g, "STEP_GRAPH", False)          # the eager chain is under test here
     g.SPEC_STATS["speculated"] = g.SPEC_STATS["failed"] = 0
     T = ("T0",)
     out, norm = g.atrg2dy(T, T, 32)

@@ -235,8 +235,8 @@ def test_graph_replay_equals_eager_launches(gtn):
 
 def test_speculative_trg_step_and_misspeculation(gtn):
     """gauge2d.trg enqueues the rest of the step behind the replayed SVD graph and verifies the certificate
-    at the end.  (a) same Tnorm as the non-speculative step; (b) a wrong iteration hint (certificate must
-    fail) is caught by verify() and the step is repeated: results unchanged."""
+    at the end.  (a) same Tnorm as the non-speculative step; (b) a failed certificate (forced through the
+    engine's test hook) is caught by verify(), the decomposition is resumed and the step repeated: results unchanged."""
     from grassmanntn_b200 import _engine as E, gauge2d as g
     def chain(spec, sabotage=False):
         old = g.SPECULATE
@@ -245,17 +245,23 @@ def test_speculative_trg_step_and_misspeculation(gtn):
         try:
             T = g.zcap(g.load_initial_tensor()).toblock()
             out = []
-            for i in range(5):
-                if sabotage and i >= 3:
-                    for k in list(E._trunc_iters_hint):
-                        E._trunc_iters_hint[k] = 0           # far too few iterations: the certificate fails
+            for i in range(8):
+                # from the 4th step on every speculative run reports a failed certificate once
+                E.FORCE_VERIFY_FAIL[0] = (lambda p: True) if (sabotage and i >= 3) else None
                 T, n = g.trg(T, 32)[:2]
                 out.append(float(n))
-            return out
+            return out, dict(g.SPEC_STATS)
         finally:
             g.SPECULATE = old
-    ref = chain(False)
-    for other in (chain(True), chain(True, sabotage=True)):
+            E.FORCE_VERIFY_FAIL[0] = None
+    g.STEP_GRAPH, old_graph = False, g.STEP_GRAPH             # the eager speculative path is under test here
+    try:
+        f0 = g.SPEC_STATS["failed"]
+        (ref, _), (good, _), (bad, st) = chain(False), chain(True), chain(True, sabotage=True)
+    finally:
+        g.STEP_GRAPH = old_graph
+    assert st["failed"] - f0 >= 1, st
+    for other in (good, bad):
         for x, y in zip(ref[:3], other[:3]):
             assert abs(x - y) <= 1e-10 * abs(x), (ref, other)
         for x, y in zip(ref[3:], other[3:]):             # from the 4th step on the cut goes through exact multiplets
@@ -266,8 +272,8 @@ def test_speculative_trg_step_and_misspeculation(gtn):
 def test_speculative_atrg_chain_and_misspeculation(gtn):
     """gauge2d.atrg2dy keeps its three dependent decompositions in flight behind each other (one workspace per
     call site) and verifies the certificates in order at the end of the step.  (a) same Tnorm as the
-    non-speculative step; (b) too few iterations at ONE stage (its certificate must fail) are caught, that stage
-    is resumed, the stages behind it are repeated; (c) same with every stage sabotaged."""
+    non-speculative step; (b) a failed certificate at ONE stage (forced through the engine's test hook) is caught,
+    that stage is resumed, the stages behind it are repeated; (c) same with every stage failing."""
     from grassmanntn_b200 import _engine as E, gauge2d as g
     T0 = g.zcap(g.load_initial_tensor()).toblock()
     for _ in range(2):
@@ -279,25 +285,83 @@ def test_speculative_atrg_chain_and_misspeculation(gtn):
         g.SPEC_STATS["speculated"] = g.SPEC_STATS["failed"] = 0
         try:
             T, out = T0, []
-            for i in range(6):
+            for i in range(12):
                 if sabotage is not None and i >= 4:
-                    for k in list(E._trunc_iters_hint):
-                        site = k[1]
-                        if isinstance(site, tuple) and site[0] == "atrg" and (sabotage == "all" or site[2] == sabotage):
-                            E._trunc_iters_hint[k] = 0           # far too few iterations: the certificate fails
+                    # the chosen stage(s) report a failed certificate on every speculative run
+                    E.FORCE_VERIFY_FAIL[0] = lambda p: (isinstance(p.key[1], tuple) and p.key[1][0] == "atrg"
+                                                        and (sabotage == "all" or p.key[1][2] == sabotage))
                 fn = g.atrg2dx if i % 2 == 0 else g.atrg2dy
                 T, n = fn(T, T, 32)[:2]
                 out.append(float(n))
             return out, dict(g.SPEC_STATS)
         finally:
             g.SPECULATE = old
-    ref, st0 = chain(False)
+            E.FORCE_VERIFY_FAIL[0] = None
+    g.STEP_GRAPH, old_graph = False, g.STEP_GRAPH             # the eager speculative chain is under test here
+    try:
+        ref, st0 = chain(False)
+        runs = [chain(True), chain(True, sabotage=2), chain(True, sabotage="all")]
+    finally:
+        g.STEP_GRAPH = old_graph
     assert st0["speculated"] == 0
-    runs = [chain(True), chain(True, sabotage=2), chain(True, sabotage="all")]
     assert runs[0][1]["speculated"] > 0, runs[0][1]
     assert runs[1][1]["failed"] >= 1 and runs[2][1]["failed"] >= 2, (runs[1][1], runs[2][1])
     for other, _ in runs:
         for i, (x, y) in enumerate(zip(ref, other)):
             # the cut goes through exact multiplets of the Z2 spectrum after the first steps
             tol = 1e-10 if i < 1 else 1e-6
+            assert abs(x - y) <= tol * abs(x), (i, ref, other)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("algo", ["trg", "atrg"])
+def test_whole_step_graph_matches_eager(gtn, algo):
+    """In steady state a step is replayed as ONE CUDA graph (gauge2d._StepGraph) and verified from the read-backs.
+    (a) the graph path engages; (b) same Tnorm chain as the eager speculative path; (c) a failed certificate at
+    replay drops the graph and the step is redone eagerly: results unchanged."""
+    from grassmanntn_b200 import _engine as E, gauge2d as g
+    T0 = g.zcap(g.load_initial_tensor()).toblock()
+    for _ in range(2):
+        T0, _ = g.trg(T0, 32)
+    nsteps = 14 if algo == "trg" else 24
+
+    def step(T, i):
+        if algo == "trg":
+            return g.trg(T, 32)[:2]
+        return (g.atrg2dx if i % 2 == 0 else g.atrg2dy)(T, T, 32)[:2]
+
+    def chain(graph, sabotage=False):
+        old = g.STEP_GRAPH
+        g.STEP_GRAPH = graph
+        E._trunc_iters_hint.clear(); E._trunc_rate.clear(); E._trunc_fail.clear()
+        g._step_graphs.clear(); g._steady.clear()
+        g.STEP_GRAPH_STATS.pop("last_error", None)
+        for k in g.STEP_GRAPH_STATS:
+            g.STEP_GRAPH_STATS[k] = 0
+        try:
+            T, out = T0, []
+            for i in range(nsteps):
+                # near the end one decomposition per step reports a failed certificate: the replayed graph is
+                # dropped, the step is redone eagerly (speculative run fails too, is resumed)
+                fails = [2]
+
+                def hook(p):
+                    fails[0] -= 1
+                    return fails[0] >= 0
+                E.FORCE_VERIFY_FAIL[0] = hook if (sabotage and i >= nsteps - 3) else None
+                T, n = step(T, i)
+                out.append(float(n))
+            return out, dict(g.STEP_GRAPH_STATS)
+        finally:
+            g.STEP_GRAPH = old
+            E.FORCE_VERIFY_FAIL[0] = None
+    ref, st0 = chain(False)
+    assert st0["captured"] == 0 and st0["replayed"] == 0
+    got, st1 = chain(True)
+    assert st1["captured"] >= 1 and st1["replayed"] >= 2 and st1["failed_capture"] == 0, st1
+    bad, st2 = chain(True, sabotage=True)
+    assert st2["failed_certificate"] >= 1, st2
+    for other in (got, bad):
+        for i, (x, y) in enumerate(zip(ref, other)):
+            tol = 1e-10 if i < 1 else 1e-6          # exact multiplets at the cut (DESIGN section 7)
             assert abs(x - y) <= tol * abs(x), (i, ref, other)
