@@ -1018,7 +1018,8 @@ class _TruncPlan:
         self.persistent = 2 <= self.maxL <= PERSISTENT_MAX_ROWS
         self.graphable = self.persistent and WHITEN == "chol"
         self.graphs, self.graph_launches = {}, {}
-        self.warmed = set()             # iteration counts whose schedule has run eagerly (its launch tables are cached)
+        self.warmed = set()             # (iterations, mode) whose schedule has run eagerly (its launch tables are cached)
+        self.half_orth = True           # re-orthonormalise between the two products of an iteration (set per run)
         self.graph_failures = 0
         self.host_sweeps = None
         self.pending = None
@@ -1090,8 +1091,14 @@ class _TruncPlan:
     def iterate(self, last, robust=False):
         ws = self.ws
         _ws_gemm(ws, list(zip(self.hQh, self.hW, self.hZh)))
-        self.orth(self.hZh, self.hPh, "q", 1, robust)
-        _ws_gemm(ws, list(zip(self.hPh, self.hWh, self.hYh)))
+        if self.half_orth or robust:
+            self.orth(self.hZh, self.hPh, "q", 1, robust)
+            _ws_gemm(ws, list(zip(self.hPh, self.hWh, self.hYh)))
+        else:
+            # fast mode: Yh = (Qh W) Wh without re-orthonormalising in between -- one whitening per iteration
+            # instead of two.  The dynamic range of the iterate squares, so directions below ~1e-4 s_0 drop out of
+            # the Gram matrix; sites where that stalls the iteration are switched to the safe mode for good
+            _ws_gemm(ws, list(zip(self.hZh, self.hWh, self.hYh)))
         self.orth(self.hYh, self.hQh, "p", 2 if last else 1, robust)
 
     def check_enqueue(self, allow_host=True):
@@ -1209,7 +1216,11 @@ class _TruncPlan:
             self.iterate(it == n)
         self.check_enqueue(allow_host=False)
 
+    def gkey(self, n):
+        return (n, self.half_orth)
+
     def graph(self, n):
+        n_, n = n, self.gkey(n)
         g = self.graphs.get(n)
         if g is None:
             cur = torch.cuda.current_stream()
@@ -1220,7 +1231,7 @@ class _TruncPlan:
             with torch.cuda.stream(side):
                 g.capture_begin()
                 try:
-                    self.schedule(n)
+                    self.schedule(n_)
                 finally:
                     g.capture_end()
             cur.wait_stream(side)
@@ -1340,7 +1351,39 @@ class SpeculativeSVD:
         return self.ok
 
 
+FAST_ITER = bool(int(__import__("os").environ.get("GTN_FAST_ITER", "1")))
+FAST_ITER_MAX = 8
+_trunc_mode = {}            # (batch shape, call site) -> "safe" once the fast iteration has failed there
+
+
 def truncated_svd_batch(mats, ks, robust=False, speculative=False, resume=None):
+    """_truncated_svd_batch with the per-site choice of iteration: 'fast' (one whitening per iteration) until it
+    fails to deliver a certified result at this (batch shape, call site), then 'safe' (two) for good."""
+    P_ = tuple(m.shape[0] for m in mats)
+    Q_ = tuple(m.shape[1] for m in mats)
+    key = ((P_, Q_, tuple(ks), str(mats[0].dtype), str(mats[0].device)), SVD_SITE[0])
+    if resume is not None:
+        key = resume.key
+    fast = FAST_ITER and not robust and _trunc_mode.get(key, "fast") == "fast"
+    out = _truncated_svd_batch(mats, ks, robust, speculative, resume, fast)
+    if out is None and fast:
+        _trunc_mode[key] = "safe"
+        _trunc_fail.pop(key, None)
+        _trunc_iters_hint.pop(key, None)
+        _trunc_rate.pop(key, None)
+        if DEBUG_TRUNC:
+            print("[trunc] fast iteration failed at", key[1], "-> safe mode", flush=True)
+        out = _truncated_svd_batch(mats, ks, robust, False, None, False)
+    elif fast and isinstance(out, list) and truncated_svd_batch.last_iters >= FAST_ITER_MAX:
+        # certified, but after so many iterations that the safe mode (better conditioned, fewer iterations) is
+        # the cheaper one at this site
+        _trunc_mode[key] = "safe"
+        _trunc_iters_hint.pop(key, None)
+        _trunc_rate.pop(key, None)
+    return out
+
+
+def _truncated_svd_batch(mats, ks, robust=False, speculative=False, resume=None, fast=False):
     """Top-k_b singular triplets of every matrix in `mats` by randomized subspace iteration:
          Yh = G Wh ; Qh = orth_rows(Yh) ; [Zh = Qh W ; Ph = orth_rows(Zh) ; Yh = Ph Wh ; Qh = orth_rows(Yh)]*
          B = Qh W (l x q) ; B = Ub S Vh (small one-sided Jacobi) ; U = Qh^H Ub
@@ -1378,6 +1421,8 @@ def truncated_svd_batch(mats, ks, robust=False, speculative=False, resume=None):
         plan = _trunc_plan((pkey, SVD_SITE[0]) if speculative else pkey, P_, Q_, ks, L_, dt, dev)
     if getattr(plan, "pending", None) is not None:
         plan.pending.verify()               # an unverified speculative run still owns the read-back buffer
+    if not (resume is not None and resume.plan is plan):
+        plan.half_orth = not fast           # (a resumed run continues in the mode it was started in)
     resumed = (resume is not None and resume.plan is plan and resume.readback is not None
                and resume.epoch == plan.epoch and not robust)
     if resumed:
@@ -1395,29 +1440,29 @@ def truncated_svd_batch(mats, ks, robust=False, speculative=False, resume=None):
         # the caller records its whole step as ONE CUDA graph: the schedule 'start, n iterations, check' is enqueued
         # inline (no nested replay, no read-back); the caller verifies the certificate after every replay
         if not (speculative and hint is not None and not robust and not resumed and plan.cached and plan.graphable
-                and (start_it in plan.graphs or start_it in plan.warmed)):
+                and (plan.gkey(start_it) in plan.graphs or plan.gkey(start_it) in plan.warmed)):
             raise NotCapturable("truncated SVD of shape %s is not in its steady state" % (pkey[:3],))
         plan.schedule(start_it)
         return SpeculativeSVD(plan, key, start_it, ks, L_, pkey)
     if resumed:
         replayed, start_it = True, resume.it
     elif (USE_GRAPHS and hint is not None and not robust and plan.cached and plan.graphable and not PROF.enabled
-          and (start_it in plan.graphs or start_it in plan.warmed)):
+          and (plan.gkey(start_it) in plan.graphs or plan.gkey(start_it) in plan.warmed)):
         # a schedule is recorded only after it has run eagerly once: building a launch table uploads it from
         # pageable host memory, which a capturing stream refuses
         try:
             g = plan.graph(start_it)
             g.replay()
-            count(plan.graph_launches[start_it])
+            count(plan.graph_launches[plan.gkey(start_it)])
             replayed = True
         except (RuntimeError, _cabi.GtnError) as exc:
             if DEBUG_TRUNC:
                 print("[trunc] CUDA graph capture/replay failed, falling back to eager launches:", repr(exc)[:300], flush=True)
             plan.graph_failures += 1
-            plan.warmed.discard(start_it)
+            plan.warmed.discard(plan.gkey(start_it))
             if plan.graph_failures >= 3:
                 plan.graphable = False
-            plan.graphs.pop(start_it, None)
+            plan.graphs.pop(plan.gkey(start_it), None)
             torch.cuda.synchronize()
     if speculative and replayed:
         return SpeculativeSVD(plan, key, start_it, ks, L_, pkey)
@@ -1435,7 +1480,7 @@ def truncated_svd_batch(mats, ks, robust=False, speculative=False, resume=None):
                 continue
             plan.check_enqueue()
             if it == start_it and not robust:
-                plan.warmed.add(start_it)        # exactly the launches of schedule(start_it) have now been built
+                plan.warmed.add(plan.gkey(start_it))        # exactly the launches of schedule(start_it) have now been built
         if resumed and it == start_it:
             svals, res, kept_host = resume.readback
         else:
