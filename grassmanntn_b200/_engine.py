@@ -1018,8 +1018,7 @@ class _TruncPlan:
         self.persistent = 2 <= self.maxL <= PERSISTENT_MAX_ROWS
         self.graphable = self.persistent and WHITEN == "chol"
         self.graphs, self.graph_launches = {}, {}
-        self.warmed = set()             # (iterations, mode) whose schedule has run eagerly (its launch tables are cached)
-        self.half_orth = True           # re-orthonormalise between the two products of an iteration (set per run)
+        self.warmed = set()             # iteration counts whose schedule has run eagerly (its launch tables are cached)
         self.graph_failures = 0
         self.host_sweeps = None
         self.pending = None
@@ -1091,14 +1090,11 @@ class _TruncPlan:
     def iterate(self, last, robust=False):
         ws = self.ws
         _ws_gemm(ws, list(zip(self.hQh, self.hW, self.hZh)))
-        if self.half_orth or robust:
-            self.orth(self.hZh, self.hPh, "q", 1, robust)
-            _ws_gemm(ws, list(zip(self.hPh, self.hWh, self.hYh)))
-        else:
-            # fast mode: Yh = (Qh W) Wh without re-orthonormalising in between -- one whitening per iteration
-            # instead of two.  The dynamic range of the iterate squares, so directions below ~1e-4 s_0 drop out of
-            # the Gram matrix; sites where that stalls the iteration are switched to the safe mode for good
-            _ws_gemm(ws, list(zip(self.hZh, self.hWh, self.hYh)))
+        # (skipping this re-orthonormalisation -- one whitening per iteration -- was tried: the iterate's dynamic
+        # range squares, directions below ~1e-4 s_0 drop out of the Gram matrix, and every site of the Z2 TRG /
+        # ATRG chains eventually stalled)
+        self.orth(self.hZh, self.hPh, "q", 1, robust)
+        _ws_gemm(ws, list(zip(self.hPh, self.hWh, self.hYh)))
         self.orth(self.hYh, self.hQh, "p", 2 if last else 1, robust)
 
     def check_enqueue(self, allow_host=True):
@@ -1217,7 +1213,7 @@ class _TruncPlan:
         self.check_enqueue(allow_host=False)
 
     def gkey(self, n):
-        return (n, self.half_orth)
+        return n
 
     def graph(self, n):
         n_, n = n, self.gkey(n)
@@ -1284,14 +1280,42 @@ def _trunc_certificate(svals, res, kept_host, ks, L_):
     return ok, worst, False
 
 
-def _trunc_accept(key, it, worst, spare=1):
-    """bookkeeping of an accepted run: remember the iteration count for this (shape, call site), lowered when
-    the run passed with a margin of d convergence factors (d - spare fewer next time, at most half).
-    Speculative runs keep two spare factors: a failed speculation costs the tail of the caller's step."""
+PROBE_EVERY = int(__import__("os").environ.get("GTN_PROBE_EVERY", "6"))
+_trunc_probe = {}           # (batch shape, call site) -> {"stable": accepts without change, "every": probe interval, ...}
+
+
+def _trunc_accept(key, it, worst, spare=1, clean=True):
+    """bookkeeping of an accepted run: remember the iteration count for this (shape, call site).
+    * lowered when the run passed with a margin of d convergence factors (d - spare fewer next time, at most half;
+      speculative runs keep two spare factors: a failed speculation costs the tail of the caller's step);
+    * the residuals floor at rounding level, so a margin cannot show that far fewer iterations would do (a chain
+      whose spectrum gets easier kept its early count of 5 where 1 suffices): after `every` accepts of the same
+      count the memory is dropped and the next run derives the count afresh (check after the range finder, then
+      at the predicted iteration).  When that does not find a lower count, probing becomes four times rarer;
+    * a clean accept (passed at its first check) never raises the count: a whole-step graph keeps replaying its
+      recorded count while a lower one waits for the graph to be recorded again."""
     rate = _trunc_rate.get(key, 0.2)
     d = int(math.log(max(worst, 1e-16) / TRUNC_TOL) / math.log(rate)) if worst < TRUNC_TOL else 0
-    _trunc_iters_hint[key] = max(it - min(max(d - spare, 0), (it + 1) // 2), 0)
+    new = max(it - min(max(d - spare, 0), (it + 1) // 2), 0)
+    st = _trunc_probe.setdefault(key, {"stable": 0, "every": PROBE_EVERY, "before": None})
+    old = _trunc_iters_hint.get(key)
     _trunc_fail[key] = 0
+    if old is None and st["before"] is not None:
+        # the run after a probe: did deriving the count afresh pay?
+        if new >= st["before"]:
+            st["every"] = min(st["every"] * 4, 1 << 20)
+        st["before"], st["stable"] = None, 0
+    elif clean:
+        if old is not None:
+            new = min(new, old)
+        st["stable"] = st["stable"] + 1 if (new == old and new == it) else 0      # this very count keeps passing
+        if PROBE_EVERY > 0 and st["stable"] >= st["every"] and new > 0:
+            st["before"], st["stable"] = new, 0
+            _trunc_iters_hint.pop(key, None)
+            return
+    else:
+        st["stable"] = 0
+    _trunc_iters_hint[key] = new
 
 
 class SpeculativeSVD:
@@ -1351,39 +1375,7 @@ class SpeculativeSVD:
         return self.ok
 
 
-FAST_ITER = bool(int(__import__("os").environ.get("GTN_FAST_ITER", "1")))
-FAST_ITER_MAX = 8
-_trunc_mode = {}            # (batch shape, call site) -> "safe" once the fast iteration has failed there
-
-
 def truncated_svd_batch(mats, ks, robust=False, speculative=False, resume=None):
-    """_truncated_svd_batch with the per-site choice of iteration: 'fast' (one whitening per iteration) until it
-    fails to deliver a certified result at this (batch shape, call site), then 'safe' (two) for good."""
-    P_ = tuple(m.shape[0] for m in mats)
-    Q_ = tuple(m.shape[1] for m in mats)
-    key = ((P_, Q_, tuple(ks), str(mats[0].dtype), str(mats[0].device)), SVD_SITE[0])
-    if resume is not None:
-        key = resume.key
-    fast = FAST_ITER and not robust and _trunc_mode.get(key, "fast") == "fast"
-    out = _truncated_svd_batch(mats, ks, robust, speculative, resume, fast)
-    if out is None and fast:
-        _trunc_mode[key] = "safe"
-        _trunc_fail.pop(key, None)
-        _trunc_iters_hint.pop(key, None)
-        _trunc_rate.pop(key, None)
-        if DEBUG_TRUNC:
-            print("[trunc] fast iteration failed at", key[1], "-> safe mode", flush=True)
-        out = _truncated_svd_batch(mats, ks, robust, False, None, False)
-    elif fast and isinstance(out, list) and truncated_svd_batch.last_iters >= FAST_ITER_MAX:
-        # certified, but after so many iterations that the safe mode (better conditioned, fewer iterations) is
-        # the cheaper one at this site
-        _trunc_mode[key] = "safe"
-        _trunc_iters_hint.pop(key, None)
-        _trunc_rate.pop(key, None)
-    return out
-
-
-def _truncated_svd_batch(mats, ks, robust=False, speculative=False, resume=None, fast=False):
     """Top-k_b singular triplets of every matrix in `mats` by randomized subspace iteration:
          Yh = G Wh ; Qh = orth_rows(Yh) ; [Zh = Qh W ; Ph = orth_rows(Zh) ; Yh = Ph Wh ; Qh = orth_rows(Yh)]*
          B = Qh W (l x q) ; B = Ub S Vh (small one-sided Jacobi) ; U = Qh^H Ub
@@ -1421,8 +1413,6 @@ def _truncated_svd_batch(mats, ks, robust=False, speculative=False, resume=None,
         plan = _trunc_plan((pkey, SVD_SITE[0]) if speculative else pkey, P_, Q_, ks, L_, dt, dev)
     if getattr(plan, "pending", None) is not None:
         plan.pending.verify()               # an unverified speculative run still owns the read-back buffer
-    if not (resume is not None and resume.plan is plan):
-        plan.half_orth = not fast           # (a resumed run continues in the mode it was started in)
     resumed = (resume is not None and resume.plan is plan and resume.readback is not None
                and resume.epoch == plan.epoch and not robust)
     if resumed:
@@ -1518,7 +1508,8 @@ def _truncated_svd_batch(mats, ks, robust=False, speculative=False, resume=None,
             next_check = min(it + max(1, min(int(math.ceil(need)), 6)), TRUNC_MAX_ITERS)
         prev_worst, prev_it = worst, it
         if ok:
-            _trunc_accept(key, it + (1 if resumed else 0), worst, spare=2 if resumed else 1)
+            _trunc_accept(key, it + (1 if resumed else 0), worst, spare=2 if resumed else 1,
+                          clean=(it == start_it and not resumed))
             out = plan.finalize()
             return [(u, svals[b], v) for b, (u, _, v) in enumerate(out)]
     _trunc_fail[key] = _trunc_fail.get(key, 0) + 1

@@ -78,6 +78,8 @@ STEP_GRAPH = bool(int(os.environ.get("GTN_STEP_GRAPH", "1")))
 STEP_GRAPH_MAX_BYTES = 160 << 20          # site tensors up to chi = 64 (the graph's pool keeps a step's intermediates)
 STEP_GRAPH_STATS = {"captured": 0, "replayed": 0, "failed_capture": 0, "failed_certificate": 0}
 _step_graphs = {}                         # key -> _StepGraph, or False after a failed capture
+_capture_failures = {}
+_POOL = [None, None, None]       # pool handle, keeper graph, keeper tensor
 _steady = {}                              # key -> (consecutive verified speculative eager steps, hints then)
 
 
@@ -114,10 +116,24 @@ class _StepGraph:
         side.wait_stream(cur)
         c0 = _cabi.launch_count
         g = torch.cuda.CUDAGraph()
+        # one memory pool for all step graphs: a graph recorded again (shorter SVD schedules) reuses the blocks of the
+        # one it replaces instead of paying ~100 cudaMallocs (60-600 ms measured for an ATRG step).  Safe because
+        # step graphs never run concurrently and every result is copied out of the pool right after its replay
+        if _POOL[0] is None:
+            # torch frees a pool with its last graph: a one-node keeper graph holds it for the life of the process
+            handle = torch.cuda.graph_pool_handle()
+            keeper = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(side):
+                keeper.capture_begin(pool=handle)
+                try:
+                    _POOL[2] = torch.zeros(1, device="cuda")
+                finally:
+                    keeper.capture_end()
+            _POOL[0], _POOL[1] = handle, keeper
         E.CAPTURING_STEP[0] = True
         try:
             with torch.cuda.stream(side):
-                g.capture_begin()
+                g.capture_begin(pool=_POOL[0])
                 try:
                     out, pend, norm_of = body(Tin)
                     self.obt = _bt_of(out)
@@ -155,10 +171,10 @@ class _StepGraph:
         return _wrap_bt(new, self.like), Tnorm
 
     def stale(self):
-        """the decompositions now need clearly fewer iterations than were recorded"""
+        """a decomposition now needs fewer iterations than were recorded, or its count is being derived afresh"""
         from . import _engine as E
-        slack = sum(max(it - E._trunc_iters_hint.get(p.key, it), 0) for p, it in zip(self.pend, self.its))
-        return slack >= 2 and self.replays >= 8
+        hints = E._trunc_iters_hint
+        return any(p.key not in hints or hints[p.key] < it for p, it in zip(self.pend, self.its))
 
 
 def _graph_step(key, T, body):
@@ -179,7 +195,10 @@ def _graph_step(key, T, body):
             STEP_GRAPH_STATS["failed_capture"] += 1
             STEP_GRAPH_STATS["last_error"] = repr(exc)[:300]
             torch.cuda.synchronize()
-            _step_graphs[key] = False
+            _steady[key] = (0, None)                  # a few eager steps first (they build what was missing)
+            _capture_failures[key] = _capture_failures.get(key, 0) + (0 if isinstance(exc, E.NotCapturable) else 1)
+            if _capture_failures[key] >= 3:
+                _step_graphs[key] = False             # CUDA keeps refusing: stay eager on this layout
             return None
         STEP_GRAPH_STATS["captured"] += 1
         if len(_step_graphs) >= 8:
@@ -193,7 +212,8 @@ def _graph_step(key, T, body):
         return None
     STEP_GRAPH_STATS["replayed"] += 1
     if sg.stale():
-        _step_graphs.pop(key, None)                   # record it again with the shorter schedules
+        _step_graphs.pop(key, None)                   # record it again with the shorter schedules ...
+        _steady[key] = (0, None)                      # ... after eager steps have run (and built) them
     return r
 
 

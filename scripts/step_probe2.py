@@ -8,7 +8,7 @@ g = gtn.gauge2d
 T0 = g.zcap(g.load_initial_tensor()).toblock()
 for _ in range(2):
     T0, _ = g.trg(T0, 32)
-for algo, nsteps in (("trg", 16), ("atrg", 28)):
+for algo, nsteps in (("trg", 60), ("atrg", 80)):
     X = T0
     ts = []
     for i in range(nsteps):
@@ -21,4 +21,4 @@ for algo, nsteps in (("trg", 16), ("atrg", 28)):
     tail = ts[-6:]
     print(algo, "last6 mean %.3f ms" % (sum(tail) / len(tail)), "all:", " ".join("%.2f" % t for t in ts))
     print("   hints", {str(k[1]): v for k, v in E._trunc_iters_hint.items()}, "paths", _ops.SVD_PATH_STATS,
-          "graph", g.STEP_GRAPH_STATS, "spec", g.SPEC_STATS, "Tnorm %.13g" % n, flush=True)
+          "graph", g.STEP_GRAPH_STATS, "spec", g.SPEC_STATS, "probe", {str(k[1]): v["every"] for k, v in E._trunc_probe.items()}, "Tnorm %.13g" % n, flush=True)

@@ -20,7 +20,7 @@ def step(X):
         return g.trg(X, args.chi)[0]
     return g.atrg2dy(X, X, args.chi)[0]
 X = T
-for _ in range(4):
+for _ in range(24 if args.method != "trg" else 14):      # reach the steady state (hints settled, step graph recorded)
     X = step(X)
 torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
