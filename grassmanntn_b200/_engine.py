@@ -1280,6 +1280,7 @@ def _trunc_certificate(svals, res, kept_host, ks, L_):
     return ok, worst, False
 
 
+ADAPT = [True]              # False: iteration counts are frozen (gauge2d.freeze): no lowering, no probing
 PROBE_EVERY = int(__import__("os").environ.get("GTN_PROBE_EVERY", "6"))
 _trunc_probe = {}           # (batch shape, call site) -> {"stable": accepts without change, "every": probe interval, ...}
 
@@ -1294,6 +1295,9 @@ def _trunc_accept(key, it, worst, spare=1, clean=True):
       at the predicted iteration).  When that does not find a lower count, probing becomes four times rarer;
     * a clean accept (passed at its first check) never raises the count: a whole-step graph keeps replaying its
       recorded count while a lower one waits for the graph to be recorded again."""
+    if not ADAPT[0] and clean and key in _trunc_iters_hint:
+        _trunc_fail[key] = 0
+        return
     rate = _trunc_rate.get(key, 0.2)
     d = int(math.log(max(worst, 1e-16) / TRUNC_TOL) / math.log(rate)) if worst < TRUNC_TOL else 0
     new = max(it - min(max(d - spare, 0), (it + 1) // 2), 0)

@@ -83,6 +83,15 @@ _POOL = [None, None, None]       # pool handle, keeper graph, keeper tensor
 _steady = {}                              # key -> (consecutive verified speculative eager steps, hints then)
 
 
+def freeze(flag=True):
+    """Freeze (or release) the engine's adaptation: the truncated SVD keeps its learnt iteration counts (no lowering,
+    no periodic re-derivation) and recorded step graphs are not recorded again.  For timing loops and for
+    production runs that repeat the same step shape; certificates are still verified on every step and a
+    failed one still falls back to the eager path."""
+    from . import _engine as E
+    E.ADAPT[0] = not flag
+
+
 def _bt_of(T):
     return T._bt if isinstance(T, gtn.block) else T._get_bt()
 
@@ -174,6 +183,8 @@ class _StepGraph:
         """a decomposition now needs fewer iterations than were recorded, or its count is being derived afresh"""
         from . import _engine as E
         hints = E._trunc_iters_hint
+        if not E.ADAPT[0]:
+            return False
         return any(p.key not in hints or hints[p.key] < it for p, it in zip(self.pend, self.its))
 
 
@@ -189,6 +200,8 @@ def _graph_step(key, T, body):
         bt = _bt_of(T)
         if n < 2 or bt.buf.numel() * bt.buf.element_size() > STEP_GRAPH_MAX_BYTES:
             return None
+        import time as _time
+        t0 = _time.perf_counter()
         try:
             sg = _StepGraph(T, body)
         except Exception as exc:                      # NotCapturable, or CUDA refusing an operation during capture
@@ -201,6 +214,7 @@ def _graph_step(key, T, body):
                 _step_graphs[key] = False             # CUDA keeps refusing: stay eager on this layout
             return None
         STEP_GRAPH_STATS["captured"] += 1
+        STEP_GRAPH_STATS["capture_ms"] = STEP_GRAPH_STATS.get("capture_ms", []) + [round((_time.perf_counter() - t0) * 1e3, 1)]
         if len(_step_graphs) >= 8:
             _step_graphs.pop(next(iter(_step_graphs)))
         _step_graphs[key] = sg

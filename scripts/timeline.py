@@ -19,13 +19,13 @@ def step(X):
     if args.method == "trg":
         return g.trg(X, args.chi)[0]
     return g.atrg2dy(X, X, args.chi)[0]
-X = T
-for _ in range(24 if args.method != "trg" else 14):      # reach the steady state (hints settled, step graph recorded)
-    X = step(X)
+for _ in range(30):      # reach the steady state on the bench's step (same tensor every time): counts settled, graph recorded
+    step(T)
+g.freeze(True)
 torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
-    X = T
     for _ in range(args.steps):
-        X = step(X)
+        X = step(T)
     torch.cuda.synchronize()
+print("steps", args.steps, "step graph", g.STEP_GRAPH_STATS)
 print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=70))

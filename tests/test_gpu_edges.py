@@ -336,6 +336,7 @@ def test_whole_step_graph_matches_eager(gtn, algo):
         E._trunc_iters_hint.clear(); E._trunc_rate.clear(); E._trunc_fail.clear()
         g._step_graphs.clear(); g._steady.clear()
         g.STEP_GRAPH_STATS.pop("last_error", None)
+        g.STEP_GRAPH_STATS.pop("capture_ms", None)
         for k in g.STEP_GRAPH_STATS:
             g.STEP_GRAPH_STATS[k] = 0
         try:
