@@ -692,7 +692,6 @@ def join_legs(InpObj, string_inp, make_format="standard", intermediate_stat=None
                 alpha.append(g["axes"][k])
     data = _engine.dense_sign_permute(obj.data, perm, alpha)
     new_stats, new_shape, final_stats, final_shape = _joined_layout(groups, intermediate_stat)
-    global skip_power_of_two_check
     J = dense(data.reshape(new_shape), statistics=new_stats)
     if make_format == "matrix":
         J = J.switch_format()

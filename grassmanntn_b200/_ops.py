@@ -499,9 +499,6 @@ def _decompose_prepare(bt, nl, kind):
     layR = group_layout([bt.leg(a) for a in Rl])
     layC = group_layout([bt.leg(a) for a in Cl])
     sectors = [0, 1] if (fR and fC) else [0]
-    if fR != fC:
-        # one side purely bosonic: an even tensor then lives entirely in the parity-0 rows/cols
-        pass
     alpha, beta, Q = (_join_sign_terms(Rl, bt.stats, ferm) if fR else (set(), set(), set()))
     rows = {s: layR.sector(s) for s in (0, 1)}
     cols = {s: layC.sector(s) for s in (0, 1)}

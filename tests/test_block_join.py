@@ -142,33 +142,6 @@ def _check_product_case(gtn, k, device):
         gtn.einsum("".join("abcdef"[:J.ndim]) + "->" + "".join("abcdef"[:J.ndim]), J)
 
 
-@pytest.fixture
-def host_tables(monkeypatch):
-    """run the product's host code without a GPU: buffers on the host, every sign+permute launch replaced by the
-    numpy emulation of the kernel's addressing / sign rule"""
-    import torch
-    from test_tables_cpu import emulate
-    from grassmanntn_b200 import _engine as E, _ops
-
-    class HostPlan:
-        def __init__(self, jobs):
-            self.jobs = jobs
-
-        def run(self, src, dst, scale=1.0):
-            s, d = src.numpy(), dst.numpy()
-            for f, tabs in self.jobs:
-                emulate(f, tabs, s, d, scale)
-    saved = dict(E._plan_cache)
-    E._plan_cache.clear()
-    monkeypatch.setattr(E, "PermutePlan", HostPlan)
-    monkeypatch.setattr(_ops, "PermutePlan", HostPlan)
-    monkeypatch.setattr(E, "require_cuda", lambda: torch.device("cpu"))
-    monkeypatch.setattr(_ops, "require_cuda", lambda: torch.device("cpu"))
-    yield
-    E._plan_cache.clear()
-    E._plan_cache.update(saved)
-
-
 @pytest.mark.parametrize("k", range(len(CASES)))
 def test_product_tables_join_split_block_vs_reference(host_tables, k):
     import grassmanntn_b200 as gtn
