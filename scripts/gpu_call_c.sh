@@ -1,7 +1,10 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 300 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
-   --log-file gpurun_out/launches_r1c.csv python scripts/ncu_step.py 3 > gpurun_out/c_ncu_list.log 2>&1; tail -1 gpurun_out/c_ncu_list.log
-timeout 400 ncu --profile-from-start off --set full --clock-control none --import-source on \
-   -k regex:"jacobi_persistent|gram_rotate|chol_whiten|grouped_gemm" -c 14 -o gpurun_out/r1c_step python scripts/ncu_step.py 1 > gpurun_out/c_ncu_full.log 2>&1; tail -1 gpurun_out/c_ncu_full.log
-timeout 300 python scripts/timeline.py --steps 5 > gpurun_out/r1c_trg_chi32_timeline.txt 2>&1; tail -3 gpurun_out/r1c_trg_chi32_timeline.txt
+( time timeout 600 python -m pytest tests -m gpu -x -q ) > gpurun_out/e_pytest.log 2>&1; tail -3 gpurun_out/e_pytest.log | head -1
+timeout 300 python __graft_entry__.py smoke 2>&1 | tail -1
+( time timeout 600 python bench.py --chi 64 --no-micro ) > gpurun_out/e_bench_chi64.json 2> gpurun_out/e_bench_chi64.err; tail -4 gpurun_out/e_bench_chi64.err
+python - <<EOF
+import json
+d=json.load(open('gpurun_out/e_bench_chi64.json'))
+print({k:d[k] for k in ['value','ms_per_step','gpu_launches']}, d['e2e']['value'], d['cpu_baseline'], d['extra']['step_graph'], d['extra']['speculation'], d['extra']['svd_paths'])
+EOF
