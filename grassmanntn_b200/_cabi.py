@@ -30,7 +30,8 @@ class GemmGroup(C.Structure):
                 ("lda", C.c_int64), ("ldb", C.c_int64), ("ldc", C.c_int64),
                 ("batch_stride_a", C.c_int64), ("batch_stride_b", C.c_int64), ("batch_stride_c", C.c_int64),
                 ("m", C.c_int32), ("n", C.c_int32), ("k", C.c_int32), ("batch", C.c_int32),
-                ("alpha", C.c_double), ("beta", C.c_double), ("tile_start", C.c_int64)]
+                ("alpha", C.c_double), ("beta", C.c_double), ("tile_start", C.c_int64),
+                ("flags", C.c_int32), ("reserved", C.c_int32)]
 
 
 class SvdProblem(C.Structure):

@@ -696,9 +696,14 @@ class GemmPlan:
             a.batch_stride_c = g.get("bsc", 0)
             a.m, a.n, a.k, a.batch = g["m"], g["n"], g["k"], g.get("batch", 1)
             a.alpha, a.beta = g.get("alpha", 1.0), g.get("beta", 0.0)
+            a.flags = g.get("flags", 0)
         # skinny problems (a side <= 48) get the 32x32 / deep-K configuration
         if config is None:
             config = 1 if all(min(g["m"], g["n"]) <= SKINNY_MAX for g in groups) else 0
+        if any(g.get("flags", 0) & 1 for g in groups):
+            # conj-transposed B operand: a whole-launch property, only built for the 32x32 configuration
+            assert all(g.get("flags", 0) & 1 for g in groups)
+            config = 3
         self.config = config
         self.tiles = int(lib.gtn_gemm_plan_host(arr, self.n, dtype_code(dtype), self.config))
         self.dev = _to_dev_bytes(bytes(arr))
@@ -911,6 +916,7 @@ def _ws_ctranspose(ws, pairs):
 DEBUG_TRUNC = bool(int(__import__("os").environ.get("GTN_DEBUG_TRUNC", "0")))
 WHITEN = "chol"            # "chol": pivoted Cholesky kernel (default); "eigh": Jacobi eigen-solver kernel
 USE_GRAPHS = bool(int(__import__("os").environ.get("GTN_GRAPHS", "1")))
+GEMM_CONJ_TRANS = bool(int(__import__("os").environ.get("GTN_GEMM_CONJ_TRANS", "0")))
 PREROTATE = bool(int(__import__("os").environ.get("GTN_PREROTATE", "1")))
 # in-kernel Jacobi tolerance of the Gram pre-rotation: the Gram matrix only determines the rows to ~1e-8
 # relative for the small ones, the global Jacobi kernel polishes the rest
@@ -1048,18 +1054,25 @@ class _TruncPlan:
                                           _stream()), "gtn_chol_whiten")
 
     def _gram(self, cur, curH):
-        """hT1_b = sum_s cur_b[:, Ks] curH_b[Ks, :]  as NS partial slices (one grouped launch)"""
+        """hT1_b = sum_s cur_b[:, Ks] cur_b[:, Ks]^H  as NS partial slices (one grouped launch).
+        curH is None: the GEMM reads its B operand as the conjugate transpose of cur itself
+        (GTN_GEMM_B_CONJ_TRANS) -- no transposed copy, one launch fewer per orthonormalisation."""
         ws, NS = self.ws, self.NS
-        if NS == 1:
+        if NS == 1 and curH is not None:
             _ws_gemm(ws, list(zip(cur, curH, self.hT1)))
             return
         groups = []
-        for a, bh, c in zip(cur, curH, self.hT1):
+        for i, (a, c) in enumerate(zip(cur, self.hT1)):
             _, l, K = ws.items[a]
             kc = -(-K // NS)
             for sp in range(NS):
                 k0 = min(sp * kc, K)
                 kk = min(kc, K - k0)
+                if curH is None:
+                    groups.append(dict(a_off=ws.off(a) + k0, b_off=ws.off(a) + k0, c_off=ws.off(c) + sp * l * l,
+                                       lda=K, ldb=K, ldc=l, m=l, n=l, k=kk, alpha=1.0, beta=0.0, flags=1))
+                    continue
+                bh = curH[i]
                 groups.append(dict(a_off=ws.off(a) + k0, b_off=ws.off(bh) + k0 * l, c_off=ws.off(c) + sp * l * l,
                                    lda=K, ldb=l, ldc=l, m=l, n=l, k=kk, alpha=1.0, beta=0.0))
         key = ("wsgram", str(ws.dtype), tuple(tuple(sorted(g.items())) for g in groups))
@@ -1076,8 +1089,11 @@ class _TruncPlan:
         hS = self.hSp if side == "p" else self.hSq
         cur = src
         for ps in range(passes):
-            _ws_ctranspose(ws, list(zip(cur, hC)))
-            self._gram(cur, hC)                                      # Gram  l x l
+            if GEMM_CONJ_TRANS:
+                self._gram(cur, None)                                # Gram  l x l  straight from cur
+            else:
+                _ws_ctranspose(ws, list(zip(cur, hC)))
+                self._gram(cur, hC)
             self._whiten(0 if ps == 0 else 1)
             out = dst if ps == passes - 1 else hS
             _ws_gemm(ws, list(zip(self.hT2, cur, out)))
@@ -1106,8 +1122,11 @@ class _TruncPlan:
         Wp = _ptr(ws.buf)
         if self.prerotate:
             # B' = T B, Qh' = T Qh with the unitary T from the Gram matrix of B: rows of B' nearly orthogonal
-            _ws_ctranspose(ws, list(zip(self.hB, self.hCq)))
-            self._gram(self.hB, self.hCq)
+            if GEMM_CONJ_TRANS:
+                self._gram(self.hB, None)
+            else:
+                _ws_ctranspose(ws, list(zip(self.hB, self.hCq)))
+                self._gram(self.hB, self.hCq)
             with prof_region("gram_rotate", 1):
                 check(lib.gtn_gram_rotate(Wp, Wp, code, _ptr(self.g_off), _ptr(self.t_off), _ptr(self.n_dev), nb,
                                           self.maxL, self.NS, 1e-15, ROTATE_TOL, 30, _ptr(self.rot_sweeps), st),

@@ -79,7 +79,7 @@ struct PeerBufs {
   char* p[GTN_MAX_PEERS];
 };
 
-template <bool CPLX, int BM, int BN, int AROW, bool BCAST>
+template <bool CPLX, int BM, int BN, int AROW, bool BCAST, bool BTRANS = false>
 __global__ void __launch_bounds__(NTHREADS)
     grouped_gemm_kernel(const char* __restrict__ Abase, const char* __restrict__ Bbase,
                         char* __restrict__ Cbase, const gtn_gemm_group* __restrict__ groups,
@@ -107,6 +107,7 @@ __global__ void __launch_bounds__(NTHREADS)
   const int64_t c_byte_off = (grp.c_off + int64_t(bidx) * grp.batch_stride_c) * C::ELEM;
   char* Cp = Cbase + c_byte_off;
   const int64_t lda = grp.lda, ldb = grp.ldb, ldc = grp.ldc;
+  constexpr bool b_trans = BTRANS;     // whole launch: every group carries GTN_GEMM_B_CONJ_TRANS (config bit 1)
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -131,12 +132,24 @@ __global__ void __launch_bounds__(NTHREADS)
       cp_async(sa + r * C::A_STRIDE + kk * C::ELEM, src, C::ELEM, p);
     }
     constexpr int B_TOTAL = C::BK * BN;
+    if constexpr (!b_trans) {
 #pragma unroll
-    for (int i = tid; i < B_TOTAL; i += NTHREADS) {
-      const int kk = i / BN, c = i % BN;
-      const bool p = (k0 + kk < K) && (n0 + c < N);
-      const char* src = p ? B + (int64_t(k0 + kk) * ldb + (n0 + c)) * C::ELEM : B;
-      cp_async(sb + kk * C::B_STRIDE + c * C::ELEM, src, C::ELEM, p);
+      for (int i = tid; i < B_TOTAL; i += NTHREADS) {
+        const int kk = i / BN, c = i % BN;
+        const bool p = (k0 + kk < K) && (n0 + c < N);
+        const char* src = p ? B + (int64_t(k0 + kk) * ldb + (n0 + c)) * C::ELEM : B;
+        cp_async(sb + kk * C::B_STRIDE + c * C::ELEM, src, C::ELEM, p);
+      }
+    } else {
+      // B given as its conjugate transpose (row-major N x K): consecutive threads walk K, the contiguous
+      // direction of the source, and scatter into the K-major tile; the conjugation happens at fragment load
+#pragma unroll
+      for (int i = tid; i < B_TOTAL; i += NTHREADS) {
+        const int c = i / C::BK, kk = i % C::BK;
+        const bool p = (k0 + kk < K) && (n0 + c < N);
+        const char* src = p ? B + (int64_t(n0 + c) * ldb + (k0 + kk)) * C::ELEM : B;
+        cp_async(sb + kk * C::B_STRIDE + c * C::ELEM, src, C::ELEM, p);
+      }
     }
   };
 
@@ -181,7 +194,7 @@ __global__ void __launch_bounds__(NTHREADS)
         for (int j = 0; j < NT; ++j) {
           const double2 v = *reinterpret_cast<const double2*>(
               sb + (ks * 4 + t) * C::B_STRIDE + (wn * WN + j * 8 + g) * 16);
-          bre[j] = v.x; bim[j] = v.y;
+          bre[j] = v.x; bim[j] = b_trans ? -v.y : v.y;
         }
 #pragma unroll
         for (int i = 0; i < MT; ++i)
@@ -254,18 +267,18 @@ __global__ void __launch_bounds__(NTHREADS)
   }
 }
 
-template <bool CPLX, int BM, int BN, int AROW, bool BCAST>
+template <bool CPLX, int BM, int BN, int AROW, bool BCAST, bool BTRANS = false>
 int launch_cfg(const void* A, const void* B, void* C, const gtn_gemm_group* groups_dev, int ngroups,
                int64_t total_tiles, const PeerBufs& peers, cudaStream_t s) {
   using K = Cfg<CPLX, BM, BN, AROW>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(grouped_gemm_kernel<CPLX, BM, BN, AROW, BCAST>,
+    cudaError_t e = cudaFuncSetAttribute(grouped_gemm_kernel<CPLX, BM, BN, AROW, BCAST, BTRANS>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  grouped_gemm_kernel<CPLX, BM, BN, AROW, BCAST><<<dim3((unsigned)total_tiles), dim3(NTHREADS), K::SMEM, s>>>(
+  grouped_gemm_kernel<CPLX, BM, BN, AROW, BCAST, BTRANS><<<dim3((unsigned)total_tiles), dim3(NTHREADS), K::SMEM, s>>>(
       (const char*)A, (const char*)B, (char*)C, groups_dev, ngroups, peers);
   return (int)cudaGetLastError();
 }
@@ -274,7 +287,7 @@ int launch_cfg(const void* A, const void* B, void* C, const gtn_gemm_group* grou
 
 extern "C" int64_t gtn_gemm_plan_host(gtn_gemm_group* groups, int ngroups, int dtype, int config) {
   (void)dtype;
-  const int64_t BM = config == 1 ? 32 : 64, BN = config == 1 ? 32 : 64;
+  const int64_t BM = (config & 1) ? 32 : 64, BN = (config & 1) ? 32 : 64;
   int64_t acc = 0;
   for (int i = 0; i < ngroups; ++i) {
     groups[i].tile_start = acc;
@@ -292,12 +305,16 @@ extern "C" int gtn_grouped_gemm(const void* A, const void* B, void* C, int dtype
   if (total_tiles > 2147483647LL) return GTN_ERR_BAD_ARG;
   cudaStream_t s = (cudaStream_t)stream;
   PeerBufs none; none.n = 0;
+  // config bit 0: 32x32 deep-K tiles; bit 1: every group's B is given as its conjugate transpose
+  // (GTN_GEMM_B_CONJ_TRANS; only with the 32x32 configuration, where the Gram matrices of the subspace iteration live)
   if (dtype == GTN_C128) {
+    if (config == 3) return launch_cfg<true, 32, 32, 512, false, true>(A, B, C, groups_dev, ngroups, total_tiles, none, s);
     if (config == 1) return launch_cfg<true, 32, 32, 512, false>(A, B, C, groups_dev, ngroups, total_tiles, none, s);
-    return launch_cfg<true, 64, 64, 128, false>(A, B, C, groups_dev, ngroups, total_tiles, none, s);
+    if (config == 0) return launch_cfg<true, 64, 64, 128, false>(A, B, C, groups_dev, ngroups, total_tiles, none, s);
   } else if (dtype == GTN_F64) {
+    if (config == 3) return launch_cfg<false, 32, 32, 512, false, true>(A, B, C, groups_dev, ngroups, total_tiles, none, s);
     if (config == 1) return launch_cfg<false, 32, 32, 512, false>(A, B, C, groups_dev, ngroups, total_tiles, none, s);
-    return launch_cfg<false, 64, 64, 128, false>(A, B, C, groups_dev, ngroups, total_tiles, none, s);
+    if (config == 0) return launch_cfg<false, 64, 64, 128, false>(A, B, C, groups_dev, ngroups, total_tiles, none, s);
   }
   return GTN_ERR_BAD_ARG;
 }

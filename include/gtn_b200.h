@@ -108,11 +108,17 @@ typedef struct {
   double alpha; /* real scalar (block sign S1*S3 = +-1 in einsum_block, __init__.py:2761) */
   double beta;  /* 0 or 1 */
   int64_t tile_start; /* prefix sum of CTA tiles (filled by gtn_gemm_plan_host) */
+  int32_t flags;      /* GTN_GEMM_B_CONJ_TRANS: B_g is given as its conjugate transpose, i.e. the kernel reads
+                         B_g[k][n] = conj(Bsrc[n * ldb + k]) from the row-major N x K array at b_off (Gram matrices
+                         X X^H and products with W^H without materialising the transposed copy) */
+  int32_t reserved;
 } gtn_gemm_group;
+#define GTN_GEMM_B_CONJ_TRANS 1
 
 /* Fills tile_start for all groups on the HOST array and returns the total CTA count.
  * config 0: 64x64 CTA tiles (large sector GEMMs); config 1: 32x32 tiles with a 4x deeper K step
- * (skinny l x p x q products of the randomized subspace iteration).  Same config at launch. */
+ * (skinny l x p x q products of the randomized subspace iteration); config 3: as 1, and EVERY group's B is
+ * given as its conjugate transpose (all groups carry GTN_GEMM_B_CONJ_TRANS).  Same config at launch. */
 int64_t gtn_gemm_plan_host(gtn_gemm_group* groups_host, int ngroups, int dtype, int config);
 
 int gtn_grouped_gemm(const void* A, const void* B, void* C, int dtype,

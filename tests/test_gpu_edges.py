@@ -366,3 +366,35 @@ def test_whole_step_graph_matches_eager(gtn, algo):
         for i, (x, y) in enumerate(zip(ref, other)):
             tol = 1e-10 if i < 1 else 1e-6          # exact multiplets at the cut
             assert abs(x - y) <= tol * abs(x), (i, ref, other)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", ["complex", "float"])
+def test_gemm_conj_transposed_b_operand(gtn, dtype):
+    """GTN_GEMM_B_CONJ_TRANS: C = A * Bsrc^H read straight from the row-major N x K array (ragged sizes, split-K
+    offsets, two groups in one launch) against torch, to rounding of a K-long dot product."""
+    import torch
+    from grassmanntn_b200 import _engine as E
+    dt = torch.complex128 if dtype == "complex" else torch.float64
+    gen = torch.Generator(device="cpu").manual_seed(3)
+    def rnd(*shape):
+        r = torch.randn(*shape, generator=gen, dtype=torch.float64)
+        if dt == torch.complex128:
+            r = torch.complex(r, torch.randn(*shape, generator=gen, dtype=torch.float64))
+        return r.cuda()
+    l1, K1, l2, n2, K2 = 48, 515, 13, 29, 70
+    X, A2, B2 = rnd(l1, K1), rnd(l2, K2), rnd(n2, K2)
+    buf = torch.cat([X.reshape(-1), A2.reshape(-1), B2.reshape(-1), torch.zeros(l1 * l1 + l2 * n2, dtype=dt, device="cuda")])
+    oX, oA, oB = 0, X.numel(), X.numel() + A2.numel()
+    oC1 = oB + B2.numel()
+    oC2 = oC1 + l1 * l1
+    k0 = 100                                   # second half of a split-K Gram matrix
+    groups = [dict(a_off=oX + k0, b_off=oX + k0, c_off=oC1, lda=K1, ldb=K1, ldc=l1, m=l1, n=l1, k=K1 - k0, flags=1),
+              dict(a_off=oA, b_off=oB, c_off=oC2, lda=K2, ldb=K2, ldc=n2, m=l2, n=n2, k=K2, alpha=-1.0, flags=1)]
+    E.GemmPlan(groups, dt).run(buf, buf, buf)
+    C1 = buf[oC1: oC1 + l1 * l1].view(l1, l1)
+    C2 = buf[oC2: oC2 + l2 * n2].view(l2, n2)
+    R1 = X[:, k0:] @ X[:, k0:].conj().T
+    R2 = -(A2 @ B2.conj().T)
+    assert float((C1 - R1).abs().max()) <= 1e-12 * float(R1.abs().max())
+    assert float((C2 - R2).abs().max()) <= 1e-12 * float(R2.abs().max())
