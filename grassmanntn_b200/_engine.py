@@ -1262,7 +1262,7 @@ def _trunc_plan(key, P_, Q_, ks, L_, dt, dev):
         plan = _TruncPlan(P_, Q_, ks, L_, dt, dev)
         plan.cached = plan.nbytes <= TRUNC_PLAN_CACHE_BYTES
         if plan.cached:
-            if len(_trunc_plans) >= 16:
+            if len(_trunc_plans) >= 32:      # (speculative callers hold one plan per call site: ATRG alone has six)
                 _trunc_plans.pop(next(iter(_trunc_plans)))
             _trunc_plans[key] = plan
     return plan

@@ -163,7 +163,7 @@ class _StepGraph:
     def replay(self, T):
         from . import _cabi
         bt = _bt_of(T)
-        if bt.key() != self.key:
+        if bt.key() != self.key or bt.buf.numel() != self.static.buf.numel():
             return None
         self.static.buf.copy_(bt.buf)
         self.g.replay()
@@ -214,7 +214,7 @@ def _graph_step(key, T, body):
                 _step_graphs[key] = False             # CUDA keeps refusing: stay eager on this layout
             return None
         STEP_GRAPH_STATS["captured"] += 1
-        STEP_GRAPH_STATS["capture_ms"] = STEP_GRAPH_STATS.get("capture_ms", []) + [round((_time.perf_counter() - t0) * 1e3, 1)]
+        STEP_GRAPH_STATS["capture_ms"] = (STEP_GRAPH_STATS.get("capture_ms", []) + [round((_time.perf_counter() - t0) * 1e3, 1)])[-16:]
         if len(_step_graphs) >= 8:
             _step_graphs.pop(next(iter(_step_graphs)))
         _step_graphs[key] = sg
