@@ -1,0 +1,101 @@
+"""CPU: the product's host logic end to end against the oracle, with the CUDA library replaced by the numpy test
+double of tests/_host_double.py.  The test bodies are the GPU parity tests themselves (tests/test_gpu_parity.py,
+tests/test_gpu_edges.py: same inputs, same tolerances); on the GPU box they run on the real kernels, here they pin
+the planner, the launch tables, the GEMM group lists, the decomposition packing / rank rule / unpacking and the
+coarse-graining drivers without a GPU."""
+import numpy as np
+import pytest
+
+import _host_double
+import test_gpu_edges as GE
+import test_gpu_parity as GP
+import test_z2_golden as Z2
+
+
+@pytest.fixture
+def gtn_host(monkeypatch):
+    gtn, saved = _host_double.install(monkeypatch)
+    yield gtn
+    _host_double.uninstall(saved)
+
+
+@pytest.mark.parametrize("trim", [False, True])
+@pytest.mark.parametrize("case", range(len(GP.EINSUM_CASES)))
+def test_einsum_vs_oracle(gtn_host, case, trim):
+    GP.test_einsum_vs_oracle(gtn_host, case, trim)
+
+
+def test_einsum_real_dtype(gtn_host):
+    GP.test_einsum_real_dtype(gtn_host)
+
+
+def test_format_encoder_switches_bit_exact(gtn_host):
+    GP.test_format_encoder_switches_bit_exact(gtn_host)
+
+
+@pytest.mark.parametrize("cut", [None, 8, 6])
+def test_svd_vs_oracle(gtn_host, cut):
+    GP.test_svd_vs_oracle(gtn_host, cut)
+
+
+def test_svd_with_bosonic_legs(gtn_host):
+    GP.test_svd_with_bosonic_legs(gtn_host)
+
+
+def test_hconjugate_bit_exact(gtn_host):
+    GP.test_hconjugate_bit_exact(gtn_host)
+
+
+def test_eig_vs_oracle(gtn_host):
+    GP.test_eig_vs_oracle(gtn_host)
+
+
+@pytest.mark.parametrize("fmt", ["dense", "block"])
+@pytest.mark.parametrize("algo", ["trg", "atrg2dy", "atrg2dx"])
+def test_cg_step_vs_oracle(gtn_host, algo, fmt):
+    GP.test_cg_step_vs_oracle(gtn_host, algo, fmt)
+
+
+@pytest.mark.parametrize("case", range(len(GP.JOIN_CASES)))
+def test_join_split_legs_bit_exact(gtn_host, case):
+    GP.test_join_split_legs_bit_exact(gtn_host, case)
+
+
+# ---- edge cases (tests/test_gpu_edges.py)
+@pytest.mark.parametrize("case", range(len(GE.SMALL)))
+def test_small_and_ragged_einsum(gtn_host, case):
+    GE.test_small_and_ragged_einsum(gtn_host, case)
+
+
+def test_einsum_errors(gtn_host):
+    GE.test_einsum_errors(gtn_host)
+
+
+def test_eig_rejects_non_hermitian(gtn_host):
+    GE.test_eig_rejects_non_hermitian(gtn_host)
+
+
+def test_svd_cutoff_larger_than_rank_and_full(gtn_host):
+    GE.test_svd_cutoff_larger_than_rank_and_full(gtn_host)
+
+
+def test_svd_of_zero_sector_and_rank_one(gtn_host):
+    GE.test_svd_of_zero_sector_and_rank_one(gtn_host)
+
+
+def test_block_non_power_of_two(gtn_host):
+    GE.test_block_non_power_of_two(gtn_host)
+
+
+def test_eig_reconstruction_D16(gtn_host):
+    GE.test_eig_reconstruction_D16(gtn_host)
+
+
+# ---- the product against the REAL reference's numbers on the Z2 gauge tensor (tests/test_z2_golden.py)
+@pytest.mark.parametrize("name,fmt,algo,cut,steps", [c for c in Z2.GPU_CONFIGS if c[3] <= 16])
+def test_host_vs_reference_on_z2(gtn_host, name, fmt, algo, cut, steps):
+    Z2.test_gpu_vs_reference_on_z2(gtn_host, name, fmt, algo, cut, steps)
+
+
+def test_host_hotrg3dz_random_vs_reference(gtn_host):
+    Z2.test_gpu_hotrg3dz_random_vs_reference(gtn_host)
