@@ -99,3 +99,40 @@ def test_host_vs_reference_on_z2(gtn_host, name, fmt, algo, cut, steps):
 
 def test_host_hotrg3dz_random_vs_reference(gtn_host):
     Z2.test_gpu_hotrg3dz_random_vs_reference(gtn_host)
+
+
+# ---- examples/example.py (the reference's example script on the product's API), log / checkpoint / resume
+def test_example_script_against_reference_numbers(gtn_host, tmp_path, capsys):
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "examples"))
+    try:
+        import example
+    finally:
+        sys.path.pop(0)
+    ref = np.load(os.path.join(Z2.G, "z2_cg.npz"))["dense_atrg_chi8"]       # real reference: Tnorm, err, F per step
+    log, ck = str(tmp_path / "run.jsonl"), str(tmp_path / "ck")
+    recs = example.main(["--cgsteps", "3", "--Dcutxy", "8", "--log", log, "--checkpoint", ck])
+    out = capsys.readouterr().out
+    assert " _atrg:" in out and "_ini:" in out and "parameters:" in out
+    assert len(recs) == 4
+    for i, r in enumerate(recs):
+        assert abs(r["F"] - complex(ref[i, 2], ref[i, 3])) <= 1e-10 * abs(r["F"]), (i, r["F"])
+        if i:
+            assert abs(r["Tnorm"] - ref[i, 0]) <= 1e-10 * ref[i, 0]
+    # interrupted after 2 steps, resumed for the 3rd: same numbers
+    ck2, log2 = str(tmp_path / "ck2"), str(tmp_path / "run2.jsonl")
+    example.main(["--cgsteps", "2", "--Dcutxy", "8", "--log", log2, "--checkpoint", ck2])
+    recs2 = example.main(["--cgsteps", "3", "--Dcutxy", "8", "--log", log2, "--checkpoint", ck2, "--resume"])
+    assert len(recs2) == 4
+    for a, b in zip(recs, recs2):
+        assert abs(a["F"] - b["F"]) <= 1e-12 * abs(a["F"])
+    from grassmanntn_b200 import checkpoint
+    assert len(checkpoint.RunLog(log2).read()) == 4 and checkpoint.latest_step(ck2)[0] == 3
+    # block format (example_block.py) and TRG
+    recs3 = example.main(["--cgsteps", "2", "--Dcutxy", "16", "--trg", "--block"])
+    refb = np.load(os.path.join(Z2.G, "z2_cg.npz"))["block_trg_chi32"]
+    assert len(recs3) == 3 and abs(recs3[0]["F"] - complex(refb[0, 2], refb[0, 3])) <= 1e-10 * abs(recs3[0]["F"])
+    with pytest.raises(SystemExit):
+        example.main(["--beta", "2.0"])                                     # no fixture for other parameters
