@@ -6,7 +6,10 @@ packing, rank rule, unpacking -- run without a GPU by standing in for the C ABI 
   gtn_grouped_gemm      -> numpy matmul per group (offsets, leading dimensions, batch strides, alpha/beta, conj-trans B)
   gtn_jacobi_* (full)   -> numpy.linalg.svd behind _engine.batched_svd's interface
   gtn_sumsq / rowsum / row_sumsq / dot / pow_rcond / scale -> numpy on the host buffers
-The truncated-SVD path, CUDA graphs and the multi-GPU mode are NOT emulated (GPU tests cover them).
+  install(truncated=True) additionally: gtn_chol_whiten (pivoted Cholesky), gtn_gram_rotate (eigenvectors of the
+  Gram matrix), gtn_jacobi_init / _persistent / _finish (numpy SVD behind the kernels' contracts) -- the randomized
+  subspace iteration with its residual certificate then runs its eager schedule on the host
+CUDA graphs, speculation and the multi-GPU mode are NOT emulated (GPU tests cover them).
 It is not a fallback: the product raises without a CUDA device (test_no_cpu_fallback) unless a test installs this."""
 import ctypes as C
 
@@ -25,6 +28,37 @@ def _arr(ptr, n, dtype):
     return raw.view(np.complex128) if dtype == np.complex128 else raw
 
 
+def _popcount(x):
+    x = x.astype(np.uint64)
+    c = np.zeros(x.shape, dtype=np.uint64)
+    for _ in range(32):
+        c += x & np.uint64(1)
+        x = x >> np.uint64(1)
+    return c
+
+
+def emulate_vec(fields, tabs, src, dst, scale=1.0):
+    """the same addressing / sign rule as test_tables_cpu.emulate (csrc/gtn_permute.cu), vectorised over the
+    product of the super-axis tables so that chi = 32 tensors are affordable; checked against the scalar
+    emulation in tests/test_host_double.py::test_vectorised_emulation_equals_scalar"""
+    i = np.full((1,), fields["in_base"], dtype=np.int64)
+    o = np.full((1,), fields["out_base"], dtype=np.int64)
+    e = np.full((1,), fields["const"], dtype=np.uint64)
+    macc = np.zeros((1,), dtype=np.uint64)
+    for t in tabs:
+        P = t["P"].astype(np.uint64)
+        low = P & np.uint64(0x0FFFFFFF)
+        i = (i[:, None] + t["in_off"].astype(np.int64)[None, :]).ravel()
+        o = (o[:, None] + t["out_off"].astype(np.int64)[None, :]).ravel()
+        cross = _popcount(low[None, :] & macc[:, None]) & np.uint64(1)
+        e = ((e[:, None] ^ (P >> np.uint64(31))[None, :]) ^ cross).ravel()
+        macc = (macc[:, None] ^ t["M"].astype(np.uint64)[None, :]).ravel()
+    v = src[i]
+    if fields["conj"]:
+        v = np.conj(v)
+    dst[o] = scale * np.where((e & np.uint64(1)).astype(bool), -v, v)
+
+
 class HostPlan:
     def __init__(self, jobs):
         self.jobs = jobs
@@ -32,7 +66,7 @@ class HostPlan:
     def run(self, src, dst, scale=1.0):
         s, d = src.numpy(), dst.numpy()
         for f, tabs in self.jobs:
-            emulate(f, tabs, s, d, scale)
+            emulate_vec(f, tabs, s, d, scale)
 
 
 class HostGemm:
@@ -129,12 +163,140 @@ class HostLib:
         return 0
 
 
-def install(monkeypatch):
+# ---- the kernels of the truncated sector SVD (contracts: include/gtn_b200.h) -----------------------------------
+def _i64(ptr, n):
+    return np.ctypeslib.as_array((C.c_int64 * n).from_address(ptr.value)) if n else np.zeros(0, np.int64)
+
+
+def _i32(ptr, n):
+    return np.ctypeslib.as_array((C.c_int32 * n).from_address(ptr.value)) if n else np.zeros(0, np.int32)
+
+
+def _pivoted_cholesky(G, rel_thr):
+    """P^T G P = L L^H stopped at numerical rank r (remaining diagonal <= rel_thr * first pivot)"""
+    n = G.shape[0]
+    A = G.copy()
+    perm = np.arange(n)
+    L = np.zeros_like(A)
+    first, r = None, 0
+    for j in range(n):
+        d = np.real(np.diag(A))[j:]
+        k = j + int(np.argmax(d))
+        piv = float(np.real(A[k, k]))
+        if first is None:
+            first = piv
+        if not (piv > rel_thr * first) or piv <= 0.0:
+            break
+        if k != j:
+            A[[j, k], :] = A[[k, j], :]
+            A[:, [j, k]] = A[:, [k, j]]
+            L[[j, k], :] = L[[k, j], :]
+            perm[[j, k]] = perm[[k, j]]
+        L[j, j] = np.sqrt(piv)
+        L[j + 1:, j] = A[j + 1:, j] / L[j, j]
+        A[j + 1:, j + 1:] -= np.outer(L[j + 1:, j], L[j + 1:, j].conj())
+        r = j + 1
+    return L, perm, r
+
+
+class HostLibSVD(HostLib):
+    def _gram_sum(self, G, off, n, nsplit, dt):
+        g = np.zeros((n, n), dtype=dt)
+        for s_ in range(nsplit):
+            g += _arr(C.c_void_p(G.value + (off + s_ * n * n) * g.itemsize), n * n, dt).reshape(n, n)
+        return g
+
+    def gtn_chol_whiten(self, G, T, code, g_off, t_off, n_dev, nprob, max_n, nsplit, rel_thr, kept, scratch, stream):
+        dt = self._dt(code)
+        go, to, ns, kp = _i64(g_off, nprob), _i64(t_off, nprob), _i32(n_dev, nprob), _i32(kept, nprob)
+        for b in range(nprob):
+            n = int(ns[b])
+            g = self._gram_sum(G, int(go[b]), n, nsplit, dt)
+            L, perm, r = _pivoted_cholesky(g, rel_thr)
+            Tm = np.zeros((n, n), dtype=dt)
+            if r:
+                Pt = np.zeros((n, n))
+                Pt[np.arange(n), perm] = 1.0                         # (P^T x)_i = x_perm[i]
+                Tm[:r, :] = np.linalg.solve(L[:r, :r], Pt[:r, :].astype(dt))
+            _arr(C.c_void_p(T.value + int(to[b]) * Tm.itemsize), n * n, dt)[:] = Tm.ravel()
+            kp[b] = r
+        return 0
+
+    def gtn_gram_rotate(self, G, T, code, g_off, t_off, n_dev, nprob, max_n, nsplit, rel_thr, tol, max_sweeps,
+                        sweeps, stream):
+        dt = self._dt(code)
+        go, to, ns = _i64(g_off, nprob), _i64(t_off, nprob), _i32(n_dev, nprob)
+        for b in range(nprob):
+            n = int(ns[b])
+            g = self._gram_sum(G, int(go[b]), n, nsplit, dt)
+            w, E_ = np.linalg.eigh((g + g.conj().T) / 2)
+            Tm = E_[:, ::-1].conj().T.astype(dt)                     # unitary; rows of T B orthogonal
+            _arr(C.c_void_p(T.value + int(to[b]) * Tm.itemsize), n * n, dt)[:] = np.ascontiguousarray(Tm).ravel()
+        if sweeps is not None and getattr(sweeps, "value", None):
+            _i32(sweeps, nprob)[:] = 1
+        return 0
+
+    def _probs(self, probs, nprob):
+        from grassmanntn_b200._cabi import SvdProblem
+        return (SvdProblem * nprob).from_address(probs.value)
+
+    def gtn_jacobi_init(self, W, Z, code, probs, nprob, max_p, rn2, fro2, rn_off, stream):
+        dt = self._dt(code)
+        ro, f2 = _i64(rn_off, nprob), _arr(fro2, nprob, np.float64)
+        for b, pr in enumerate(self._probs(probs, nprob)):
+            w = _arr(C.c_void_p(W.value + pr.w_off * np.dtype(dt).itemsize), pr.p * pr.q, dt).reshape(pr.p, pr.q)
+            _arr(C.c_void_p(Z.value + pr.z_off * np.dtype(dt).itemsize), pr.p * pr.p, dt)[:] = np.eye(pr.p, dtype=dt).ravel()
+            n2 = np.sum(np.abs(w) ** 2, axis=1)
+            _arr(C.c_void_p(rn2.value + int(ro[b]) * 8), pr.p, np.float64)[:] = n2
+            f2[b] = n2.max() if pr.p else 0.0
+        return 0
+
+    def gtn_jacobi_persistent(self, W, Z, code, probs, nprob, max_p, tol, offd, rn2, fro2, rn_off, max_sweeps,
+                              sweeps, stream):
+        """W0 = Z^H diag(s) Vh with the rows of W orthogonal: W <- diag(s) Vh, Z <- U^H from numpy's SVD of W0"""
+        dt = self._dt(code)
+        isz = np.dtype(dt).itemsize
+        ro = _i64(rn_off, nprob)
+        for b, pr in enumerate(self._probs(probs, nprob)):
+            w = _arr(C.c_void_p(W.value + pr.w_off * isz), pr.p * pr.q, dt).reshape(pr.p, pr.q)
+            z = _arr(C.c_void_p(Z.value + pr.z_off * isz), pr.p * pr.p, dt).reshape(pr.p, pr.p)
+            u, s_, vh = np.linalg.svd(z.conj().T @ w, full_matrices=False)
+            w[...] = s_[:, None] * vh
+            z[...] = u.conj().T
+            _arr(C.c_void_p(rn2.value + int(ro[b]) * 8), pr.p, np.float64)[:] = s_ ** 2
+        sw = _i32(sweeps, 4)
+        sw[0], sw[1] = 1, 1
+        return 0
+
+    def gtn_jacobi_finish(self, W, Z, U_out, Vh_out, s_out, code, probs, outs, order, nscratch, nprob, max_p, max_q,
+                          stream):
+        from grassmanntn_b200._cabi import SvdOut
+        dt = self._dt(code)
+        isz = np.dtype(dt).itemsize
+        outs_ = (SvdOut * nprob).from_address(outs.value)
+        for pr, ou in zip(self._probs(probs, nprob), outs_):
+            w = _arr(C.c_void_p(W.value + pr.w_off * isz), pr.p * pr.q, dt).reshape(pr.p, pr.q).copy()
+            z = _arr(C.c_void_p(Z.value + pr.z_off * isz), pr.p * pr.p, dt).reshape(pr.p, pr.p).copy()
+            nrm = np.sqrt(np.sum(np.abs(w) ** 2, axis=1))
+            idx = np.argsort(-nrm, kind="stable")
+            _arr(C.c_void_p(s_out.value + ou.s_off * 8), pr.p, np.float64)[:] = nrm[idx]
+            _arr(C.c_void_p(U_out.value + ou.u_off * isz), pr.p * pr.p, dt)[:] = z.conj().T[:, idx].ravel()
+            vh = np.where(nrm[idx, None] > 0, w[idx] / np.maximum(nrm[idx, None], 1e-300), 0.0)
+            _arr(C.c_void_p(Vh_out.value + pr.w_off * isz), pr.p * pr.q, dt)[:] = vh.ravel()
+        return 0
+
+
+class _NoStream:
+    def synchronize(self):
+        pass
+
+
+def install(monkeypatch, truncated=False):
     """patch the product for one test; returns the package"""
     import grassmanntn_b200 as gtn
     from grassmanntn_b200 import _cabi, _engine as E, _ops
     cpu = torch.device("cpu")
-    fake = HostLib(_cabi.lib)
+    fake = (HostLibSVD if truncated else HostLib)(_cabi.lib)
     saved = dict(E._plan_cache)
     E._plan_cache.clear()
     for mod in (E, _ops):
@@ -145,7 +307,14 @@ def install(monkeypatch):
         monkeypatch.setattr(mod, "batched_svd", host_batched_svd)
         monkeypatch.setattr(mod, "lib", fake)
     monkeypatch.setattr(_cabi, "lib", fake)
-    monkeypatch.setattr(_ops, "TRUNCATED_SVD", False)
+    monkeypatch.setattr(_ops, "TRUNCATED_SVD", bool(truncated))
+    if truncated:
+        # the subspace iteration with its certificate, eager launches only (no CUDA graphs, no speculation)
+        monkeypatch.setattr(E, "USE_GRAPHS", False)
+        monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: _NoStream())
+        monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
+        for name in ("_trunc_plans", "_trunc_iters_hint", "_trunc_rate", "_trunc_fail", "_trunc_probe"):
+            monkeypatch.setattr(E, name, {})
     monkeypatch.setattr(gtn.gauge2d, "SPECULATE", False)
     monkeypatch.setattr(gtn.gauge2d, "STEP_GRAPH", False)
     return gtn, saved

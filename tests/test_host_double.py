@@ -136,3 +136,54 @@ def test_example_script_against_reference_numbers(gtn_host, tmp_path, capsys):
     assert len(recs3) == 3 and abs(recs3[0]["F"] - complex(refb[0, 2], refb[0, 3])) <= 1e-10 * abs(recs3[0]["F"])
     with pytest.raises(SystemExit):
         example.main(["--beta", "2.0"])                                     # no fixture for other parameters
+
+
+# ---- the truncated sector SVD (subspace iteration + certificate) on the host double
+@pytest.fixture
+def gtn_host_trunc(monkeypatch):
+    gtn, saved = _host_double.install(monkeypatch, truncated=True)
+    yield gtn
+    _host_double.uninstall(saved)
+
+
+@pytest.mark.parametrize("kind", ["decaying", "flat"])
+def test_truncated_svd_path(gtn_host_trunc, kind):
+    GP.test_truncated_svd_path(gtn_host_trunc, kind)
+
+
+def test_vectorised_emulation_equals_scalar():
+    """the vectorised kernel emulation of the test double against the scalar one (tests/test_tables_cpu.py) on a job
+    with the full sign program (alpha, beta, Q cross terms between super-axes, conj)"""
+    from test_tables_cpu import emulate
+    from grassmanntn_b200 import _engine as E
+    rng = np.random.RandomState(3)
+    shape = (4, 2, 8, 4, 2)
+    n = int(np.prod(shape))
+    src = rng.rand(n) + 1j * rng.rand(n)
+    in_st = E._row_strides(shape)
+    perm = (3, 0, 4, 2, 1)
+    out_shape = tuple(shape[a] for a in perm)
+    ost = E._row_strides(out_shape)
+    out_st = [ost[perm.index(a)] for a in range(5)]
+    legs = []
+    for a, d in enumerate(shape):
+        pc = E._popcount_vec(np.arange(d))
+        legs.append(E.LegTab(d, np.arange(d) * in_st[a], np.arange(d) * out_st[a], p=pc & 1, q=(pc >> 1) & 1))
+    Q = [0] * 5
+    for x, y in ((0, 3), (1, 2), (2, 4), (0, 4)):
+        Q[x] |= 1 << y
+        Q[y] |= 1 << x
+    f, tabs = E.build_job(legs, alpha=[1, 0, 1, 0, 0], beta=[0, 1, 0, 0, 1], Q=Q, const=1, conj=True)
+    a, b = np.zeros(n, complex), np.zeros(n, complex)
+    emulate(f, tabs, src, a, 0.5)
+    _host_double.emulate_vec(f, tabs, src, b, 0.5)
+    assert len(tabs) >= 2 and np.array_equal(a, b)
+
+
+def test_truncated_path_on_the_z2_chain_vs_reference(gtn_host_trunc):
+    """three block-format TRG steps at chi = 32 on the Z2 gauge tensor: the third runs the truncated sector SVD
+    (512 x 512 sector matrices, 48-row subspace) -- Tnorm, F and the trace error against the real reference"""
+    from grassmanntn_b200 import _ops
+    before = dict(_ops.SVD_PATH_STATS)
+    Z2.test_gpu_vs_reference_on_z2(gtn_host_trunc, "block_trg_chi32", "block", "trg", 32, 3)
+    assert _ops.SVD_PATH_STATS["truncated"] > before["truncated"]
