@@ -60,7 +60,7 @@ def _load():
         "gtn_grouped_gemm_bcast": (i32, [vp, vp, vp, i32, i32, vp, i32, i64, vp]),
         "gtn_jacobi_init": (i32, [vp, vp, i32, vp, i32, i32, vp, vp, vp, vp]),
         "gtn_jacobi_sweep": (i32, [vp, vp, i32, vp, i32, i32, i32, dbl, vp, vp, vp, vp, vp]),
-        "gtn_jacobi_persistent": (i32, [vp, vp, i32, vp, i32, i32, dbl, vp, vp, vp, vp, i32, vp, vp]),
+        "gtn_jacobi_persistent": (i32, [vp, vp, i32, vp, i32, i32, dbl, vp, vp, vp, vp, i32, vp, vp, dbl]),
         "gtn_jacobi_finish": (i32, [vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, i32, i32, i32, vp]),
         "gtn_small_eigh_whiten": (i32, [vp, vp, i32, vp, vp, vp, i32, i32, dbl, vp, vp, vp, vp]),
         "gtn_chol_whiten": (i32, [vp, vp, i32, vp, vp, vp, i32, i32, i32, dbl, vp, vp, vp]),

@@ -731,6 +731,9 @@ def gemm(A, B, m, n, k, lda=None, ldb=None, ldc=None, out=None):
 # ------------------------------------------------------------------------------------------------
 JACOBI_TOL = 4e-15
 JACOBI_MAX_SWEEPS = 60
+# projected matrix of the truncated SVD: skip the confirming sweep once a sweep only rotated pairs with a normalised
+# inner product below this (quadratic convergence; the residual certificate checks the result anyway).  0 = off
+JACOBI_EARLY_STOP = float(__import__("os").environ.get("GTN_JACOBI_EARLY_STOP", "1e-10"))
 PERSISTENT_MAX_ROWS = 160   # batches up to this many rows try the one-launch cooperative Jacobi kernel
 
 
@@ -788,7 +791,7 @@ def batched_svd(mats):
         rb = sum(2 * esz * (pr[2] * pr[3] + pr[2] * pr[2]) for pr in probs)
         with prof_region("jacobi_persistent", 1, 0) as pr_:
             rc = lib.gtn_jacobi_persistent(_ptr(W), _ptr(Z), code, _ptr(pdev), nprob, maxp, JACOBI_TOL, _ptr(offd),
-                                           _ptr(rn2), _ptr(fro2), _ptr(rn_off), JACOBI_MAX_SWEEPS, _ptr(sw), st)
+                                           _ptr(rn2), _ptr(fro2), _ptr(rn_off), JACOBI_MAX_SWEEPS, _ptr(sw), st, 0.0)
             swh = sw.cpu().tolist()[:2] if rc == 0 else [0, 0]
             # algorithmic bytes: every row of W and Z read + written once per round
             pr_.set_bytes(rb * (P - 1) * max(swh[0], 1))
@@ -1149,7 +1152,7 @@ class _TruncPlan:
             with prof_region("jacobi_persistent", 1, 0):
                 rc = lib.gtn_jacobi_persistent(Wp, Wp, code, _ptr(self.pdev), nb, self.maxL, JACOBI_TOL, _ptr(self.offd),
                                                _ptr(self.rn2), _ptr(self.fro2), _ptr(self.rn_off), JACOBI_MAX_SWEEPS,
-                                               _ptr(self.sw), st)
+                                               _ptr(self.sw), st, JACOBI_EARLY_STOP)
             if rc == 0:
                 done = True
             elif rc == -2:

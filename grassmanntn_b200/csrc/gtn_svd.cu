@@ -251,7 +251,8 @@ __global__ void __launch_bounds__(JT)
                              const gtn_svd_problem* __restrict__ probs, int nprob, int max_p, double tol,
                              double* __restrict__ offdiag2, double* __restrict__ rn2,
                              const double* __restrict__ fro2, const int64_t* __restrict__ rn_off,
-                             int max_sweeps, int32_t* __restrict__ sweeps_out, unsigned int* __restrict__ bar) {
+                             int max_sweeps, int32_t* __restrict__ sweeps_out, unsigned int* __restrict__ bar,
+                             double early2) {
   const int P = (max_p + 1) & ~1;
   const int prob = blockIdx.y, k = blockIdx.x;
   const unsigned int nblocks = gridDim.x * gridDim.y;
@@ -265,17 +266,19 @@ __global__ void __launch_bounds__(JT)
       grid_barrier(bar, nblocks, epoch);
       if (round == 0 && k == 0 && threadIdx.x == 0) off_next[prob] = 0.0;
     }
-    // converged when no pair of any problem rotated in this sweep
+    // converged when no pair of any problem rotated in this sweep -- or, with early2 > 0, when every pair that was
+    // rotated had a normalised inner product^2 <= early2: the cyclic Jacobi iteration converges quadratically, so
+    // what this sweep leaves behind is already below the rotation threshold and the confirming sweep is skipped
     double m = 0.0;
     for (int b = 0; b < nprob; ++b) m = fmax(m, *reinterpret_cast<volatile double*>(off + b));
-    if (m == 0.0) { ++sweep; break; }
+    if (m <= early2) { ++sweep; break; }
   }
   if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
     sweeps_out[0] = sweep;
     double m = 0.0;
     const double* off = offdiag2 + ((sweep - 1) & 1) * nprob;
     for (int b = 0; b < nprob; ++b) m = fmax(m, off[b]);
-    sweeps_out[1] = (m == 0.0) ? 1 : 0;
+    sweeps_out[1] = (m <= early2) ? 1 : 0;
   }
 }
 
@@ -433,7 +436,7 @@ extern "C" int gtn_jacobi_persistent(void* W, void* Z, int dtype, const gtn_svd_
                                      int nprob, int max_p, double tol, double* offdiag2_dev,
                                      double* rownorm2_dev, const double* fro2_dev,
                                      const int64_t* rn_off_dev, int max_sweeps, int32_t* sweeps_dev,
-                                     void* stream) {
+                                     void* stream, double early_stop) {
   if (nprob <= 0 || max_p < 2) return GTN_ERR_UNSUPPORTED;
   const int P = (max_p + 1) & ~1;
   dim3 grid(P / 2, nprob), block(JT);
@@ -452,8 +455,9 @@ extern "C" int gtn_jacobi_persistent(void* W, void* Z, int dtype, const gtn_svd_
   // the barrier counter lives behind the two sweep counters in sweeps_dev (int32[4])
   unsigned int* bar = reinterpret_cast<unsigned int*>(sweeps_dev) + 2;
   cudaMemsetAsync(bar, 0, sizeof(unsigned int), s);
+  double early2 = early_stop > 0.0 ? early_stop * early_stop : 0.0;
   void* args[] = {&W, &Z, (void*)&probs_dev, &nprob, &max_p, &tol, &offdiag2_dev, &rownorm2_dev,
-                  (void*)&fro2_dev, (void*)&rn_off_dev, &max_sweeps, &sweeps_dev, &bar};
+                  (void*)&fro2_dev, (void*)&rn_off_dev, &max_sweeps, &sweeps_dev, &bar, &early2};
   cudaError_t e = cudaLaunchCooperativeKernel(fn, grid, block, args, 0, s);
   return (int)e;
 }

@@ -175,7 +175,12 @@ int gtn_jacobi_sweep(void* W, void* Z, int dtype, const gtn_svd_problem* probs_d
 int gtn_jacobi_persistent(void* W, void* Z, int dtype, const gtn_svd_problem* probs_dev, int nprob,
                           int max_p, double tol, double* offdiag2_dev, double* rownorm2_dev,
                           const double* fro2_dev, const int64_t* rn_off_dev, int max_sweeps,
-                          int32_t* sweeps_dev, void* stream);
+                          int32_t* sweeps_dev, void* stream, double early_stop);
+/* early_stop = 0: stop after the first sweep in which no pair exceeded `tol` (a confirming sweep).
+ * early_stop > 0: also stop after a sweep whose rotated pairs all had |<w_i,w_j>| / (|w_i||w_j|) <= early_stop --
+ * the iteration converges quadratically, so that sweep leaves at most ~early_stop^2 / (relative gap) behind.
+ * Used (1e-10) for the projected matrix of the truncated SVD, whose result is checked by the residual
+ * certificate anyway; the full SVD of a sector passes 0. */
 
 /* s_out: double[sum p_b] at offsets s_off_b (descending); U_out (p x p row-major) at u_off;
  * Vh_out: rows of W normalised and permuted, at w_off.  order_dev: int32 [sum p_b] receives the

@@ -252,7 +252,7 @@ class HostLibSVD(HostLib):
         return 0
 
     def gtn_jacobi_persistent(self, W, Z, code, probs, nprob, max_p, tol, offd, rn2, fro2, rn_off, max_sweeps,
-                              sweeps, stream):
+                              sweeps, stream, early_stop=0.0):
         """W0 = Z^H diag(s) Vh with the rows of W orthogonal: W <- diag(s) Vh, Z <- U^H from numpy's SVD of W0"""
         dt = self._dt(code)
         isz = np.dtype(dt).itemsize
