@@ -1,3 +1,3 @@
 #!/bin/bash
 mkdir -p gpurun_out
-( time timeout 300 python bench.py ) > gpurun_out/i_bench.json 2> gpurun_out/i_bench.err; tail -3 gpurun_out/i_bench.err
+timeout 40 python bench.py > gpurun_out/j_bench.json 2> gpurun_out/j_bench.err; echo "rc $?"; tail -2 gpurun_out/j_bench.err | cut -c1-300
