@@ -331,9 +331,10 @@ def test_whole_step_graph_matches_eager(gtn, algo):
         return (g.atrg2dx if i % 2 == 0 else g.atrg2dy)(T, T, 32)[:2]
 
     def chain(graph, sabotage=False):
-        old = g.STEP_GRAPH
+        old, old_probe = g.STEP_GRAPH, E.PROBE_EVERY
         g.STEP_GRAPH = graph
-        E._trunc_iters_hint.clear(); E._trunc_rate.clear(); E._trunc_fail.clear()
+        E.PROBE_EVERY = 0                # no periodic re-derivation of the counts: a recorded graph stays live
+        E._trunc_iters_hint.clear(); E._trunc_rate.clear(); E._trunc_fail.clear(); E._trunc_probe.clear()
         g._step_graphs.clear(); g._steady.clear()
         g.STEP_GRAPH_STATS.pop("last_error", None)
         g.STEP_GRAPH_STATS.pop("capture_ms", None)
@@ -354,7 +355,8 @@ def test_whole_step_graph_matches_eager(gtn, algo):
                 out.append(float(n))
             return out, dict(g.STEP_GRAPH_STATS)
         finally:
-            g.STEP_GRAPH = old
+            g.STEP_GRAPH, E.PROBE_EVERY = old, old_probe
+            E._trunc_probe.clear()       # (entries made with interval 0 must not outlive the test)
             E.FORCE_VERIFY_FAIL[0] = None
     ref, st0 = chain(False)
     assert st0["captured"] == 0 and st0["replayed"] == 0
