@@ -149,6 +149,19 @@ def _cpu_reference_run(args, data, stats, label):
     return args.steps / dt, dt / args.steps * 1e3, B.effective_shape
 
 
+def settle(g, fn, max_steps=12, quiet_needed=2):
+    """Run fn() until `quiet_needed` consecutive calls replayed a recorded step graph without recording one -- or
+    max_steps calls, for workloads that never use a step graph.  A graph dropped for a re-derivation of the SVD
+    iteration counts is recorded again within a few steps; timing loops start after that.  Returns the calls made."""
+    st, quiet, n = g.STEP_GRAPH_STATS, 0, 0
+    while n < max_steps and quiet < quiet_needed:
+        c0, r0 = st["captured"], st["replayed"]
+        fn()
+        n += 1
+        quiet = quiet + 1 if (st["captured"] == c0 and st["replayed"] > r0) else 0
+    return n
+
+
 def config_dict(args, label, shape):
     return {"workload": "TRG step (gauge2d_block.trg), 2D Z2 gauge theory K=2 Nf=1 beta=m=q=a=1 mu=0, block format, "
                         "chi=%d, site tensor %s complex128" % (args.chi, "x".join(str(int(s)) for s in shape)),
@@ -207,6 +220,7 @@ def main():
     # iterations, not the nearly rank-deficient fixed point the chain reaches later), like the CPU arm does.
     for _ in range(24):
         g.trg(T, args.chi)
+    settle(g, lambda: g.trg(T, args.chi))
     g.freeze(True)                           # timing: learnt iteration counts and recorded graphs stay as they are
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
@@ -260,6 +274,7 @@ def main():
         return host_out[0], Tn
     for _ in range(max(24, args.warmup)):       # the host-fed tensor has its own layout (all 16 blocks): own graph
         e2e_step()
+    settle(g, e2e_step)
     g.freeze(True)
     for _ in range(args.warmup):
         e2e_step()
@@ -403,13 +418,12 @@ def other_workloads(gtn, torch, data, stats, args):
             X = fn(X)
         g.freeze(True)
         # settle: a step graph dropped just before the freeze is recorded again within a few steps; do not time that
-        st, quiet = g.STEP_GRAPH_STATS, 0
-        for _ in range(8):
-            c0, r0 = st["captured"], st["replayed"]
-            X = fn(X)
-            quiet = quiet + 1 if (st["captured"] == c0 and st["replayed"] > r0) else 0
-            if quiet >= 2:
-                break
+        box = [X]
+
+        def one():
+            box[0] = fn(box[0])
+        settle(g, one, max_steps=8)
+        X = box[0]
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for _ in range(n):
