@@ -187,3 +187,16 @@ def test_truncated_path_on_the_z2_chain_vs_reference(gtn_host_trunc):
     before = dict(_ops.SVD_PATH_STATS)
     Z2.test_gpu_vs_reference_on_z2(gtn_host_trunc, "block_trg_chi32", "block", "trg", 32, 3)
     assert _ops.SVD_PATH_STATS["truncated"] > before["truncated"]
+
+
+# ---- flavour HOTRG (hotrg3dz: 6-leg tensors, bosonic legs, eig, hconjugate) on the Z2 tensor against the reference
+@pytest.mark.parametrize("cut", [8, 16])
+def test_host_hotrg3dz_z2_loose(gtn_host_trunc, cut):
+    Z2.test_gpu_hotrg3dz_z2_loose(gtn_host_trunc, cut)
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("GTN_SLOW_TESTS"),
+                    reason="~2 min of numpy SVDs of 4096 x 4096 matrices; set GTN_SLOW_TESTS=1")
+def test_host_hotrg3dz_z2_chi64_vs_reference(gtn_host_trunc):
+    """BASELINE.json configs[2] ('HOTRG chi=64'): Tnorm and F equal to the real reference to 1e-10"""
+    Z2.test_gpu_hotrg3dz_z2_chi64_vs_reference(gtn_host_trunc)
