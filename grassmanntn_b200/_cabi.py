@@ -57,6 +57,8 @@ def _load():
         "gtn_sign_permute": (i32, [vp, vp, i32, vp, vp, i32, i64, dbl, dbl, vp]),
         "gtn_gemm_plan_host": (i64, [C.POINTER(GemmGroup), i32, i32, i32]),
         "gtn_grouped_gemm": (i32, [vp, vp, vp, i32, vp, i32, i64, i32, vp]),
+        "gtn_gemm_tma_check": (i32, [C.POINTER(GemmGroup), i32, i32]),
+        "gtn_grouped_gemm_tma": (i32, [vp, vp, vp, i32, C.POINTER(GemmGroup), vp, i32, i64, i32, vp]),
         "gtn_grouped_gemm_bcast": (i32, [vp, vp, vp, i32, i32, vp, i32, i64, vp]),
         "gtn_jacobi_init": (i32, [vp, vp, i32, vp, i32, i32, vp, vp, vp, vp]),
         "gtn_jacobi_sweep": (i32, [vp, vp, i32, vp, i32, i32, i32, dbl, vp, vp, vp, vp, vp]),

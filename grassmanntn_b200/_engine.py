@@ -671,9 +671,21 @@ class GroupLayout:
 #  grouped GEMM
 # ------------------------------------------------------------------------------------------------
 SKINNY_MAX = int(__import__("os").environ.get("GTN_SKINNY_MAX", "128"))
+# TMA-staged DMMA kernel (csrc/gtn_gemm_tma.cu) for launches with at least this many 128x64 (or 64x64) tiles
+USE_TMA = bool(int(__import__("os").environ.get("GTN_TMA", "1")))
+TMA_MIN_TILES = int(__import__("os").environ.get("GTN_TMA_MIN_TILES", "74"))
+TMA_MAX_GROUPS = 32         # GTN_TMA_MAX_GROUPS of include/gtn_b200.h
+GEMM_FAMILY = {0: "gemm_ldgsts_64x64", 1: "gemm_skinny_32x32", 3: "gemm_skinny_32x32", 4: "gemm_tma_64x64",
+               12: "gemm_tma_128x64"}
 
 
 class GemmPlan:
+    """Device-resident group list of one grouped GEMM launch and the tile configuration it runs in:
+       12 / 4  TMA-staged 128x64 / 64x64 tiles (large products: every side >= 64, enough tiles to fill the GPU,
+               16-byte aligned operands, <= 32 groups), tile grid rasterised in bands of row tiles;
+       1       32x32 tiles with a deep K step (skinny products and Gram matrices of the subspace iteration);
+       0       64x64 cp.async tiles (everything else: ragged block sectors, misaligned float64 views)."""
+
     def __init__(self, groups, dtype, config=None):
         self.n = len(groups)
         self.tiles = 0
@@ -697,31 +709,51 @@ class GemmPlan:
             a.m, a.n, a.k, a.batch = g["m"], g["n"], g["k"], g.get("batch", 1)
             a.alpha, a.beta = g.get("alpha", 1.0), g.get("beta", 0.0)
             a.flags = g.get("flags", 0)
-        # skinny problems (a side <= 48) get the 32x32 / deep-K configuration
+        code = dtype_code(dtype)
         if config is None:
-            config = 1 if all(min(g["m"], g["n"]) <= SKINNY_MAX for g in groups) else 0
+            config = self._choose(groups, arr, code)
         if any(g.get("flags", 0) & 1 for g in groups):
             # conj-transposed B operand: a whole-launch property, only built for the 32x32 configuration
             assert all(g.get("flags", 0) & 1 for g in groups)
             config = 3
         self.config = config
-        self.tiles = int(lib.gtn_gemm_plan_host(arr, self.n, dtype_code(dtype), self.config))
+        if config & 4:
+            # band height of the rasterised tile walk: the CTAs resident at one time (148 x 128x64 tiles, or 296 x
+            # 64x64) cover a square-ish region of C
+            for a in arr:
+                a.reserved = 8 if config & 8 else 16
+        self.family = GEMM_FAMILY.get(config, "grouped_gemm")
+        self.tiles = int(lib.gtn_gemm_plan_host(arr, self.n, code, self.config))
+        self.host = arr                      # the TMA path encodes its tensor maps from the host copy
         self.dev = _to_dev_bytes(bytes(arr))
+
+    def _choose(self, groups, arr, code):
+        if USE_TMA and self.n <= TMA_MAX_GROUPS and min(min(g["m"], g["n"], g["k"]) for g in groups) >= 64 \
+                and lib.gtn_gemm_tma_check(arr, self.n, code):
+            cfg = 12 if max(g["m"] for g in groups) >= 128 else 4
+            if int(lib.gtn_gemm_plan_host(arr, self.n, code, cfg)) >= TMA_MIN_TILES:
+                return cfg
+        # skinny problems (a side <= SKINNY_MAX) get the 32x32 / deep-K configuration
+        return 1 if all(min(g["m"], g["n"]) <= SKINNY_MAX for g in groups) else 0
 
     def run(self, A, B, Cm):
         if self.n == 0 or self.tiles == 0:
             return
-        with prof_region("grouped_gemm", 1, self.bytes, self.flops):
-            check(lib.gtn_grouped_gemm(_ptr(A), _ptr(B), _ptr(Cm), dtype_code(A.dtype), _ptr(self.dev), self.n,
-                                       self.tiles, self.config, _stream()), "gtn_grouped_gemm")
+        with prof_region(self.family, 1, self.bytes, self.flops):
+            if self.config & 4:
+                check(lib.gtn_grouped_gemm_tma(_ptr(A), _ptr(B), _ptr(Cm), dtype_code(A.dtype), self.host, _ptr(self.dev),
+                                               self.n, self.tiles, self.config, _stream()), "gtn_grouped_gemm_tma")
+            else:
+                check(lib.gtn_grouped_gemm(_ptr(A), _ptr(B), _ptr(Cm), dtype_code(A.dtype), _ptr(self.dev), self.n,
+                                           self.tiles, self.config, _stream()), "gtn_grouped_gemm")
 
 
-def gemm(A, B, m, n, k, lda=None, ldb=None, ldc=None, out=None):
+def gemm(A, B, m, n, k, lda=None, ldb=None, ldc=None, out=None, config=None):
     """plain C[m,n] = A[m,k] B[k,n] on the DMMA kernel (row-major)."""
     if out is None:
         out = torch.empty(m * n, dtype=A.dtype, device=A.device)
-    plan = _cached(("gemm1", m, n, k, lda, ldb, ldc, str(A.dtype)), lambda: GemmPlan(
-        [dict(a_off=0, b_off=0, c_off=0, lda=lda or k, ldb=ldb or n, ldc=ldc or n, m=m, n=n, k=k)], A.dtype))
+    plan = _cached(("gemm1", m, n, k, lda, ldb, ldc, str(A.dtype), config), lambda: GemmPlan(
+        [dict(a_off=0, b_off=0, c_off=0, lda=lda or k, ldb=ldb or n, ldc=ldc or n, m=m, n=n, k=k)], A.dtype, config))
     plan.run(A, B, out)
     return out
 

@@ -287,7 +287,8 @@ int launch_cfg(const void* A, const void* B, void* C, const gtn_gemm_group* grou
 
 extern "C" int64_t gtn_gemm_plan_host(gtn_gemm_group* groups, int ngroups, int dtype, int config) {
   (void)dtype;
-  const int64_t BM = (config & 1) ? 32 : 64, BN = (config & 1) ? 32 : 64;
+  // bit 0: 32x32 deep-K tiles; bit 2: TMA-staged kernel (gtn_gemm_tma.cu), bit 3 with it: 128-row tiles
+  const int64_t BM = (config & 8) ? 128 : ((config & 1) ? 32 : 64), BN = (config & 1) ? 32 : 64;
   int64_t acc = 0;
   for (int i = 0; i < ngroups; ++i) {
     groups[i].tile_start = acc;

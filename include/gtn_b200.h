@@ -111,7 +111,8 @@ typedef struct {
   int32_t flags;      /* GTN_GEMM_B_CONJ_TRANS: B_g is given as its conjugate transpose, i.e. the kernel reads
                          B_g[k][n] = conj(Bsrc[n * ldb + k]) from the row-major N x K array at b_off (Gram matrices
                          X X^H and products with W^H without materialising the transposed copy) */
-  int32_t reserved;
+  int32_t reserved;   /* TMA configurations: `raster` -- the tile grid of the group is walked in bands of this many row
+                         tiles, column-major inside a band (0 = 1); ignored by the cp.async configurations */
 } gtn_gemm_group;
 #define GTN_GEMM_B_CONJ_TRANS 1
 
@@ -124,6 +125,23 @@ int64_t gtn_gemm_plan_host(gtn_gemm_group* groups_host, int ngroups, int dtype, 
 int gtn_grouped_gemm(const void* A, const void* B, void* C, int dtype,
                      const gtn_gemm_group* groups_dev, int ngroups, int64_t total_tiles,
                      int config, void* stream);
+
+/* TMA-staged variant of gtn_grouped_gemm (north_star: "FP64 DMMA tensor-core tiles staged by TMA"): one producer
+ * warp feeds a 4-stage shared-memory ring with cp.async.bulk.tensor loads (SASS UTMALDG) completing on mbarriers,
+ * the consumer warps (32x32 warp tiles of DMMA.8x8x4) never compute a load address; tiles are dense 128-byte rows in
+ * the hardware SWIZZLE_128B pattern; out-of-range parts of a tile are zero-filled by the TMA unit from the true
+ * extents in the tensor maps.  config 4: 64x64 CTA tiles, config 12: 128x64 (same values for gtn_gemm_plan_host).
+ * The tensor maps (one per group and operand) are encoded on the host at every call from `groups_host` -- the same
+ * array as groups_dev -- and travel as a kernel parameter, so ngroups <= GTN_TMA_MAX_GROUPS.  Requires 16-byte aligned
+ * operand sub-matrices (always true for GTN_C128; even offsets / leading dimensions for GTN_F64) and no
+ * GTN_GEMM_B_CONJ_TRANS: gtn_gemm_tma_check returns 1 when a group list qualifies.  Returns GTN_ERR_UNSUPPORTED when
+ * the driver does not export cuTensorMapEncodeTiled or an operand is misaligned.
+ * Replaces the same reference call sites as gtn_grouped_gemm (__init__.py:2295, :2781, :2928). */
+#define GTN_TMA_MAX_GROUPS 32
+int gtn_gemm_tma_check(const gtn_gemm_group* groups_host, int ngroups, int dtype);
+int gtn_grouped_gemm_tma(const void* A, const void* B, void* C, int dtype, const gtn_gemm_group* groups_host,
+                         const gtn_gemm_group* groups_dev, int ngroups, int64_t total_tiles, int config,
+                         void* stream);
 
 /* Fused GEMM + all-gather for the multi-GPU output-tile sharding: same product as
  * gtn_grouped_gemm (64x64 tiles, beta = 0), but every result element is stored at the same offset into
