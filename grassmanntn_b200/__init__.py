@@ -148,10 +148,14 @@ class dense:
 
     @property
     def data(self):
+        """the coefficient array (a live CUDA tensor: `X.data[...] = v` and `X.data /= s` work like on the reference's
+        numpy array).  Once it has been handed out the array is the ONLY storage of the object: the parity-blocked
+        form is dropped here and rebuilt from the array by every later op, so in-place edits are never missed."""
         if self._data is None:
             if self._bt is None:
                 return None
             self._data = bt_to_dense(self._bt, self.encoder)
+        self._bt = None
         return self._data
 
     @data.setter
@@ -172,7 +176,8 @@ class dense:
             if self._hybrid():
                 raise NotImplementedError("grassmanntn_b200: this operation does not support hybrid ('*') legs; "
                                           "split them first")
-            self._bt = bt_from_dense(self._data, self.statistics, self.encoder, self.format)
+            # not cached while a dense array exists: the caller may hold it and edit it in place (see `data`)
+            return bt_from_dense(self._data, self.statistics, self.encoder, self.format)
         return self._bt
 
     # ---- properties (reference :878-903)
@@ -1001,7 +1006,8 @@ def trim_grassmann_odd(Obj):
 def is_grassmann_even(Obj):
     bt = Obj._bt if isinstance(Obj, block) else Obj._get_bt()
     odd = [p for p in bt.live() if sum(p) % 2 == 1]
-    return (not odd) or math.sqrt(float(bt.sumsq(odd).item())) <= numer_cutoff
+    # reference :3901-3912: every odd block's L2 norm <= numer_cutoff
+    return all(math.sqrt(float(bt.sumsq([p]).item())) <= numer_cutoff for p in odd)
 
 
 from . import gauge2d  # noqa: E402

@@ -70,6 +70,7 @@ def _load():
         "gtn_debug_phase_clocks": (i32, [vp]),
         "gtn_gram_rotate": (i32, [vp, vp, i32, vp, vp, vp, i32, i32, i32, dbl, dbl, i32, vp, vp]),
         "gtn_sumsq": (i32, [vp, i64, i32, vp, i32, vp]),
+        "gtn_sumabs": (i32, [vp, i64, i32, vp, i32, vp]),
         "gtn_rowsum": (i32, [vp, vp, i64, i64, i32, vp]),
         "gtn_dot": (i32, [vp, vp, i64, i32, vp, vp, i32, vp]),
         "gtn_row_sumsq": (i32, [vp, vp, i64, i64, i32, vp]),

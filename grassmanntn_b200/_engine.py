@@ -399,6 +399,17 @@ class BT:
     def norm(self):
         return math.sqrt(float(self.sumsq().item()))
 
+    def sumabs(self, pats):
+        """sum of |x| over the blocks `pats` (the reference's Grassmann-evenness tests are L1 means)"""
+        acc = torch.zeros(1, dtype=torch.float64, device=self.buf.device)
+        code = dtype_code(self.dtype)
+        for p in pats:
+            if p in self.off and self.block_size(p) > 0:
+                v = self.buf[self.off[p]:]
+                check(lib.gtn_sumabs(_ptr(v), self.block_size(p), code, _ptr(acc), 0, _stream()), "gtn_sumabs")
+                count()
+        return acc
+
     def scale_(self, s):
         s = complex(s)
         check(lib.gtn_scale(_ptr(self.buf), self.buf.numel(), dtype_code(self.dtype), s.real, s.imag, _stream()),
@@ -416,6 +427,20 @@ def _row_strides(shape):
 
 
 _plan_cache = {}
+_graph_droppers = []        # callbacks that forget recorded CUDA graphs (gauge2d registers its step graphs)
+
+
+def drop_graphs():
+    """Forget every recorded CUDA graph (truncated-SVD schedules, whole-step graphs).  Recorded graphs bake raw
+    pointers to the device launch tables of the plans they enqueued; those tables are owned by the plan caches
+    (`_plan_cache`, `_ops._einsum_cache`), so a cache wipe must take the graphs with it -- otherwise a replay would
+    read tables from freed (and possibly reused) memory."""
+    for plan in list(globals().get("_trunc_plans", {}).values()):
+        plan.graphs.clear()
+        plan.graph_launches.clear()
+        plan.warmed.clear()
+    for fn in _graph_droppers:
+        fn()
 
 
 def _cached(key, builder):
@@ -423,6 +448,7 @@ def _cached(key, builder):
     if p is None:
         if len(_plan_cache) > 4096:
             _plan_cache.clear()
+            drop_graphs()
         p = builder()
         _plan_cache[key] = p
     return p
@@ -1532,7 +1558,12 @@ def truncated_svd_batch(mats, ks, robust=False, speculative=False, resume=None):
         if resumed and it == start_it:
             svals, res, kept_host = resume.readback
         else:
-            svals, res, kept_host = plan.read()
+            try:
+                svals, res, kept_host = plan.read()
+            except _cabi.GtnError:
+                # the small Jacobi SVD of the projected matrix did not converge: let the caller run the full SVD
+                _trunc_fail[key] = _trunc_fail.get(key, 0) + 1
+                return None
         if robust:
             kept_host = None
         ok, worst, reject = _trunc_certificate(svals, res, kept_host, ks, L_)

@@ -171,6 +171,7 @@ def einsum_bt(subscripts, ops, ignore_anticommutation=False):
     if ex is None:
         if len(_einsum_cache) > 2048:
             _einsum_cache.clear()
+            _engine_mod.drop_graphs()        # recorded graphs point into the launch tables of the evicted executors
         ex = _build_einsum(subscripts, ops, ignore_anticommutation)
         _einsum_cache[key] = ex
     return ex(ops)
@@ -490,7 +491,7 @@ def _decompose_prepare(bt, nl, kind):
         # <= 1e-14, __init__.py:3977-3983); blocks that are numerically zero are flagged and skipped
         odd = [p for p in bt.live() if sum(p) % 2 == 1]
         n_odd = sum(bt.block_size(p) for p in odd)
-        if math.sqrt(float(bt.sumsq(odd).item())) / max(n_odd, 1) > NUMER_CUTOFF:
+        if float(bt.sumabs(odd).item()) / max(n_odd, 1) > NUMER_CUTOFF:
             _err("Error[BlockSVD]: This matrix is not constructed from a Grassmann-even tensor.")
         import copy
         bt = copy.copy(bt)

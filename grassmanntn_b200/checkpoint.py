@@ -7,7 +7,9 @@ chi = 128..256 runs resumable and comparable:
 * `save_tensor` / `load_tensor` -- one `.npz` per tensor holding the parity-blocked device buffer exactly as it
   lives in HBM (`_engine.BT`: one contiguous buffer + block offsets; only the stored, i.e. even-parity, blocks),
   its statistics / even / odd dimensions / format, the container kind (dense | block, encoder) and free-form
-  metadata.  Loading restores the same bits: a resumed run continues bit-identically.
+  metadata.  Loading restores the same tensor bits; the continuation agrees with an uninterrupted run to rounding
+  (the adaptive state of the truncated SVD -- iteration counts, recorded graphs -- is not checkpointed, and the
+  Jacobi rotation order is not bitwise reproducible run to run).
 * `RunLog` -- JSON-lines file, one record per coarse-graining step with the columns example.py prints
   (reference example.py:158-196): process, volume, F (real, imag), shape, trace error, Tnorm, seconds.
 * `gauge2d.coarse_grain(..., log=, checkpoint_dir=, resume=)` uses both.
@@ -125,6 +127,14 @@ class RunLog:
             return []
         with open(self.path) as f:
             return [json.loads(line) for line in f if line.strip()]
+
+    def truncate_to(self, nrecords):
+        """keep the first `nrecords` records (a resumed run continues from a checkpoint that may be older than the
+        last logged step: the steps after it are run, and logged, again)"""
+        recs = self.read()[:nrecords]
+        with open(self.path, "w") as f:
+            for r in recs:
+                f.write(json.dumps(r) + "\n")
 
 
 def step_path(directory, step):

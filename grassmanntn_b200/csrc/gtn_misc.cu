@@ -42,6 +42,23 @@ __global__ void __launch_bounds__(RT) sumsq_kernel(const double* __restrict__ x,
   if (threadIdx.x == 0) atomicAdd(out, acc);
 }
 
+// sum of |x_i| (complex modulus for GTN_C128): the reference's Grassmann-evenness test is an L1 mean
+template <bool CPLX>
+__global__ void __launch_bounds__(RT) sumabs_kernel(const double* __restrict__ x, int64_t n, double* __restrict__ out) {
+  double acc = 0;
+  const int64_t stride = int64_t(gridDim.x) * RT;
+  for (int64_t i = int64_t(blockIdx.x) * RT + threadIdx.x; i < n; i += stride) {
+    if (CPLX) {
+      const double2 v = __ldg(reinterpret_cast<const double2*>(x) + i);
+      acc += hypot(v.x, v.y);
+    } else {
+      acc += fabs(__ldg(x + i));
+    }
+  }
+  acc = block_sum(acc);
+  if (threadIdx.x == 0) atomicAdd(out, acc);
+}
+
 template <bool CPLX>
 __global__ void __launch_bounds__(RT) rowsum_kernel(const double* __restrict__ x, double* __restrict__ y,
                                                     int64_t rows, int64_t cols) {
@@ -190,6 +207,16 @@ extern "C" int gtn_sumsq(const void* x, int64_t n, int dtype, double* out_dev, i
   if (n <= 0) return GTN_OK;
   const int64_t nd = dtype == GTN_C128 ? 2 * n : n;
   sumsq_kernel<<<grid_for(nd / 2 + 1), RT, 0, s>>>((const double*)x, nd, out_dev);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int gtn_sumabs(const void* x, int64_t n, int dtype, double* out_dev, int zero_first, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (zero_first) cudaMemsetAsync(out_dev, 0, sizeof(double), s);
+  if (n <= 0) return GTN_OK;
+  if (dtype == GTN_C128) sumabs_kernel<true><<<grid_for(n), RT, 0, s>>>((const double*)x, n, out_dev);
+  else if (dtype == GTN_F64) sumabs_kernel<false><<<grid_for(n), RT, 0, s>>>((const double*)x, n, out_dev);
+  else return GTN_ERR_BAD_ARG;
   return (int)cudaGetLastError();
 }
 

@@ -83,6 +83,20 @@ _POOL = [None, None, None]       # pool handle, keeper graph, keeper tensor
 _steady = {}                              # key -> (consecutive verified speculative eager steps, hints then)
 
 
+def _drop_step_graphs():
+    _step_graphs.clear()
+    _steady.clear()
+
+
+def _register_dropper():
+    from . import _engine as E
+    if _drop_step_graphs not in E._graph_droppers:
+        E._graph_droppers.append(_drop_step_graphs)
+
+
+_register_dropper()
+
+
 def freeze(flag=True):
     """Freeze (or release) the engine's adaptation: the truncated SVD keeps its learnt iteration counts (no lowering,
     no periodic re-derivation) and recorded step graphs are not recorded again.  For timing loops and for
@@ -505,8 +519,8 @@ def coarse_grain(T, cgsteps=5, dcut=32, method="atrg", boundary_conditions="anti
     (volume, F, Tnorm, err, shape).
     log: path of a JSON-lines run log (checkpoint.RunLog), one line per step.
     checkpoint_dir: the tensor and the accumulated log-norm are saved after every `checkpoint_every` steps;
-    with resume=True the loop continues bit-identically from the newest checkpoint found there (the reference has
-    neither).  logNorm0: log-norm accumulated before the 2D loop (flavour coarse-graining,
+    with resume=True the loop continues from the newest checkpoint found there with the same tensor bits (the
+    continuation agrees with an uninterrupted run to rounding; the reference has neither).  logNorm0: log-norm accumulated before the 2D loop (flavour coarse-graining,
     example.py:144-150)."""
     import time as _time
     from . import checkpoint as ck
@@ -520,11 +534,15 @@ def coarse_grain(T, cgsteps=5, dcut=32, method="atrg", boundary_conditions="anti
         step, path = ck.latest_step(checkpoint_dir) if resume else (None, None)
         if step is not None:
             T, meta = ck.load_tensor(path)
-            if (meta["dcut"], meta["method"], meta["boundary_conditions"]) != (dcut, method, boundary_conditions):
+            have = (meta["dcut"], meta["method"], meta["boundary_conditions"], bool(meta.get("error_test", error_test)),
+                    float(meta.get("logNorm0", logNorm0)))
+            if have != (dcut, method, boundary_conditions, bool(error_test), float(logNorm0)):
                 gtn.error("Error[coarse_grain]: the checkpoint was written with different run parameters.")
             logNorm, first, cgxfirst, records = meta["logNorm"], step, meta["cgxfirst"], meta["records"]
             for r in records:
                 r["F"], r["shape"] = complex(*r["F"]), tuple(r["shape"])
+            if runlog:
+                runlog.truncate_to(len(records))        # steps logged after the checkpoint are run (and logged) again
     if first == 0:
         F = logZ(T, boundary_conditions) + logNorm
         records.append(dict(vol=1, F=complex(F), Tnorm=None, err=None, shape=tuple(getattr(T, "effective_shape", T.shape)[:2])))
@@ -550,5 +568,6 @@ def coarse_grain(T, cgsteps=5, dcut=32, method="atrg", boundary_conditions="anti
         if checkpoint_dir and ((i + 1) % checkpoint_every == 0 or i + 1 == cgsteps):
             meta_records = [dict(r, F=[r["F"].real, r["F"].imag], shape=list(r["shape"])) for r in records]
             ck.save_tensor(ck.step_path(checkpoint_dir, i + 1), T, logNorm=logNorm, dcut=dcut, method=method,
-                           boundary_conditions=boundary_conditions, cgxfirst=bool(cgxfirst), records=meta_records)
+                           boundary_conditions=boundary_conditions, cgxfirst=bool(cgxfirst), records=meta_records,
+                           error_test=bool(error_test), logNorm0=float(logNorm0))
     return T, records

@@ -69,13 +69,24 @@ def gemm_allgather_fused(splan, A, B, out):
     from ._cabi import check, lib
     from ._engine import _ptr, _stream, dtype_code, prof_region
     nbytes = out.numel() * out.element_size()
-    try:
-        t, hdl, ptrs = _symm_output(nbytes, out.device)
-    except Exception as exc:                      # no peer access / symmetric memory on this system
-        _state["fused"] = False
-        import warnings
-        warnings.warn("grassmanntn_b200.parallel: fused GEMM+all-gather unavailable (%s); using NCCL all-gather" % exc)
-        return False
+    err = None
+    if nbytes not in _symm:
+        # first use of this size: every rank tries, then all ranks agree on the outcome (one rank falling back to
+        # the NCCL all-gather while its peers wait in the symmetric-memory barrier would deadlock)
+        try:
+            _symm_output(nbytes, out.device)
+        except Exception as exc:                  # no peer access / symmetric memory on this system
+            err = exc
+        ok = torch.tensor([0 if err is not None else 1], dtype=torch.int32, device=out.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            _symm.pop(nbytes, None)
+            _state["fused"] = False
+            import warnings
+            warnings.warn("grassmanntn_b200.parallel: fused GEMM+all-gather unavailable (%s); using NCCL all-gather"
+                          % (err if err is not None else "a peer could not map the buffer"))
+            return False
+    t, hdl, ptrs = _symm[nbytes]
     hdl.barrier(channel=0)                        # every peer has copied the previous result out of its buffer
     if splan.n and splan.tiles:
         with prof_region("grouped_gemm_bcast", 1, splan.bytes, splan.flops):

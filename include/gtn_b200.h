@@ -257,6 +257,11 @@ int gtn_debug_phase_clocks(long long* host_out8);
  * (__init__.py:891-893, :432-437).  `out` must be zeroed by the caller (or pass zero_first=1). */
 int gtn_sumsq(const void* x, int64_t n, int dtype, double* out_dev, int zero_first, void* stream);
 
+/* out[0] += sum |x_i| (complex modulus for GTN_C128).  The reference's Grassmann-evenness tests are L1 means over
+ * the odd-parity entries: BlockSVD / BlockEig (__init__.py:3977-3983, :4369-4375) and decompose_block reject a
+ * tensor whose odd entries have mean |x| > numer_cutoff. */
+int gtn_sumabs(const void* x, int64_t n, int dtype, double* out_dev, int zero_first, void* stream);
+
 /* y[r] = sum_c x[r*cols + c]  (row sums; the summed tail of a trace-type einsum such as
  * 'IJIJ' -- the final reduction of oe.contract at __init__.py:2295 when nothing is left to
  * multiply).  y has `rows` elements of the same dtype. */

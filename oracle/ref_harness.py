@@ -51,7 +51,7 @@ def load_reference():
         if hasattr(mod, "arith") and not hasattr(mod.arith, "exp"):
             mod.arith.exp = arith.exp_gnum
 
-    def power_block_fixed(T, p, rcond=0.0):
+    def power_block_fixed(T, p, rcond=1e-10):    # the reference's own default (:6071); gtn.power drops the caller's
         # restatement of the intent of __init__.py:6071-6082 (result stored, not dropped)
         this_format = T.format
         T = T.force_format("matrix")

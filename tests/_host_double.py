@@ -134,6 +134,13 @@ class HostLib:
         o[0] += float(np.sum(v.real ** 2 + (v.imag ** 2 if np.iscomplexobj(v) else 0.0)))
         return 0
 
+    def gtn_sumabs(self, x, n, code, out, zero_first, stream):
+        o = _arr(out, 1, np.float64)
+        if zero_first:
+            o[0] = 0.0
+        o[0] += float(np.sum(np.abs(_arr(x, n, self._dt(code)))))
+        return 0
+
     def gtn_rowsum(self, x, y, rows, cols, code, stream):
         dt = self._dt(code)
         _arr(y, rows, dt)[:] = _arr(x, rows * cols, dt).reshape(rows, cols).sum(axis=1)
