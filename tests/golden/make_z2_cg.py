@@ -17,6 +17,7 @@ CONFIGS = {
     "block_trg_chi32": ("block", "trg", 32, 3),
     "block_trg_chi25": ("block", "trg", 25, 2),
     "block_atrg_chi16": ("block", "atrg", 16, 3),
+    "block_atrg_chi32": ("block", "atrg", 32, 4),      # BASELINE config 1: example.py's default (ATRG, --Dcutxy 32)
     "dense_trg_chi16": ("dense", "trg", 16, 2),
     "dense_atrg_chi8": ("dense", "atrg", 8, 3),
 }

@@ -1,0 +1,169 @@
+"""Parity of the configurations the bench times, at their own sizes (round-1 review: untested configs).
+
+  * ATRG chi = 32 on the Z2 tensor (BASELINE config 1, example.py's default) against the REAL reference
+    (tests/golden/make_z2_cg.py block_atrg_chi32);
+  * TRG chi = 64 chain on the Z2 tensor (4 steps, the last one a full D = chi = 64 step on the TMA GEMM tiles and the
+    truncated SVD) against the oracle port (tests/golden/make_chain_goldens.py chi64);
+  * a 12-step TRG chain on a perturbed Z2 tensor against the REAL reference, long enough that the product's recorded
+    whole-step CUDA graph produces the compared numbers (make_chain_goldens.py stepgraph);
+  * the einsum sweep at dims 16 / 32 / 40 (ragged block) / 64 against the oracle: both GEMM tile families and
+    multi-tile permutes.
+Tolerance 1e-10 relative on Tnorm and F (north_star) unless a test states otherwise."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+import gtn_oracle as O
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+BC = "anti-periodic"
+
+
+def _z2():
+    z = np.load(os.path.join(G, "z2_initial_tensor.npz"))
+    return z["data"], tuple(int(s) for s in z["statistics"])
+
+
+# ---------------------------------------------------------------------------------------------- CPU: pin the oracle
+def test_oracle_atrg_chi32_vs_reference():
+    """the oracle port against the real reference's ATRG chi = 32 numbers (first two steps: seconds on the CPU)"""
+    ref = np.load(os.path.join(G, "z2_cg.npz"))["block_atrg_chi32"]
+    data, stats = _z2()
+    from threadpoolctl import threadpool_limits
+    with threadpool_limits(limits=1):
+        T = O.zcap(O.Dense(data, stats))
+        logNorm = 0.0
+        cgxfirst = T.shape[0] > T.shape[1]
+        for i in range(2):
+            fn = O.atrg2dx if ((i % 2 == 0) == cgxfirst) else O.atrg2dy
+            T, Tn, err = fn(T, T, 32, rule="block", error_test=True)
+            logNorm = 2 * logNorm + math.log(Tn)
+            F = (O.logZ(T, BC, block_format=True) + logNorm) / 2 ** (i + 1)
+            assert abs(Tn - ref[i + 1, 0]) <= 1e-10 * ref[i + 1, 0], (i, Tn, ref[i + 1, 0])
+            assert abs(F - complex(ref[i + 1, 2], ref[i + 1, 3])) <= 1e-10 * abs(F), (i, F)
+
+
+# ---------------------------------------------------------------------------------------------- GPU
+def _chain(gtn, T, method, cut, steps, error_test=False):
+    return gtn.gauge2d.coarse_grain(T, cgsteps=steps, dcut=cut, method=method, boundary_conditions=BC,
+                                    error_test=error_test)
+
+
+@pytest.mark.gpu
+def test_gpu_atrg_chi32_vs_reference(gtn):
+    """BASELINE config 1 at its own size: ATRG, Dcutxy = 32, Z2 tensor, block format, 4 steps, real reference."""
+    ref = np.load(os.path.join(G, "z2_cg.npz"))["block_atrg_chi32"]
+    g = gtn.gauge2d
+    T = g.zcap(g.load_initial_tensor().toblock())
+    T, recs = _chain(gtn, T, "atrg", 32, 4, error_test=True)
+    assert abs(recs[0]["F"] - complex(ref[0, 2], ref[0, 3])) < 1e-11
+    for i in range(1, 5):
+        r = recs[i]
+        assert abs(r["Tnorm"] - ref[i, 0]) <= 1e-10 * ref[i, 0], (i, r["Tnorm"], ref[i, 0])
+        assert abs(r["F"] - complex(ref[i, 2], ref[i, 3])) <= 1e-10 * abs(r["F"]), (i, r["F"])
+        assert abs(r["err"] - ref[i, 1]) <= 1e-8 * max(ref[i, 1], 1e-3), (i, r["err"], ref[i, 1])
+        assert tuple(r["shape"]) == (int(ref[i, 4]), int(ref[i, 5]))
+
+
+@pytest.mark.gpu
+def test_gpu_trg_chi64_chain_vs_oracle(gtn):
+    """TRG chi = 64 on the Z2 tensor, 4 steps (32^4 -> 32^4 -> 64^4 -> 64^4); the last step decomposes 2048 x 2048
+    sector matrices with the truncated SVD and contracts with the TMA GEMM tiles."""
+    ref = np.load(os.path.join(G, "chains.npz"))["oracle_trg_chi64"]
+    g = gtn.gauge2d
+    T = g.zcap(g.load_initial_tensor().toblock())
+    T, recs = _chain(gtn, T, "trg", 64, 4)
+    for i in range(1, 5):
+        r = recs[i]
+        assert tuple(r["shape"]) == (int(ref[i - 1, 3]), int(ref[i - 1, 4])), (i, r["shape"])
+        assert abs(r["Tnorm"] - ref[i - 1, 0]) <= 1e-10 * ref[i - 1, 0], (i, r["Tnorm"], ref[i - 1, 0])
+        assert abs(r["F"] - complex(ref[i - 1, 1], ref[i - 1, 2])) <= 1e-10 * abs(r["F"]), (i, r["F"])
+
+
+@pytest.mark.gpu
+def test_gpu_step_graph_chain_vs_reference(gtn):
+    """12 TRG steps (dcut 16) on the perturbed Z2 tensor against the real reference.  From the second step on the
+    layout is fixed (16^4), so the product first speculates its truncated SVDs and then records the whole step as one
+    CUDA graph; the test requires that at least one COMPARED step came out of a graph replay."""
+    z = np.load(os.path.join(G, "chains.npz"))
+    ref = z["stepgraph_chain"]
+    g = gtn.gauge2d
+    T = gtn.dense(z["stepgraph_input"], statistics=tuple(int(s) for s in z["stepgraph_stats"])).toblock()
+    logNorm, replayed_steps = 0.0, []
+    for i in range(12):
+        before = g.STEP_GRAPH_STATS["replayed"]
+        T, Tn = g.trg(T, 16)
+        if g.STEP_GRAPH_STATS["replayed"] > before:
+            replayed_steps.append(i)
+        logNorm = 2 * logNorm + math.log(Tn)
+        F = (g.logZ(T, BC) + logNorm) / 2 ** (i + 1)
+        assert tuple(T.effective_shape[:2]) == (int(ref[i, 3]), int(ref[i, 4]))
+        assert abs(Tn - ref[i, 0]) <= 1e-10 * ref[i, 0], (i, Tn, ref[i, 0], replayed_steps)
+        assert abs(F - complex(ref[i, 1], ref[i, 2])) <= 1e-10 * abs(F), (i, F, replayed_steps)
+    assert replayed_steps, ("no step of the chain was produced by a recorded step graph", dict(g.STEP_GRAPH_STATS))
+
+
+# einsum sweep at the dims the bench sweeps (BASELINE config 5): (subscripts, [(shape, statistics)], block format?)
+SWEEP = [
+    ("ijkl->jkli", [((16,) * 4, (1, 1, -1, -1))], False),
+    ("ijkl->lkji", [((32,) * 4, (1, -1, 1, -1))], False),
+    ("ijkl->klij", [((64,) * 4, (1, 1, -1, -1))], False),
+    ("abcdef->fedcba", [((16, 8, 16, 8, 16, 8), (1, 1, 1, -1, -1, -1))], False),
+    ("ijkl,klmn->ijmn", [((16,) * 4, (1, 1, 1, 1)), ((16,) * 4, (-1, -1, 1, 1))], False),
+    ("ijkl,klmn->ijmn", [((32,) * 4, (1, 1, 1, 1)), ((32,) * 4, (-1, -1, 1, 1))], False),
+    ("lxzk,jzxi->ijkl", [((32,) * 4, (1, 1, -1, 1)), ((32,) * 4, (-1, 1, -1, 1))], False),
+    ("lxzk,jzxi->ijkl", [((32, 64, 64, 32), (1, 1, -1, 1)), ((32, 64, 64, 32), (-1, 1, -1, 1))], False),
+    ("ajk,jib->aibk", [((32, 32, 32), (1, 1, -1)), ((32, 32, 32), (-1, 1, -1))], False),
+    ("ijkl,klij", [((32,) * 4, (1, 1, 1, 1)), ((32,) * 4, (-1, -1, -1, -1))], False),
+    ("ijkl,klmn->ijmn", [((40, 38, 42, 36), (1, 1, 1, 1)), ((42, 36, 40, 38), (-1, -1, 1, 1))], True),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", range(len(SWEEP)))
+def test_gpu_einsum_sweep_large_dims_vs_oracle(gtn, case):
+    sub, ops, as_block = SWEEP[case]
+    rng = np.random.RandomState(900 + case)
+    if as_block:
+        # ragged parity blocks (non-power-of-two bond dimensions): built block by block on both sides
+        refs, objs = [], []
+        for shape, st in ops:
+            e = [(d + 1) // 2 + 1 for d in shape]
+            o = [d - x for d, x in zip(shape, e)]
+            blocks = {}
+            B = O.Blocks(st, e, o, {})
+            gb = gtn.zero_block_eo(e, o, st, dtype=complex)
+            arr = gb.data
+            import itertools
+            for pat in itertools.product((0, 1), repeat=len(shape)):
+                shp = B.block_shape(pat)
+                v = (rng.rand(*shp) + 1j * rng.rand(*shp)) if sum(pat) % 2 == 0 else np.zeros(shp, dtype=complex)
+                blocks[pat] = v
+                arr[pat] = v
+            gb.data = arr
+            refs.append(O.Blocks(st, e, o, blocks))
+            objs.append(gtn.trim_grassmann_odd(gb))
+        ref = O.einsum_block(sub, *refs)
+        got = gtn.einsum(sub, *objs)
+        scale = max(float(np.abs(b).max()) for b in ref.blocks.values())
+        gd = got.data
+        for pat, b in ref.blocks.items():
+            assert np.abs(gd[pat].cpu().numpy() - b).max() <= 1e-12 * scale, (sub, pat)
+        return
+    pairs = []
+    for shape, st in ops:
+        o = O.random_dense(shape, st, dtype=complex, rng=rng)
+        pairs.append((o, gtn.dense(o.data, statistics=st)))
+    ref = O.einsum(sub, *[p[0] for p in pairs])
+    got = gtn.einsum(sub, *[p[1] for p in pairs])
+    if isinstance(ref, O.Dense):
+        assert got.shape == ref.shape and tuple(got.statistics) == tuple(ref.statistics)
+        g_ = got.data.cpu().numpy()
+        if "," not in sub:
+            assert np.array_equal(g_, ref.data), sub            # sign + permute only: bit-exact
+        else:
+            assert np.abs(g_ - ref.data).max() <= 1e-12 * np.abs(ref.data).max(), sub
+    else:
+        assert abs(got - ref) <= 1e-12 * max(abs(ref), 1.0)

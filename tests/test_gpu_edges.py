@@ -400,3 +400,23 @@ def test_gemm_conj_transposed_b_operand(gtn, dtype):
     R2 = -(A2 @ B2.conj().T)
     assert float((C1 - R1).abs().max()) <= 1e-12 * float(R1.abs().max())
     assert float((C2 - R2).abs().max()) <= 1e-12 * float(R2.abs().max())
+
+
+def test_dense_data_inplace_edit_is_seen(gtn):
+    """the reference idiom `X.data[...] = v` / `X.data /= s` (gauge2d.py:1748): once `.data` has been handed out the
+    array is the object's only storage, so later ops see in-place edits (round-1 advisor finding); a block made from
+    the dense object does not alias it."""
+    rng = np.random.RandomState(77)
+    o, A = _mk(gtn, (4, 4), (1, -1), rng)
+    tr0 = gtn.einsum('ii', A)
+    Bk = A.toblock()
+    A.data[0, 0] = 5.0
+    d = o.data.copy()
+    d[0, 0] = 5.0
+    ref = O.einsum('ii', O.Dense(d, (1, -1)))
+    assert abs(gtn.einsum('ii', A) - ref) <= 1e-13 * max(abs(ref), 1.0)
+    assert abs(gtn.einsum('ii', Bk) - tr0) <= 1e-13 * max(abs(tr0), 1.0)
+    X = gtn.einsum('ij->ji', A)
+    view = X.data                      # a result keeps its block form until .data is asked for
+    view *= 2.0
+    assert abs(gtn.einsum('ii', X) - 2 * gtn.einsum('ii', gtn.einsum('ij->ji', A))) <= 1e-12 * max(abs(ref), 1.0)

@@ -200,3 +200,38 @@ def test_host_hotrg3dz_z2_loose(gtn_host_trunc, cut):
 def test_host_hotrg3dz_z2_chi64_vs_reference(gtn_host_trunc):
     """BASELINE.json configs[2] ('HOTRG chi=64'): Tnorm and F equal to the real reference to 1e-10"""
     Z2.test_gpu_hotrg3dz_z2_chi64_vs_reference(gtn_host_trunc)
+
+
+# ---- large-dimension sweep / chains (tests/test_chains.py) through the host double
+import test_chains as CH  # noqa: E402
+
+
+@pytest.mark.parametrize("case", [0, 3, 4, 8, 10])
+def test_einsum_sweep_large_dims(gtn_host, case):
+    CH.test_gpu_einsum_sweep_large_dims_vs_oracle(gtn_host, case)
+
+
+def test_dense_data_inplace_edit_is_seen(gtn_host):
+    GE.test_dense_data_inplace_edit_is_seen(gtn_host)
+
+
+def test_perturbed_z2_chain_truncated_vs_reference(gtn_host_trunc):
+    """the 12-step dcut-16 TRG chain of tests/test_chains.py (real-reference golden) with the subspace-iteration SVD
+    and its certificate running on the host double: Tnorm and F to 1e-10 at every step (no graphs here; the GPU test
+    adds the recorded step graph)"""
+    import math
+    import os
+    gtn = gtn_host_trunc
+    z = np.load(os.path.join(CH.G, "chains.npz"))
+    ref = z["stepgraph_chain"]
+    g = gtn.gauge2d
+    T = gtn.dense(z["stepgraph_input"], statistics=tuple(int(s) for s in z["stepgraph_stats"])).toblock()
+    logNorm = 0.0
+    for i in range(12):
+        T, Tn = g.trg(T, 16)
+        logNorm = 2 * logNorm + math.log(Tn)
+        F = (g.logZ(T, CH.BC) + logNorm) / 2 ** (i + 1)
+        assert abs(Tn - ref[i, 0]) <= 1e-10 * ref[i, 0], (i, Tn, ref[i, 0])
+        assert abs(F - complex(ref[i, 1], ref[i, 2])) <= 1e-10 * abs(F), (i, F)
+    from grassmanntn_b200 import _ops
+    assert _ops.SVD_PATH_STATS["truncated"] >= 8
