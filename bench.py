@@ -1,27 +1,31 @@
 #!/usr/bin/env python
 """bench.py -- TRG coarse-graining steps/sec of the 2D Z2 gauge theory at chi (BASELINE.json metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--chi 32] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--chi 128] [--impl ours|reference]
 
-One "step" = one Levin-Nave TRG coarse-graining step (reference gauge2d_block.trg) of the
-chi-saturated site tensor of the Z2 (K=2), N_f=1, beta=m=q=a=1, mu=0 model in block format at
-chi (default 32 = example_block.py, BASELINE.json configs[1]).  Prints ONE JSON line.
+One "step" = one Levin-Nave TRG coarse-graining step (reference gauge2d_block.trg, gauge2d_block.py:1649-1755) of the
+chi-saturated site tensor (chi^4 complex128, block format) of the Z2 (K=2), N_f=1, beta=m=q=a=1, mu=0 model.  The
+default chi = 128 is the regime BASELINE.json's north_star names (chi >= 128: 4 GiB site tensor, 8192 x 8192 sector
+matrices); --chi 32 / 64 run the smaller configurations (chi = 32 = example_block.py; its numbers also appear in
+`extra` of the default run).  Prints ONE JSON line.
 
-  value      steps/s with the tensor already resident in HBM (CUDA events per step, L2 flushed
-             between steps, max over ranks)
-  e2e        steps/s through the public API from HOST buffers: pinned host T -> H2D -> gtn.block ->
-             trg -> dense -> D2H of T' and Tnorm, every step
-  roofline   the kernel family with the largest share of the timed region (events around every C-ABI
-             launch) against the measured peak in MEASURED_PEAKS.json; extra.microbench holds the
-             sign+permute kernel (HBM) and the DMMA GEMM (FP64 tensor pipe, yard-stick = cuBLAS
-             ZGEMM timed in the same run) at large sizes
-  cpu_baseline  the numpy oracle port (oracle/gtn_oracle.py: trg_block) on the host cores, one
-             bounded sample (rank 0, N=1)
+  value      steps/s with the tensor already resident in HBM (CUDA events per step, L2 flushed between steps, max
+             over ranks)
+  e2e        steps/s through the public API from HOST buffers: pinned host tensor in the block storage layout
+             (checkpoint.HostTensor) -> H2D -> gauge2d.trg -> D2H of T' and Tnorm, every step
+  roofline   the kernel family with the largest share of the step (CUDA events around every C-ABI launch in a second
+             pass over the same steps) against its bound: FP64 tensor pipe (yard-stick: cuBLAS ZGEMM timed in this
+             run; nominal 40 TFLOP/s stated beside it) or HBM (MEASURED_PEAKS.json)
+  cpu_baseline  the numpy oracle port (oracle/gtn_oracle.py trg_block) on the host cores, one bounded sample
+             (rank 0, N=1): a full step for chi <= 64; for chi = 128 one full step at D = chi = 64 (the same chain one
+             level earlier) scaled by (chi/64)^6 -- every O(D^6) term of the step (the four sector SVDs of
+             (D^2/2)^2 matrices, the eight sector GEMMs of the contraction) scales that way
 
---impl reference runs ONLY the CPU oracle port (the reference is Python and does not travel to
-the GPU box) with all host threads on the same config/metric.
-N > 1 (torchrun): independent replicas, one per GPU -- the TRG step at one chi does not shard in
-this round (DESIGN.md "Multi-GPU"); value = N * K / max-over-ranks time, scaling "weak".
+--impl reference runs ONLY the CPU oracle port (the reference is Python and does not travel to the GPU box; see
+DESIGN.md) with all host threads on the same config/metric; at chi = 128 every "step" is a bounded quarter sample
+of the D = 64 step (one 2048^2 sector SVD + two 2048^3 sector GEMMs), scaled to the full chi = 128 step.
+N > 1 (torchrun): ONE chain sharded over the N GPUs (gauge2d.trg on a leg-sharded tensor: grassmanntn_b200/sharded.py),
+value = K / max-over-ranks time, scaling "strong".
 """
 import argparse
 import json
@@ -37,16 +41,19 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
 import numpy as np
 
+CPU_LEVEL_MAX = 64          # the CPU oracle port runs full steps up to this D = chi
+
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--chi", type=int, default=32)
+    ap.add_argument("--chi", type=int, default=128)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--no-micro", action="store_true")
-    ap.add_argument("--micro-chi", type=int, default=64)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--replicas", action="store_true", help="N > 1: independent replicas instead of one sharded chain")
     return ap.parse_args()
 
 
@@ -104,6 +111,8 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------
+#  CPU arm: the oracle port on the host cores
+# ------------------------------------------------------------------------------------------------
 def best_blas_threads():
     """OpenBLAS/LAPACK gesdd can be pathologically slow with all threads on a busy or CPU-limited
     host (seen: 17 s vs 0.24 s for one 512x512 complex SVD).  Give the CPU baseline its best
@@ -125,28 +134,76 @@ def best_blas_threads():
     return threadpool_limits, best[0]
 
 
-def cpu_reference_run(args, data, stats, label):
-    """the oracle port of gauge2d_block.trg on the host cores"""
+def cpu_level(chi):
+    """(D = chi level the CPU port runs at, factor to the full step): every O(D^6) term scales by (chi/level)^6"""
+    if chi <= CPU_LEVEL_MAX:
+        return chi, 1.0
+    return CPU_LEVEL_MAX, (chi / CPU_LEVEL_MAX) ** 6
+
+
+def cpu_saturated(O, data, stats, level):
+    """the first site tensor of the chain with all four legs at `level` (same rule as the GPU arm)"""
+    B = O.Blocks.from_dense(O.zcap(O.Dense(data, stats)))
+    for _ in range(8):
+        if tuple(B.effective_shape) == (level,) * 4:
+            break
+        B, _ = O.trg_block(B, level)
+    return B
+
+
+def cpu_quarter_setup(O, B):
+    """the even-sector matrix of the (ab|cd) matricisation of T1 = T[jkli] (magnitudes only: a timing sample)"""
+    T1 = O.einsum_block("ijkl->jkli", B)
+
+    def mat(p):
+        b = T1.blocks[p]
+        return b.reshape(b.shape[0] * b.shape[1], -1)
+    return np.block([[mat((0, 0, 0, 0)), mat((0, 0, 1, 1))], [mat((1, 1, 0, 0)), mat((1, 1, 1, 1))]])
+
+
+def cpu_reference_run(args, data, stats, quick=False):
+    """-> dict(value, ms, shape, threads, sample).  quick: the N=1 GPU arm's cpu_baseline (one bounded sample)."""
+    import gtn_oracle as O
     limiter, nthreads = best_blas_threads()
+    level, scale = cpu_level(args.chi)
+
+    def body():
+        B = cpu_saturated(O, data, stats, level)
+        steps, warm = (3, 1) if quick else (args.steps, args.warmup)
+        if scale == 1.0:
+            for _ in range(warm):
+                O.trg_block(B, level)
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                O.trg_block(B, level)
+            dt = (time.perf_counter() - t0) / steps
+            return dt, "%d full TRG steps at chi=%d (oracle/gtn_oracle.py trg_block; numpy/LAPACK)" % (steps, level)
+        if quick:
+            t0 = time.perf_counter()
+            O.trg_block(B, level)
+            dt = time.perf_counter() - t0
+            return dt * scale, ("one full TRG step of the oracle port at D=chi=%d (%.1f s; same chain one level earlier) "
+                                "x (chi/%d)^6 = %g: the four (D^2/2)^2 sector SVDs and the eight sector GEMMs of a step "
+                                "are O(D^6)" % (level, dt, level, scale))
+        M = cpu_quarter_setup(O, B)
+        for _ in range(min(warm, 1)):
+            np.linalg.svd(M, full_matrices=False)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            np.linalg.svd(M, full_matrices=False)
+            M @ M
+            M @ M
+        dt = (time.perf_counter() - t0) / steps
+        return dt * 4 * scale, ("per step a QUARTER sample of the D=chi=%d step: LAPACK SVD of one %dx%d sector matrix of "
+                                "T1 + two of its eight %d^3 sector GEMMs (%.2f s), x 4 x (chi/%d)^6 = %g (the smaller "
+                                "O(D^5) terms of a step are left out: favours the CPU)"
+                                % (level, M.shape[0], M.shape[1], M.shape[0], dt, level, 4 * scale))
     if limiter is not None:
         with limiter(limits=nthreads):
-            return _cpu_reference_run(args, data, stats, label) + (nthreads,)
-    return _cpu_reference_run(args, data, stats, label) + (nthreads,)
-
-
-def _cpu_reference_run(args, data, stats, label):
-    import gtn_oracle as O
-    T = O.zcap(O.Dense(data, stats))
-    B = O.Blocks.from_dense(T)
-    for _ in range(2):                      # saturate chi (untimed)
-        B, _ = O.trg_block(B, args.chi)
-    for _ in range(args.warmup):
-        O.trg_block(B, args.chi)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        Bn, _ = O.trg_block(B, args.chi)
-    dt = time.perf_counter() - t0
-    return args.steps / dt, dt / args.steps * 1e3, B.effective_shape
+            t_step, sample = body()
+    else:
+        t_step, sample = body()
+    return {"value": 1.0 / t_step, "ms": t_step * 1e3, "threads": nthreads, "sample": sample}
 
 
 def settle(g, fn, max_steps=12, quiet_needed=2):
@@ -162,77 +219,89 @@ def settle(g, fn, max_steps=12, quiet_needed=2):
     return n
 
 
-def config_dict(args, label, shape):
+def config_dict(args, label, parallelism):
+    chi = args.chi
     return {"workload": "TRG step (gauge2d_block.trg), 2D Z2 gauge theory K=2 Nf=1 beta=m=q=a=1 mu=0, block format, "
-                        "chi=%d, site tensor %s complex128" % (args.chi, "x".join(str(int(s)) for s in shape)),
-            "input": label, "chi": args.chi, "parallelism": "replicas x%d" % args.gpus,
+                        "chi=%d, site tensor %s complex128 (%.2f GiB of even parity blocks)"
+                        % (chi, "x".join([str(chi)] * 4), chi ** 4 * 16 / 2 / 2 ** 30),
+            "input": label, "chi": chi, "parallelism": parallelism,
             "l2": "flushed between timed steps (256 MiB write)",
-            "batch": "every timed step processes the same site tensor (the third of the chain), in both arms"}
+            "batch": "every timed step processes the same site tensor (the first of the chain with all legs at chi), "
+                     "in both arms"}
+
+
+def saturate(g, T, chi):
+    """the first tensor of the TRG chain whose four legs have reached chi (untimed prologue)"""
+    n = 0
+    while tuple(T.effective_shape) != (chi,) * 4 and n < 8:
+        T, _ = g.trg(T, chi)
+        n += 1
+    return T, n
 
 
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
     data, stats, label = load_z2()
 
     if args.impl == "reference":
         if rank != 0:
             return
-        cores = os.cpu_count()
-        v, ms, shape, nthr = cpu_reference_run(args, data, stats, label)
-        cores = "%d BLAS threads (best of 1/all) on %d logical cores" % (nthr, cores)
-        line = {"impl": "reference", "metric": "TRG coarse-grain steps/sec at chi", "value": v, "unit": "steps/s",
-                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "complex128",
-                "data": "synthetic", "config": config_dict(args, label, shape),
-                "cpu_baseline": {"value": v, "unit": "steps/s", "cores": cores, "kind": "port",
-                                 "sample": "%d full TRG steps at chi=%d (oracle/gtn_oracle.py trg_block; numpy/LAPACK, "
-                                           "all host threads)" % (args.steps, args.chi)},
-                "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        r = cpu_reference_run(args, data, stats)
+        cores = "%d BLAS threads (best of 1/all) on %d logical cores" % (r["threads"], os.cpu_count())
+        line = {"impl": "reference", "metric": "TRG coarse-grain steps/sec at chi", "value": r["value"], "unit": "steps/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms"],
+                "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None,
+                "dtype": "complex128", "data": "synthetic",
+                "config": config_dict(args, label, "1 CPU process, all host threads"),
+                "cpu_baseline": {"value": r["value"], "unit": "steps/s", "cores": cores, "kind": "port", "sample": r["sample"]},
+                "e2e": {"value": r["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
+    if world > 1 and not args.replicas:
+        return main_sharded(args, data, stats, label)
+    return main_single(args, data, stats, label)
 
+
+def main_single(args, data, stats, label):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl")
     import grassmanntn_b200 as gtn
-    from grassmanntn_b200 import _engine as E
+    from grassmanntn_b200 import _engine as E, checkpoint as ck
     g = gtn.gauge2d
     dev = torch.device("cuda", local)
+    chi = args.chi
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    T0 = g.zcap(gtn.dense(data, statistics=stats)).toblock()
-    T = T0
-    for _ in range(2):                       # saturate chi (untimed prologue)
-        T, _ = g.trg(T, args.chi)
-    shape = T.effective_shape
-    # untimed prologue, continued: reach the engine's steady state on this layout (iteration hints settled, SVD
-    # schedules and the whole-step graph recorded) -- the one-off recording costs ~50 ms and is setup, not a step
-    # Every timed step works on the SAME input T (third tensor of the chain: a spectrum that still needs subspace
-    # iterations, not the nearly rank-deficient fixed point the chain reaches later), like the CPU arm does.
-    for _ in range(24):
-        g.trg(T, args.chi)
-    settle(g, lambda: g.trg(T, args.chi))
+    T, sat_steps = saturate(g, g.zcap(gtn.dense(data, statistics=stats)).toblock(), chi)
+    # untimed prologue, continued: reach the engine's steady state on this layout (iteration counts of the truncated SVD
+    # settled, its schedules -- and at chi <= 64 the whole-step graph -- recorded): one-off set-up, not a step.
+    # Every timed step works on the SAME input T, like the CPU arm does.
+    for _ in range(24 if chi <= 64 else 6):
+        g.trg(T, chi)
+    settle(g, lambda: g.trg(T, chi), max_steps=12 if chi <= 64 else 2)
     g.freeze(True)                           # timing: learnt iteration counts and recorded graphs stay as they are
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    # ---- clocks / throttle reasons under load: sampled on rank 0 only (one nvidia-smi poller per box; eight of
-    #      them steal host cores from the ranks) from the warm-up to the end of the end-to-end loop
+    # ---- clocks / throttle reasons under load: sampled on rank 0 only, from the warm-up to the end of the e2e loop
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler is not None:
         sampler.start()
     # ---- device-resident steps
     for _ in range(args.warmup):
         flush.fill_(1)
-        g.trg(T, args.chi)
+        g.trg(T, chi)
     barrier()
     n0 = gtn.launch_count()
     evs = []
@@ -240,130 +309,93 @@ def main():
         flush.fill_(1)
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
-        X, Tn = g.trg(T, args.chi)
+        X, Tn = g.trg(T, chi)
         e.record()
         evs.append((s, e))
     barrier()
     launches = gtn.launch_count() - n0
     t_dev = sum(s.elapsed_time(e) for s, e in evs) * 1e-3
-    # ---- per-kernel-family shares: the same steps once more with CUDA events around every launch.  The
-    #      timed loop above replays the truncated-SVD schedule as a CUDA graph, where single launches
-    #      cannot be bracketed; with the profiler on the engine launches the same kernels one by one.
+    del X
+    # ---- per-kernel-family shares: the same steps once more with CUDA events around every launch (the timed loop
+    #      replays the truncated-SVD schedule as a CUDA graph, where single launches cannot be bracketed; with the
+    #      profiler on the engine launches the same kernels one by one).  At chi >= 64 a launch lasts 0.1-250 ms, so
+    #      the event overhead (~10 us) does not distort the shares; at chi = 32 see DESIGN.md.
+    nprof = min(args.steps, 5 if chi > 64 else args.steps)
     E.PROF.start()
-    for _ in range(args.steps):
+    for _ in range(nprof):
         flush.fill_(1)
-        X, Tn = g.trg(T, args.chi)
+        g.trg(T, chi)
     prof = E.PROF.stop()
     g.freeze(False)
 
-    # ---- end to end from host buffers
-    host_in = torch.from_numpy(np.ascontiguousarray(T.todense().data.cpu().numpy())).pin_memory()
-    tstats = T.statistics
-
-    host_out = [None]
+    # ---- end to end from host buffers (block storage layout in pinned memory, one copy each way per step)
+    h_in = ck.to_host(T)
+    torch.cuda.synchronize()
+    box = [None]
 
     def e2e_step():
-        d = host_in.to(dev, non_blocking=True)
-        Xb = gtn.dense(d, statistics=tstats).toblock()
-        Y, Tn = g.trg(Xb, args.chi)
-        out = Y.todense().data
-        if host_out[0] is None or host_out[0].shape != out.shape:
-            host_out[0] = torch.empty(out.shape, dtype=out.dtype).pin_memory()
-        host_out[0].copy_(out, non_blocking=True)
+        Xb = ck.from_host(h_in)
+        Y, Tn_ = g.trg(Xb, chi)
+        box[0] = ck.to_host(Y, out=box[0])
         torch.cuda.current_stream().synchronize()
-        return host_out[0], Tn
-    for _ in range(max(24, args.warmup)):       # the host-fed tensor has its own layout (all 16 blocks): own graph
+        return Tn_
+    for _ in range(3):
         e2e_step()
-    settle(g, e2e_step)
+    settle(g, e2e_step, max_steps=12 if chi <= 64 else 1)
     g.freeze(True)
     for _ in range(args.warmup):
         e2e_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        ho, _ = e2e_step()
+        e2e_step()
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
     g.freeze(False)
     clocks = sampler.result() if sampler is not None else None
-    h2d = host_in.numel() * host_in.element_size()
-    d2h = ho.numel() * ho.element_size() + 8
+    h2d, d2h = h_in.nbytes, box[0].nbytes + 8
+    peak_mem = torch.cuda.max_memory_allocated() / 2 ** 30
 
     tt = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     t_dev, t_e2e = tt.tolist()
-    sharded = None
-    if world > 1:
-        sharded = sharded_contraction(gtn, torch, dist, dev, 128 if not args.no_micro else 64)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+    del T, h_in, box
+    torch.cuda.empty_cache()
 
     hbm_peak, peak_src = peaks()
-    tot_ms = sum(v["ms"] for v in prof.values())
-    dom = max(prof, key=lambda k: prof[k]["ms"])
-    d = prof[dom]
-    per_launch_ms = d["ms"] / max(d["launches"], 1)
-    common = {"timing": "CUDA events around every launch in a second pass over the same steps (the timed loop "
-                        "replays the SVD schedule as a CUDA graph)",
-              "note": "at chi=32 every kernel of the step works on L2-resident data (the whole tensor is 16 MiB; the "
-                      "projected matrices are 40 rows) and is latency / issue bound; the HBM and FP64-tensor "
-                      "rooflines of the same kernels at chi>=64/128 are in extra.microbench and extra.rooflines_at_scale",
-              "share_of_step": d["ms"] / tot_ms if tot_ms else None,
-              "avg_launch_us": per_launch_ms * 1e3, "launches_per_step": d["launches"] / args.steps}
-    if dom == "grouped_gemm" and d["flops"]:
-        # FP64 tensor-core bound: algorithmic flops of the non-zero sectors / launch time, against cuBLAS ZGEMM
-        # measured in this run (MEASURED_PEAKS.json has no FP64 entry; nominal B200 figure is 40 TFLOP/s)
-        f64_peak, f64_src = fp64_tensor_peak(torch, dev)
-        achieved = d["flops"] / (d["ms"] * 1e-3) / 1e12
-        roofline = dict({"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": f64_peak, "unit": "TFLOP/s",
-                         "frac": achieved / f64_peak, "traffic": None, "peak_source": f64_src}, **common)
-    else:
-        achieved = (d["bytes"] / max(d["launches"], 1)) / (per_launch_ms * 1e-3) / 1e9 if d["bytes"] else 0.0
-        roofline = dict({"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src}, **common)
-    if dom in NCU_TRAFFIC and args.chi == 32:
-        roofline["traffic"], roofline["traffic_source"] = NCU_TRAFFIC[dom]
-    shares = {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
-                  "share": v["ms"] / tot_ms if tot_ms else None,
-                  "algorithmic_GBps": (v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] and v["bytes"] else None,
-                  "algorithmic_TFLOPs": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["ms"] and v["flops"] else None}
-              for k, v in prof.items()}
+    f64_peak, f64_src = fp64_tensor_peak(torch, dev)
+    roofline, shares, step_frac = roofline_of(prof, nprof, t_dev / args.steps, chi, hbm_peak, peak_src, f64_peak, f64_src)
     from grassmanntn_b200 import _ops
-    extra = {"step_graph": dict(g.STEP_GRAPH_STATS), "speculation": dict(g.SPEC_STATS),
-             "sharded_contraction": sharded, "kernel_shares": shares, "jacobi_sweeps_last": E.batched_svd.last_sweeps,
-             "svd_paths": dict(_ops.SVD_PATH_STATS), "trunc_refinements_last": E.truncated_svd_batch.last_iters}
+    extra = {"step_graph": dict(g.STEP_GRAPH_STATS), "speculation": dict(g.SPEC_STATS), "kernel_shares": shares,
+             "whole_step_vs_fp64_yardstick": step_frac, "saturation_steps": sat_steps, "peak_mem_GiB": peak_mem,
+             "jacobi_sweeps_last": E.batched_svd.last_sweeps, "svd_paths": dict(_ops.SVD_PATH_STATS),
+             "trunc_refinements_last": E.truncated_svd_batch.last_iters}
     if not args.no_micro:
-        extra["microbench"] = microbench(gtn, E, torch, dev, args, hbm_peak)
-        extra["other_workloads"] = other_workloads(gtn, torch, data, stats, args)
-        mb = extra["microbench"]
-        f64_peak, f64_src = fp64_tensor_peak(torch, dev)
+        extra["microbench"] = mb = microbench(gtn, E, torch, dev, args, hbm_peak)
+        extra["other_workloads"] = other_workloads(gtn, torch, data, stats, 32)
         extra["rooflines_at_scale"] = {
             "sign_permute_D128": {"bound": "hbm", "achieved": mb["sign_permute_D128"]["GBps"], "peak": hbm_peak,
                                   "unit": "GB/s", "frac": mb["sign_permute_D128"]["GBps"] / hbm_peak,
                                   "peak_source": peak_src, "algorithmic_bytes": mb["sign_permute_D128"]["bytes"],
                                   "traffic": 8546507000,
-                                  "traffic_source": "profiles/r1_sign_permute_D128_ncu_full.txt (dram read + write per launch)"},
-            "trg_contraction_D128": {"bound": "tensor", "achieved": mb["trg_contraction_D128"]["TFLOPs_total"],
-                                     "peak": f64_peak, "unit": "TFLOP/s",
-                                     "frac": mb["trg_contraction_D128"]["TFLOPs_total"] / f64_peak,
-                                     "peak_source": f64_src}}
+                                  "traffic_source": "profiles/r1_sign_permute_D128_ncu_full.txt (dram read + write per launch)"}}
 
     cpu = None
-    if world == 1:
-        a2 = argparse.Namespace(**vars(args))
-        a2.steps, a2.warmup = 3, 1
-        v, ms, _, nthr = cpu_reference_run(a2, data, stats, label)
-        cpu = {"value": v, "unit": "steps/s",
-               "cores": "%d BLAS threads (best of 1/all) on %d logical cores" % (nthr, os.cpu_count()), "kind": "port",
-               "sample": "3 full TRG steps at chi=%d with the numpy oracle port (oracle/gtn_oracle.py trg_block)" % args.chi}
+    if world == 1 and not args.no_cpu:
+        r = cpu_reference_run(args, data, stats, quick=True)
+        cpu = {"value": r["value"], "unit": "steps/s",
+               "cores": "%d BLAS threads (best of 1/all) on %d logical cores" % (r["threads"], os.cpu_count()),
+               "kind": "port", "sample": r["sample"]}
 
     line = {"metric": "TRG coarse-grain steps/sec at chi", "value": world * args.steps / t_dev, "unit": "steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_dev / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "complex128",
-            "data": "synthetic", "config": config_dict(args, label, shape), "clocks": clocks,
+            "data": "synthetic", "config": config_dict(args, label, "replicas x%d" % world), "clocks": clocks,
             "e2e": {"value": world * args.steps / t_e2e, "unit": "steps/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "extra": extra}
@@ -372,15 +404,49 @@ def main():
         dist.destroy_process_group()
 
 
+def roofline_of(prof, nprof, step_s, chi, hbm_peak, peak_src, f64_peak, f64_src):
+    """(roofline of the dominant kernel family, per-family shares, whole-step fraction of the FP64 yard-stick)"""
+    tot_ms = sum(v["ms"] for v in prof.values())
+    shares = {k: {"ms_per_step": v["ms"] / nprof, "launches_per_step": v["launches"] / nprof,
+                  "share": v["ms"] / tot_ms if tot_ms else None,
+                  "algorithmic_GBps": (v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] and v["bytes"] else None,
+                  "algorithmic_TFLOPs": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["ms"] and v["flops"] else None}
+              for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+    dom = max(prof, key=lambda k: prof[k]["ms"])
+    d = prof[dom]
+    per_launch_ms = d["ms"] / max(d["launches"], 1)
+    common = {"kernel": dom, "share_of_step": d["ms"] / tot_ms if tot_ms else None, "avg_launch_us": per_launch_ms * 1e3,
+              "launches_per_step": d["launches"] / nprof,
+              "timing": "CUDA events on the launching stream around every launch of a second pass over the same steps"}
+    gemm_flops = sum(v["flops"] for k, v in prof.items() if k.startswith("gemm")) / nprof
+    step_frac = {"algorithmic_TFLOP_per_step": gemm_flops / 1e12, "TFLOPs": gemm_flops / step_s / 1e12,
+                 "frac_of_yardstick": gemm_flops / step_s / 1e12 / f64_peak, "frac_of_nominal_40": gemm_flops / step_s / 4e13,
+                 "note": "all DMMA GEMM flops of a step (contraction + subspace-iteration panels; non-zero parity sectors "
+                         "only) over the whole step time"}
+    if dom.startswith("gemm") and d["flops"]:
+        achieved = d["flops"] / (d["ms"] * 1e-3) / 1e12
+        roofline = dict({"bound": "tensor", "achieved": achieved, "peak": f64_peak, "unit": "TFLOP/s",
+                         "frac": achieved / f64_peak, "traffic": None, "peak_source": f64_src,
+                         "frac_of_nominal_40": achieved / 40.0,
+                         "algorithmic_flops_per_launch": d["flops"] / max(d["launches"], 1)}, **common)
+    else:
+        achieved = (d["bytes"] / max(d["launches"], 1)) / (per_launch_ms * 1e-3) / 1e9 if d["bytes"] else 0.0
+        roofline = dict({"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src}, **common)
+    if (dom, chi) in NCU_TRAFFIC:
+        roofline["traffic"], roofline["traffic_source"] = NCU_TRAFFIC[(dom, chi)]
+    return roofline, shares, step_frac
+
+
 # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the chi=32 step's kernel families from
 # the committed `ncu --set full` captures: the working set is L2-resident, so DRAM traffic is far below the
 # algorithmic bytes.  (For the HBM-bound kernel at scale, sign+permute D=128: 8.55 GB measured = 8.59 GB algorithmic,
 # profiles/r1_sign_permute_D128_ncu_full.txt.)
 NCU_TRAFFIC = {
-    "jacobi_persistent": (1449984, "profiles/r1b_jacobi_persistent_ncu_full.txt"),
-    "grouped_gemm": (304640, "profiles/r1_skinny_gemm_ncu_full.txt (32x32 panel configuration)"),
-    "chol_whiten": (443136, "profiles/r1b_chol_whiten_ncu_full.txt"),
-    "gram_rotate": (454400, "profiles/r1b_gram_rotate_ncu_full.txt"),
+    ("jacobi_persistent", 32): (1449984, "profiles/r1b_jacobi_persistent_ncu_full.txt"),
+    ("gemm_skinny_32x32", 32): (304640, "profiles/r1_skinny_gemm_ncu_full.txt (32x32 panel configuration)"),
+    ("chol_whiten", 32): (443136, "profiles/r1b_chol_whiten_ncu_full.txt"),
+    ("gram_rotate", 32): (454400, "profiles/r1b_gram_rotate_ncu_full.txt"),
 }
 
 
@@ -402,13 +468,14 @@ def fp64_tensor_peak(torch, dev, n=4096):
         return 40.0, "nominal B200 FP64 tensor peak (cuBLAS yard-stick unavailable)"
 
 
-def other_workloads(gtn, torch, data, stats, args):
+def other_workloads(gtn, torch, data, stats, chi):
     """steps/s of the other coarse-graining drivers on the same Z2 tensor (not part of `value`):
     ATRG (example.py's default) in block and dense format, TRG in dense format, and TRG on a random
     Grassmann-even tensor (flat spectrum: the truncated SVD is rejected, full Jacobi SVD runs)."""
     import gtn_oracle as O
     g = gtn.gauge2d
     out = {}
+    args = argparse.Namespace(chi=chi)
 
     def timed(fn, T, n=5, warm=2):
         """ms per step of the chain X -> fn(X) after `warm` steps (the chain goes on: no restart, the engine's
@@ -448,6 +515,18 @@ def other_workloads(gtn, torch, data, stats, args):
     out["atrg_block_chi%d_ms" % args.chi] = timed(atrg, sat_b, n=6, warm=31)
     out["atrg_dense_chi%d_ms" % args.chi] = timed(atrg, sat_d, n=6, warm=31)
     out["speculation"] = dict(g.SPEC_STATS)
+    # the round-1 headline (chi = 32, same tensor every step, whole-step graph), device-resident
+    for _ in range(24):
+        g.trg(sat_b, args.chi)
+    settle(g, lambda: g.trg(sat_b, args.chi))
+    g.freeze(True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(20):
+        g.trg(sat_b, args.chi)
+    torch.cuda.synchronize()
+    out["trg_block_same_tensor_chi%d_ms" % args.chi] = (time.perf_counter() - t0) / 20 * 1e3
+    g.freeze(False)
     out["trg_block_late_chain_chi%d_ms" % args.chi] = timed(lambda X: g.trg(X, args.chi)[0], sat_b, n=6, warm=30)
     out["trg_dense_chi%d_ms" % args.chi] = timed(lambda X: g.trg(X, args.chi)[0], sat_d, n=5, warm=30)
     rng = np.random.RandomState(3)
@@ -502,8 +581,10 @@ def einsum_sweep(gtn, torch, O):
         ent = {"ms": ms}
         if "sign_permute" in pr:
             ent["permute_GBps"] = pr["sign_permute"]["bytes"] / (pr["sign_permute"]["ms"] * 1e-3) / 1e9
-        if "grouped_gemm" in pr and pr["grouped_gemm"]["flops"]:
-            ent["gemm_TFLOPs"] = pr["grouped_gemm"]["flops"] / (pr["grouped_gemm"]["ms"] * 1e-3) / 1e12
+        gm = [v for k, v in pr.items() if k.startswith("gemm") and v["flops"]]
+        if gm:
+            ent["gemm_TFLOPs"] = sum(v["flops"] for v in gm) / (sum(v["ms"] for v in gm) * 1e-3) / 1e12
+            ent["gemm_family"] = [k for k in pr if k.startswith("gemm")]
         res[sub] = ent
     return res
 
@@ -623,13 +704,14 @@ def microbench(gtn, E, torch, dev, args, hbm_peak):
             pr = E.PROF.stop()
             ms = s.elapsed_time(e) / reps
             flops = 2.0 * D ** 6
-            gm = pr["grouped_gemm"]
+            fam = [k for k in pr if k.startswith("gemm")]
+            gm = {"ms": sum(pr[k]["ms"] for k in fam), "flops": sum(pr[k]["flops"] for k in fam)}
             out["trg_contraction_D%d" % D] = {
                 "ms_total": ms, "TFLOPs_total": flops / (ms * 1e-3) / 1e12,
                 "ms_gemm": gm["ms"] / reps, "TFLOPs_gemm": gm["flops"] / reps / (gm["ms"] / reps * 1e-3) / 1e12,
                 "ms_pack": pr["sign_permute"]["ms"] / reps,
                 "pack_GBps": pr["sign_permute"]["bytes"] / reps / (pr["sign_permute"]["ms"] / reps * 1e-3) / 1e9,
-                "algorithmic_flops": flops}
+                "algorithmic_flops": flops, "gemm_family": fam}
             del VV, UU, r
             torch.cuda.empty_cache()
         except Exception as ex:       # e.g. out of memory on a smaller part

@@ -74,6 +74,45 @@ def unpack_bt(z, device=None):
     return bt
 
 
+class HostTensor:
+    """A tensor parked in (pinned) host memory in the storage layout of the device: the parity-block buffer plus its
+    block table.  `to_host` / `from_host` move it with ONE asynchronous copy each way -- the host-side format of a
+    long run that streams site tensors between host and device (and of bench.py's end-to-end measurement)."""
+    __slots__ = ("buf", "stats", "e", "o", "fmt", "dtype", "off", "zero", "kind", "encoder", "shape")
+
+    @property
+    def nbytes(self):
+        return self.buf.numel() * self.buf.element_size()
+
+
+def to_host(T, out=None, pinned=True):
+    """device tensor -> HostTensor (reusing `out`'s pinned buffer when its size fits).  The copy is enqueued on the
+    current stream; synchronise before reading `out.buf`."""
+    bt, kind, encoder = _bt_of(T)
+    h = out if out is not None else HostTensor()
+    if out is None or out.buf.numel() != bt.buf.numel() or out.buf.dtype != bt.buf.dtype:
+        h.buf = torch.empty(bt.buf.numel(), dtype=bt.buf.dtype)
+        if pinned and torch.cuda.is_available():
+            h.buf = h.buf.pin_memory()
+    h.buf.copy_(bt.buf, non_blocking=True)
+    h.stats, h.e, h.o, h.fmt, h.dtype = tuple(bt.stats), tuple(bt.e), tuple(bt.o), bt.fmt, bt.dtype
+    h.off, h.zero = dict(bt.off), set(bt.zero)
+    h.kind, h.encoder, h.shape = kind, encoder, tuple(T.shape)
+    return h
+
+
+def from_host(h, device=None):
+    """HostTensor -> device tensor of the container kind it was taken from (one asynchronous H2D copy)."""
+    from . import block, dense
+    bt = _engine.BT(h.stats, h.e, h.o, h.dtype, h.fmt)
+    bt.off, bt.zero = dict(h.off), set(h.zero)
+    dev = device if device is not None else _engine.require_cuda()
+    bt.buf = h.buf.to(dev, non_blocking=True)
+    if h.kind == "block":
+        return block._from_bt(bt, h.shape)
+    return dense._from_bt(bt, h.encoder or "canonical")
+
+
 def save_tensor(path, T, **meta):
     """Write T (dense or block) and JSON-serialisable metadata to `path` (.npz), atomically."""
     bt, kind, encoder = _bt_of(T)

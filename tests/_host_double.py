@@ -306,6 +306,9 @@ def install(monkeypatch, truncated=False):
     fake = (HostLibSVD if truncated else HostLib)(_cabi.lib)
     saved = dict(E._plan_cache)
     E._plan_cache.clear()
+    from grassmanntn_b200 import sharded
+    for name, val in (("_stream", lambda: None), ("PermutePlan", HostPlan), ("lib", fake)):
+        monkeypatch.setattr(sharded, name, val)
     for mod in (E, _ops):
         monkeypatch.setattr(mod, "require_cuda", lambda: cpu)
         monkeypatch.setattr(mod, "_stream", lambda: None)
