@@ -404,6 +404,127 @@ def main_single(args, data, stats, label):
         dist.destroy_process_group()
 
 
+def main_sharded(args, data, stats, label):
+    """N > 1: ONE TRG chain, site tensor sharded along its first leg over the N ranks (grassmanntn_b200/sharded.py):
+    column-sharded truncated SVD (all-reduce of sketch panels), all-gather of the isometries, output-row sharded
+    contraction.  Same step, same input tensor as the N = 1 line: strong scaling."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl")
+    import grassmanntn_b200 as gtn
+    from grassmanntn_b200 import _engine as E, checkpoint as ck, sharded
+    g = gtn.gauge2d
+    dev = torch.device("cuda", local)
+    chi = args.chi
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    # prologue: every rank runs the short chain to the first chi^4 tensor, then rank 0's copy becomes everybody's
+    # (SVD gauges are not bitwise reproducible between processes)
+    T, sat_steps = saturate(g, g.zcap(gtn.dense(data, statistics=stats)).toblock(), chi)
+    sharded.broadcast_tensor(T, 0)
+    Tl = sharded.shard(T)
+    # one single-GPU step of the same tensor on rank 0's data (every rank: it is the parity reference of the line)
+    _, tn_single = g.trg(T, chi)
+    del T
+    torch.cuda.empty_cache()
+    for _ in range(6):                        # iteration counts of the sharded decomposition settle
+        sharded.trg(Tl, chi)
+    g.freeze(True)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler is not None:
+        sampler.start()
+    for _ in range(args.warmup):
+        flush.fill_(1)
+        sharded.trg(Tl, chi)
+    barrier()
+    n0 = gtn.launch_count()
+    st0 = dict(sharded.STATS)
+    evs = []
+    for _ in range(args.steps):
+        flush.fill_(1)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        X, tn_sharded = sharded.trg(Tl, chi)
+        e.record()
+        evs.append((s, e))
+    barrier()
+    launches = gtn.launch_count() - n0
+    comm = {k: (sharded.STATS[k] - st0[k]) / args.steps for k in st0}
+    t_dev = sum(s.elapsed_time(e) for s, e in evs) * 1e-3
+    del X
+    nprof = min(args.steps, 5)
+    E.PROF.start()
+    for _ in range(nprof):
+        flush.fill_(1)
+        sharded.trg(Tl, chi)
+    prof = E.PROF.stop()
+    # ---- end to end: every rank streams ITS shard from / to pinned host memory
+    h_in = ck.to_host(Tl)
+    torch.cuda.synchronize()
+    box = [None]
+
+    def e2e_step():
+        Xb = ck.from_host(h_in)
+        Xb._shard_full = Tl._shard_full
+        Y, tn = sharded.trg(Xb, chi)
+        box[0] = ck.to_host(Y, out=box[0])
+        torch.cuda.current_stream().synchronize()
+    for _ in range(max(args.warmup, 2)):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    t_e2e = time.perf_counter() - t0
+    g.freeze(False)
+    clocks = sampler.result() if sampler is not None else None
+    peak_mem = torch.cuda.max_memory_allocated() / 2 ** 30
+    tt = torch.tensor([t_dev, t_e2e, peak_mem], dtype=torch.float64, device=dev)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_dev, t_e2e, peak_mem = tt.tolist()
+    h2d, d2h = h_in.nbytes * world, (box[0].nbytes + 8) * world
+    if rank != 0:
+        dist.destroy_process_group()
+        return
+    hbm_peak, peak_src = peaks()
+    f64_peak, f64_src = fp64_tensor_peak(torch, dev)
+    roofline, shares, step_frac = roofline_of(prof, nprof, t_dev / args.steps, chi, hbm_peak, peak_src, f64_peak, f64_src)
+    step_frac["note"] += "; rank 0's share of the flops over the step time (x N for the job)"
+    coll = {k: v for k, v in shares.items() if k.startswith("nccl")}
+    limiting = max(coll, key=lambda k: coll[k]["ms_per_step"]) if coll else None
+    line = {"metric": "TRG coarse-grain steps/sec at chi", "value": args.steps / t_dev, "unit": "steps/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_dev / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "complex128",
+            "data": "synthetic",
+            "config": config_dict(args, label, "sharded: site tensor split along its first leg over %d ranks "
+                                               "(column-sharded truncated SVD, isometry all-gather, output-row "
+                                               "sharded contraction)" % world),
+            "clocks": clocks,
+            "e2e": {"value": args.steps / t_e2e, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches,
+            "sharded": {"ranks": world, "tnorm_rel_diff_vs_single_gpu": abs(tn_sharded - tn_single) / tn_single,
+                        "allreduce_MiB_per_step": comm["allreduce_bytes"] / 2 ** 20,
+                        "allgather_MiB_per_step": comm["allgather_bytes"] / 2 ** 20,
+                        "broadcast_MiB_per_step": comm["broadcast_bytes"] / 2 ** 20,
+                        "collectives_per_step": comm["collectives"],
+                        "collective_ms_per_step": {k: v["ms_per_step"] for k, v in coll.items()},
+                        "limiting_collective": limiting, "peak_mem_GiB_per_rank": peak_mem,
+                        "svd_iterations": E.truncated_svd_batch.last_iters},
+            "roofline": roofline, "cpu_baseline": None,
+            "extra": {"kernel_shares": shares, "whole_step_vs_fp64_yardstick": step_frac, "saturation_steps": sat_steps}}
+    print(json.dumps(line))
+    dist.destroy_process_group()
+
+
 def roofline_of(prof, nprof, step_s, chi, hbm_peak, peak_src, f64_peak, f64_src):
     """(roofline of the dominant kernel family, per-family shares, whole-step fraction of the FP64 yard-stick)"""
     tot_ms = sum(v["ms"] for v in prof.values())

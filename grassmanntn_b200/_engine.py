@@ -699,7 +699,7 @@ class GroupLayout:
 SKINNY_MAX = int(__import__("os").environ.get("GTN_SKINNY_MAX", "128"))
 # TMA-staged DMMA kernel (csrc/gtn_gemm_tma.cu) for launches with at least this many 128x64 (or 64x64) tiles
 USE_TMA = bool(int(__import__("os").environ.get("GTN_TMA", "1")))
-TMA_MIN_TILES = int(__import__("os").environ.get("GTN_TMA_MIN_TILES", "74"))
+TMA_MIN_TILES = int(__import__("os").environ.get("GTN_TMA_MIN_TILES", "37"))
 TMA_MAX_GROUPS = 32         # GTN_TMA_MAX_GROUPS of include/gtn_b200.h
 GEMM_FAMILY = {0: "gemm_ldgsts_64x64", 1: "gemm_skinny_32x32", 3: "gemm_skinny_32x32", 4: "gemm_tma_64x64",
                12: "gemm_tma_128x64"}
@@ -753,14 +753,32 @@ class GemmPlan:
         self.host = arr                      # the TMA path encodes its tensor maps from the host copy
         self.dev = _to_dev_bytes(bytes(arr))
 
+    # measured on the B200 (scripts/gemm_bench.py, profiles/r2_gemm_bench.json): rate of a configuration on a large
+    # problem without a partial last wave, relative to cuBLAS ZGEMM; CTAs resident per GPU; tile shape
+    _CFG = {12: (0.975, 148, 128, 64), 4: (0.975, 296, 64, 64), 1: (0.91, 296, 32, 32), 0: (0.95, 296, 64, 64)}
+
     def _choose(self, groups, arr, code):
-        if USE_TMA and self.n <= TMA_MAX_GROUPS and min(min(g["m"], g["n"], g["k"]) for g in groups) >= 64 \
-                and lib.gtn_gemm_tma_check(arr, self.n, code):
-            cfg = 12 if max(g["m"] for g in groups) >= 128 else 4
-            if int(lib.gtn_gemm_plan_host(arr, self.n, code, cfg)) >= TMA_MIN_TILES:
-                return cfg
-        # skinny problems (a side <= SKINNY_MAX) get the 32x32 / deep-K configuration
-        return 1 if all(min(g["m"], g["n"]) <= SKINNY_MAX for g in groups) else 0
+        """the configuration with the best estimated rate: (rate on full waves) x (useful part of the padded tiles)
+        x (filled part of the last wave).  Large square products take the TMA tiles; the l x q x p panels of the
+        subspace iteration at chi = 128 (512 tiles of 128x64: 3.5 waves) run faster on the fine 32x32 tiles."""
+        cands = [1, 0]
+        if USE_TMA and self.n <= TMA_MAX_GROUPS and min(min(g["m"], g["n"]) for g in groups) >= 64 \
+                and min(g["k"] for g in groups) >= 16 and lib.gtn_gemm_tma_check(arr, self.n, code):
+            cands.insert(0, 12 if max(g["m"] for g in groups) >= 128 else 4)
+        useful = sum(g["m"] * g["n"] * g.get("batch", 1) for g in groups)
+        best, best_eff = 0, -1.0
+        for cfg in cands:
+            base, slots, bm, bn = self._CFG[cfg]
+            tiles = int(lib.gtn_gemm_plan_host(arr, self.n, code, cfg))
+            if tiles <= 0:
+                continue
+            waves = -(-tiles // slots)
+            eff = base * (useful / (tiles * bm * bn)) * (tiles / (waves * slots))
+            if (cfg & 4) and tiles < TMA_MIN_TILES:
+                continue
+            if eff > best_eff * 1.005:
+                best, best_eff = cfg, eff
+        return best
 
     def run(self, A, B, Cm):
         if self.n == 0 or self.tiles == 0:

@@ -60,10 +60,25 @@ def _nbytes(t):
 
 def all_reduce_(t):
     if world() > 1:
-        dist.all_reduce(_real(t))
+        with E.prof_region("nccl_allreduce", 0, _nbytes(t)):
+            dist.all_reduce(_real(t))
         STATS["allreduce_bytes"] += _nbytes(t)
         STATS["collectives"] += 1
     return t
+
+
+def _all_gather(out, mine):
+    with E.prof_region("nccl_allgather", 0, _nbytes(out)):
+        dist.all_gather_into_tensor(_real(out), _real(mine))
+    STATS["allgather_bytes"] += _nbytes(out)
+    STATS["collectives"] += 1
+
+
+def _broadcast(t, src):
+    with E.prof_region("nccl_broadcast", 0, _nbytes(t)):
+        dist.broadcast(_real(t), src=src)
+    STATS["broadcast_bytes"] += _nbytes(t)
+    STATS["collectives"] += 1
 
 
 def leg_range(n, r, w):
@@ -141,9 +156,7 @@ def gather_leg(bt, leg, full_e, full_o):
         if lays[r][3] < pad:
             mine = torch.cat([mine, torch.zeros(pad - lays[r][3], dtype=bt.dtype, device=bt.buf.device)])
         gathered = torch.empty(w * pad, dtype=bt.dtype, device=bt.buf.device)
-        dist.all_gather_into_tensor(_real(gathered), _real(mine.contiguous()))
-        STATS["allgather_bytes"] += _nbytes(gathered)
-        STATS["collectives"] += 1
+        _all_gather(gathered, mine.contiguous())
 
     def build():
         jobs = []
@@ -272,9 +285,7 @@ class ShardedTruncPlan(E._TruncPlan):
         for b in range(nb):
             loc = ws.view(self.hB[b])
             if w > 1:
-                dist.all_gather_into_tensor(_real(self.gbuf[b]), _real(loc.reshape(-1)))
-                STATS["allgather_bytes"] += _nbytes(self.gbuf[b])
-                STATS["collectives"] += 1
+                _all_gather(self.gbuf[b], loc.reshape(-1))
             else:
                 self.gbuf[b].copy_(loc.reshape(-1))
         jws = self.jws
@@ -332,9 +343,7 @@ class ShardedTruncPlan(E._TruncPlan):
             for b in range(nb):
                 src = b % w
                 for t in (jws.view(self.jU[b]), jws.view(self.jV[b]), self.s_dev[self.soff[b]: self.soff[b] + self.L_[b]]):
-                    dist.broadcast(_real(t), src=src)
-                    STATS["broadcast_bytes"] += _nbytes(t)
-                    STATS["collectives"] += 1
+                    _broadcast(t, src)
         for b in range(nb):
             l, q = self.L_[b], self.Q_[b]
             ws.view(self.hUb[b]).copy_(jws.view(self.jU[b]))
@@ -460,8 +469,7 @@ def unshard(Tl, full_e=None, full_o=None, leg=0):
 def broadcast_tensor(T, src=0):
     """make rank `src`'s tensor the tensor of every rank (same layout assumed): one broadcast of the block buffer"""
     if world() > 1:
-        dist.broadcast(_real(T._bt.buf), src=src)
-        STATS["broadcast_bytes"] += _nbytes(T._bt.buf)
+        _broadcast(T._bt.buf, src)
     return T
 
 

@@ -91,14 +91,15 @@ def test_tma_gemm_groups_batch_raster(gtn, cplx):
 
 
 def test_tma_plan_selection(gtn):
-    """large aligned products take the TMA configuration, ragged / misaligned / skinny ones keep cp.async"""
+    """large aligned products take the TMA tiles; products whose tile grid leaves a partial last wave, ragged /
+    misaligned / skinny ones take the fine 32x32 or the 64x64 cp.async tiles (GemmPlan._choose)"""
     import torch
     from grassmanntn_b200 import _engine as E
-    big = dict(a_off=0, b_off=0, c_off=0, lda=2048, ldb=2048, ldc=2048, m=2048, n=2048, k=2048)
+    big = dict(a_off=0, b_off=0, c_off=0, lda=4096, ldb=4096, ldc=4096, m=4096, n=4096, k=4096)
     assert E.GemmPlan([big], torch.complex128).config == 12
-    assert E.GemmPlan([dict(big, m=64, lda=2048)], torch.complex128).config in (4, 1)
-    odd = dict(big, lda=2049)
-    assert E.GemmPlan([odd], torch.float64).config == 0            # float64 rows not 16-byte aligned
+    assert E.GemmPlan([dict(big, m=2048, n=2048, k=2048)], torch.complex128).config == 1     # 3.5 waves of 128x64 tiles
+    odd = dict(big, lda=4097)
+    assert E.GemmPlan([odd], torch.float64).config in (0, 1)       # float64 rows not 16-byte aligned: no TMA
     assert E.GemmPlan([odd], torch.complex128).config == 12
     small = dict(a_off=0, b_off=0, c_off=0, lda=13, ldb=12, ldc=12, m=13, n=12, k=13)
     assert E.GemmPlan([small], torch.complex128).config == 1
