@@ -45,6 +45,14 @@ def test_oracle_atrg_chi32_vs_reference():
             assert abs(F - complex(ref[i + 1, 2], ref[i + 1, 3])) <= 1e-10 * abs(F), (i, F)
 
 
+# From the third ATRG step on (first step with every leg at chi = 32) the cut of the Z2 model's spectrum falls inside an
+# exact multiplet: which members survive is decided by rounding in ANY implementation.  Measured here: the numpy /
+# LAPACK oracle port -- the same algorithm as the reference, line by line -- differs from the real reference by 6.8e-7
+# (Tnorm) / 7.4e-7 (F) at step 3 and 6.2e-8 / 3.9e-8 at step 4, after agreeing to 1e-15 at steps 1 and 2.  The GPU path
+# is held to 1e-10 where the reference is reproducible and to 5e-6 (the weight of the cut multiplet) beyond.
+ATRG32_TOL = [1e-10, 1e-10, 5e-6, 5e-6]
+
+
 # ---------------------------------------------------------------------------------------------- GPU
 def _chain(gtn, T, method, cut, steps, error_test=False):
     return gtn.gauge2d.coarse_grain(T, cgsteps=steps, dcut=cut, method=method, boundary_conditions=BC,
@@ -61,9 +69,10 @@ def test_gpu_atrg_chi32_vs_reference(gtn):
     assert abs(recs[0]["F"] - complex(ref[0, 2], ref[0, 3])) < 1e-11
     for i in range(1, 5):
         r = recs[i]
-        assert abs(r["Tnorm"] - ref[i, 0]) <= 1e-10 * ref[i, 0], (i, r["Tnorm"], ref[i, 0])
-        assert abs(r["F"] - complex(ref[i, 2], ref[i, 3])) <= 1e-10 * abs(r["F"]), (i, r["F"])
-        assert abs(r["err"] - ref[i, 1]) <= 1e-8 * max(ref[i, 1], 1e-3), (i, r["err"], ref[i, 1])
+        tol = ATRG32_TOL[i - 1]
+        assert abs(r["Tnorm"] - ref[i, 0]) <= tol * ref[i, 0], (i, r["Tnorm"], ref[i, 0])
+        assert abs(r["F"] - complex(ref[i, 2], ref[i, 3])) <= tol * abs(r["F"]), (i, r["F"])
+        assert abs(r["err"] - ref[i, 1]) <= max(1e-8, 100 * tol) * max(ref[i, 1], 1e-3), (i, r["err"], ref[i, 1])
         assert tuple(r["shape"]) == (int(ref[i, 4]), int(ref[i, 5]))
 
 
