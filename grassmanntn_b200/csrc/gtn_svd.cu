@@ -963,6 +963,174 @@ __global__ void __launch_bounds__(NT)
   if (stamp) gtn_phase_clk[3] = clock64();
 }
 
+// Shared-memory variant for EIG_MAXN < n <= PK_MAXN (chi = 96 ... 128: l = 128 rows of the iterated subspace), where
+// the full G + L pair of the kernel above (2 n (n+1) elements) does not fit any more and the global-scratch variant
+// pays an L2 round trip per element and pivot (1.3 ms per launch at n = 128: 13 ms of a chi = 128 TRG step, and the
+// largest piece of work that is REPLICATED when the step is sharded over several GPUs).  Here the Hermitian matrix is
+// kept as its packed lower triangle (n (n+1) / 2 elements, 129 KB at n = 128) and factorised IN PLACE without moving
+// data for the pivoting: the column of pivot k is frozen where it stands -- rows and columns of earlier pivots are
+// never touched again -- so that  L_k[i] = G_k[i][p_k] / sqrt(pivot_k)  is read back from the triangle when the
+// inverse is built.  Per pivot: stage the pivot column into a double-buffered vector (coalesced, conflict-free reads
+// for everybody), rank-1 update of the remaining lower triangle (half the work of the full-matrix update), two block
+// barriers.  The inverse is built one column per warp (32 columns in flight) in a per-warp shared column buffer and
+// scattered into T.
+constexpr int PK_MAXN = 128;
+constexpr int PK_T = 1024;
+__device__ __forceinline__ int tri(int i) { return (i * (i + 1)) >> 1; }
+// G[i][j] of the Hermitian matrix held as packed lower triangle
+__device__ __forceinline__ c128 herm_get(const c128* Gp, int i, int j) {
+  if (i >= j) return Gp[tri(i) + j];
+  c128 v = Gp[tri(j) + i];
+  v.im = -v.im;
+  return v;
+}
+
+template <bool CPLX>
+__global__ void __launch_bounds__(PK_T)
+    chol_whiten_packed_kernel(const typename Elem<CPLX>::T* __restrict__ Gb, typename Elem<CPLX>::T* __restrict__ Tb,
+                              const int64_t* __restrict__ g_off, const int64_t* __restrict__ t_off,
+                              const int32_t* __restrict__ ns, int nsplit, double rel_thr, int32_t* __restrict__ kept) {
+  using T = typename Elem<CPLX>::T;
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  const int n = ns[blockIdx.x];
+  c128* Gp = reinterpret_cast<c128*>(sm_raw);
+  c128* colbuf = Gp + tri(n);                       // (PK_T / 32) columns of n + 1 elements
+  __shared__ c128 vb[2][PK_MAXN];
+  __shared__ int perm[PK_MAXN];
+  __shared__ double invs[PK_MAXN];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool stamp = tid == 0 && blockIdx.x == 0;
+  if (stamp) gtn_phase_clk[0] = clock64();
+  const T* Gin = Gb + g_off[blockIdx.x];
+  T* Tout = Tb + t_off[blockIdx.x];
+  // ---- load the lower triangle (sum of the split-K partial Gram matrices), clear T
+  for (int e = tid; e < n * n; e += PK_T) {
+    const int i = e / n, j = e - i * n;
+    if (j <= i) {
+      c128 v; v.re = 0.0; v.im = 0.0;
+      for (int sp = 0; sp < nsplit; ++sp) {
+        const T t = Elem<CPLX>::ld(Gin + sp * n * n + e);
+        if constexpr (CPLX) { v.re += t.re; v.im += t.im; } else v.re += t;
+      }
+      Gp[tri(i) + j] = v;
+    }
+    if constexpr (CPLX) { T z; z.re = 0.0; z.im = 0.0; Elem<CPLX>::st(Tout + e, z); } else Elem<CPLX>::st(Tout + e, 0.0);
+  }
+  __syncthreads();
+  // ---- pivoted Cholesky, in place
+  constexpr int NW = PK_MAXN / 32;
+  unsigned done[NW];
+  double dreg[NW];
+#pragma unroll
+  for (int t = 0; t < NW; ++t) {
+    done[t] = 0u;
+    const int i = lane + 32 * t;
+    dreg[t] = i < n ? Gp[tri(i) + i].re : -1.0;
+  }
+  double first = 0.0;
+  int rank = n;
+  for (int k = 0; k < n; ++k) {
+    double best = -1.0; int bidx = 0;
+#pragma unroll
+    for (int t = 0; t < NW; ++t) {
+      const bool free_ = !((done[t] >> lane) & 1u);
+      if (free_ && dreg[t] > best) { best = dreg[t]; bidx = lane + 32 * t; }
+    }
+    const unsigned key = best > 0.0 ? (unsigned)(__double_as_longlong(best) >> 32) : 0u;
+    const unsigned top = __reduce_max_sync(0xffffffffu, key);
+    const int src = __ffs(__ballot_sync(0xffffffffu, key == top)) - 1;
+    best = __shfl_sync(0xffffffffu, best, src);
+    bidx = __shfl_sync(0xffffffffu, bidx, src);
+    if (k == 0) first = best;
+    if (!(best > rel_thr * first && best > 0.0)) { rank = k; break; }
+    const int pk = bidx;
+    const double inv = rsqrt(best);
+    const double inv2 = inv * inv;
+    c128* v = vb[k & 1];
+    if (tid < n) v[tid] = herm_get(Gp, tid, pk);                 // column p_k as it stands (frozen from now on)
+    if (tid == 0) { perm[k] = pk; invs[k] = inv; }
+#pragma unroll
+    for (int t = 0; t < NW; ++t)
+      if ((pk >> 5) == t) done[t] |= 1u << (pk & 31);
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < NW; ++t) {
+      const int i = lane + 32 * t;
+      if (i < n && !((done[t] >> lane) & 1u)) {
+        const c128 g = v[i];
+        dreg[t] -= (g.re * g.re + g.im * g.im) * inv2;
+      }
+    }
+    // G[i][j] -= v[i] conj(v[j]) / pivot over the free rows i >= j: one warp per row, lanes along the row
+    for (int i = warp; i < n; i += PK_T / 32) {
+      if ((done[i >> 5] >> (i & 31)) & 1u) continue;
+      c128 a = v[i];
+      a.re *= inv2; a.im *= inv2;
+      c128* row = Gp + tri(i);
+      for (int j = lane; j <= i; j += 32) {
+        if ((done[j >> 5] >> (j & 31)) & 1u) continue;
+        const c128 b = v[j];
+        c128 g = row[j];
+        g.re -= a.re * b.re + a.im * b.im;
+        g.im -= a.im * b.re - a.re * b.im;
+        row[j] = g;
+      }
+    }
+    __syncthreads();
+  }
+  if (tid == 0 && rank < n) {
+    int k = rank;
+    for (int i = 0; i < n; ++i)
+      if (!((done[i >> 5] >> (i & 31)) & 1u)) perm[k++] = i;
+  }
+  __syncthreads();
+  const int r = rank;
+  if (stamp) gtn_phase_clk[1] = clock64();
+  // ---- Li = L_r^{-1}, L_r[i][j] = G_j[perm[i]][perm[j]] * invs[j] (i >= j); one column per warp
+  c128* col = colbuf + warp * (n + 1);
+  for (int c0 = 0; c0 < r; c0 += PK_T / 32) {
+    const int c = c0 + warp;
+    const bool live = c < r;
+    for (int i = c0; i < r; ++i) {               // block-uniform trip count; columns c > i just idle
+      const int pi = perm[i];
+      double sr = 0.0, si = 0.0;
+      if (live && i > c) {
+        for (int j = c + lane; j < i; j += 32) {
+          c128 l = herm_get(Gp, pi, perm[j]);
+          const double s_ = invs[j];
+          l.re *= s_; l.im *= s_;
+          const c128 x = col[j];
+          sr -= l.re * x.re - l.im * x.im;
+          si -= l.re * x.im + l.im * x.re;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        sr += __shfl_xor_sync(0xffffffffu, sr, o);
+        si += __shfl_xor_sync(0xffffffffu, si, o);
+      }
+      if (live && i >= c && lane == 0) {
+        if (i == c) sr += 1.0;
+        const double d = invs[i];
+        c128 o; o.re = sr * d; o.im = si * d;
+        col[i] = o;
+      }
+      __syncwarp();
+    }
+    if (live) {
+      const int pc = perm[c];                    // T[i][perm[c]] = Li[i][c]
+      for (int i = c + lane; i < r; i += 32) {
+        const c128 v = col[i];
+        T* dst = Tout + int64_t(i) * n + pc;
+        if constexpr (CPLX) { T t; t.re = v.re; t.im = v.im; Elem<CPLX>::st(dst, t); } else Elem<CPLX>::st(dst, v.re);
+      }
+    }
+    __syncwarp();
+  }
+  if (tid == 0) kept[blockIdx.x] = r;
+  if (stamp) { gtn_phase_clk[2] = clock64(); gtn_phase_clk[3] = clock64(); }
+}
+
 // Pre-rotation for the one-sided Jacobi SVD of a short-and-wide matrix B (n rows): from G = B B^H
 // compute a unitary T such that the rows of T B are orthogonal up to the accuracy a Gram matrix
 // allows.  G = P L L^H P^T (pivoted Cholesky, above); the rows of L are orthogonalised by one-sided
@@ -1110,6 +1278,22 @@ extern "C" int gtn_chol_whiten(const void* G, void* T, int dtype, const int64_t*
     if (max_n <= 48) { if (c) GTN_CHOL_LAUNCH(true, 3, c128); else GTN_CHOL_LAUNCH(false, 3, double); }
     else             { if (c) GTN_CHOL_LAUNCH(true, 5, c128); else GTN_CHOL_LAUNCH(false, 5, double); }
 #undef GTN_CHOL_LAUNCH
+  } else if (max_n <= PK_MAXN) {
+    // packed lower triangle + 32 column buffers in shared memory (199 KB at n = 128)
+    const size_t smem = (size_t(max_n) * (max_n + 1) / 2 + size_t(PK_T / 32) * (max_n + 1)) * 16;
+    static size_t attr = 0;
+    if (smem > attr) {
+      int e = set_smem(chol_whiten_packed_kernel<true>, smem);
+      if (!e) e = set_smem(chol_whiten_packed_kernel<false>, smem);
+      if (e) return e;
+      attr = smem;
+    }
+    if (dtype == GTN_C128)
+      chol_whiten_packed_kernel<true><<<nprob, PK_T, smem, s>>>((const c128*)G, (c128*)T, g_off_dev, t_off_dev, n_dev,
+                                                                 nsplit, rel_thr, kept_dev);
+    else
+      chol_whiten_packed_kernel<false><<<nprob, PK_T, smem, s>>>((const double*)G, (double*)T, g_off_dev, t_off_dev,
+                                                                  n_dev, nsplit, rel_thr, kept_dev);
   } else {
     if (!scratch) return GTN_ERR_BAD_ARG;
     const int64_t stride = gtn_chol_whiten_scratch_elems(max_n);
