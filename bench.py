@@ -564,6 +564,12 @@ def roofline_of(prof, nprof, step_s, chi, hbm_peak, peak_src, f64_peak, f64_src)
 # algorithmic bytes.  (For the HBM-bound kernel at scale, sign+permute D=128: 8.55 GB measured = 8.59 GB algorithmic,
 # profiles/r1_sign_permute_D128_ncu_full.txt.)
 NCU_TRAFFIC = {
+    # the chi = 128 main contraction (8 sector GEMMs 4096 x 4096 x 8192 in one launch: 242 of the family's 247 ms per
+    # step): 37.13 GB read + 2.35 GB written against 6.44 GB of operands + result -- with K = 8192 the A / B panels of
+    # the 148 resident 128x64 tiles (2 x 1100 rows x 8192 x 16 B = 288 MB per wave, 111 waves) exceed L2, so every wave
+    # streams its panels once; DRAM is 2 % busy, the tensor pipe 97.9 % (profiles/r2_tma_contraction_chi128_ncu_full.txt)
+    ("gemm_tma_128x64", 128): (39483494000, "profiles/r2_tma_contraction_chi128_ncu_full.txt (dram read + write of the "
+                                            "main-contraction launch, 98 % of the family's time)"),
     ("jacobi_persistent", 32): (1449984, "profiles/r1b_jacobi_persistent_ncu_full.txt"),
     ("gemm_skinny_32x32", 32): (304640, "profiles/r1_skinny_gemm_ncu_full.txt (32x32 panel configuration)"),
     ("chol_whiten", 32): (443136, "profiles/r1b_chol_whiten_ncu_full.txt"),

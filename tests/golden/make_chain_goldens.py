@@ -8,7 +8,10 @@
                     real reference's element-wise Python loops need hours at D = 64).  The port itself is pinned
                     against the real reference at chi <= 32 by tests/test_z2_golden.py.
 
-  python tests/golden/make_chain_goldens.py [stepgraph] [chi64]
+  atrg_chain        8 ATRG steps (alternating atrg2dx / atrg2dy like example.py:178-188, Dcut 16) of the REAL reference on the
+                    same perturbed tensor: golden for the sharded ATRG chain (tests/test_sharded_gloo.py, test_gpu_sharded.py)
+
+  python tests/golden/make_chain_goldens.py [stepgraph] [chi64] [atrg]
 """
 import math
 import os
@@ -24,7 +27,7 @@ from threadpoolctl import threadpool_limits  # noqa: E402
 
 OUT = os.path.join(HERE, "chains.npz")
 out = dict(np.load(OUT)) if os.path.exists(OUT) else {}
-want = sys.argv[1:] or ["stepgraph", "chi64"]
+want = sys.argv[1:] or ["stepgraph", "chi64", "atrg"]
 z = np.load(os.path.join(HERE, "z2_initial_tensor.npz"))
 stats6 = tuple(int(s) for s in z["statistics"])
 BC = "anti-periodic"
@@ -57,6 +60,27 @@ if "stepgraph" in want:
     out["stepgraph_input"] = data
     out["stepgraph_stats"] = np.asarray(st)
     out["stepgraph_chain"] = np.array(rec, dtype=float)
+    np.savez_compressed(OUT, **out)
+
+if "atrg" in want:
+    import ref_harness
+    gtn = ref_harness.load_reference()
+    data, st = perturbed_tensor()
+    T = gtn.dense(data, statistics=st).toblock()
+    mod = gtn.gauge2d_block
+    rec, logNorm = [], 0.0
+    cgxfirst = T.shape[0] > T.shape[1]
+    t0 = time.time()
+    with threadpool_limits(limits=1):
+        for i in range(8):
+            use_x = (i % 2 == 0) == cgxfirst
+            fn = mod.atrg2dx if use_x else mod.atrg2dy
+            T, Tn = fn(T, T, 16, iternum=i)[:2]
+            logNorm = 2 * logNorm + math.log(Tn)
+            F = (mod.logZ(T.copy(), BC) + logNorm) / 2 ** (i + 1)
+            rec.append([Tn, F.real, F.imag, T.effective_shape[0], T.effective_shape[1], 1.0 if use_x else 0.0])
+            print("atrg", i, "x" if use_x else "y", Tn, F, T.effective_shape, "%.1f s" % (time.time() - t0), flush=True)
+    out["atrg_chain"] = np.array(rec, dtype=float)
     np.savez_compressed(OUT, **out)
 
 if "chi64" in want:

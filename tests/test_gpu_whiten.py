@@ -36,13 +36,15 @@ def _whiten(torch, G_list, nsplit=1, rel_thr=1e-13):
                 parts[0] = parts[0] - d
         Gbuf[off: off + nsplit * n * n] = torch.from_numpy(parts.reshape(-1)).to(dev)
     Tbuf = torch.full((acc_t,), 7.0, dtype=dt, device=dev)
-    i64 = lambda v: torch.tensor(v, dtype=torch.int64, device=dev)
+    g_off_d = torch.tensor(g_off, dtype=torch.int64, device=dev)       # (kept alive until the kernel has run)
+    t_off_d = torch.tensor(t_off, dtype=torch.int64, device=dev)
+    n_d = torch.tensor(ns, dtype=torch.int32, device=dev)
     kept = torch.zeros(nb, dtype=torch.int32, device=dev)
     se = int(lib.gtn_chol_whiten_scratch_elems(max(ns)))
     scratch = torch.empty(max(se * nb, 1), dtype=torch.complex128, device=dev)
-    check(lib.gtn_chol_whiten(E._ptr(Gbuf), E._ptr(Tbuf), E.dtype_code(dt), E._ptr(i64(g_off)), E._ptr(i64(t_off)),
-                              E._ptr(torch.tensor(ns, dtype=torch.int32, device=dev)), nb, max(ns), nsplit, rel_thr,
-                              E._ptr(kept), E._ptr(scratch), None), "gtn_chol_whiten")
+    check(lib.gtn_chol_whiten(E._ptr(Gbuf), E._ptr(Tbuf), E.dtype_code(dt), E._ptr(g_off_d), E._ptr(t_off_d),
+                              E._ptr(n_d), nb, max(ns), nsplit, rel_thr, E._ptr(kept), E._ptr(scratch), None),
+          "gtn_chol_whiten")
     torch.cuda.synchronize()
     Ts = [Tbuf[o: o + n * n].view(n, n).cpu().numpy() for o, n in zip(t_off, ns)]
     return Ts, kept.cpu().numpy()
