@@ -460,6 +460,7 @@ def shard(T, leg=0):
 
 
 def unshard(Tl, full_e=None, full_o=None, leg=0):
+    """the full tensor on every rank (all-gather along the sharded leg `leg`)"""
     import grassmanntn_b200 as gtn
     if full_e is None:
         full_e, full_o = Tl._shard_full
@@ -547,3 +548,99 @@ def trg(Tl, dcut, full_e=None, full_o=None):
     out = Tn * (1.0 / Tnorm)
     out._shard_full = new_full
     return out, Tnorm
+
+
+# ------------------------------------------------------------------------------------------------
+#  sharded ATRG step
+# ------------------------------------------------------------------------------------------------
+def _swap_xy(T):
+    import grassmanntn_b200 as gtn
+    return gtn.einsum("jikl->jilk", gtn.einsum("ijkl->jikl", T))
+
+
+def _need(cond, what):
+    if not cond:
+        import grassmanntn_b200 as gtn
+        gtn.error("Error[sharded.atrg]: %s does not split evenly over %d ranks." % (what, world()))
+
+
+def _blk(bt):
+    import grassmanntn_b200 as gtn
+    return gtn.block._from_bt(bt)
+
+
+def atrg2dy(Tl, dcut, intermediate_dcut=None):
+    """One ATRG step along y (reference gauge2d_block.py atrg2dy, gauge2d.py:1761-1869, T1 is T2) on a site tensor
+    T[i,j,k,l] sharded along its SECOND leg j.  Returns (T' sharded along its FIRST leg, Tnorm): a y step consumes the
+    legs i, k and hands j, l through, the x step that follows (atrg2dx) consumes j, l -- so the result is sharded on
+    a new bond, which costs nothing because the isometries it is built from are replicated.
+
+    Where the sharded leg sits in the three decompositions (always a COLUMN leg, so every sector matrix is a column
+    block W[:, C_r] for sharded.truncated_svd_sharded):
+        T[l,i | j,k]  (j)    ->  V1[a,j,k] sharded on j, U1 replicated
+        M[a,i | b,k]         <-  C = S1 V1 is all-gathered (an isometry: chi D^2 numbers) and re-cut along k, so that
+                                 M = C . B comes out sharded on k without a reduction over the sharded j
+        Q[i,j | k,l]  (l)    <-  Q2 = X . A with A = V1 (sharded on T's j leg = Q's l), X all-gathered; Q1 replicated
+    and T' = H . G with G all-gathered and H cut along its new bond.  Collectives: three isometry-sized all-gathers
+    plus the panels of the three decompositions."""
+    import grassmanntn_b200 as gtn
+    E_ = gtn.einsum
+    w = world()
+    chi_i = dcut if intermediate_dcut is None else intermediate_dcut
+    bt = Tl._bt
+    full_j = getattr(Tl, "_shard_full", (bt.e[1] * w, bt.o[1] * w))
+    full_k = (bt.e[2], bt.o[2])
+    _need(full_j[0] % w == 0 and full_j[1] % w == 0, "the sharded leg j")
+    _need(full_k[0] % w == 0 and full_k[1] % w == 0, "leg k")
+
+    def svd1(obj, string, cut, tag):
+        res = svd_many_sharded([obj], string, cut, site=("atrg", "sharded", tag))
+        if res is None:
+            gtn.error("Error[sharded.atrg]: decomposition %s did not meet its certificate on the sharded matrices; "
+                      "gather the tensor (sharded.unshard) and run gauge2d.atrg2dy for this step." % tag)
+        return res[0]
+    Tr = E_("ijkl->lijk", Tl)                                   # [l,i,j,k], sharded on index 2
+    U1, S1, V1 = svd1(Tr, "li|jk", chi_i, 1)
+    A = V1                                                       # [a, j in R_r, k]
+    B = E_("lia,ab->lib", U1, S1)                                # replicated
+    C = E_("ab,bjk->ajk", S1, V1)                                # sharded on j
+    C = _blk(gather_leg(C._bt, 1, *full_j))                      # all-gather (isometry) ...
+    C = _blk(slice_leg(C._bt, 2))                                # ... and re-cut along k
+    M = E_("ajk,jib->aibk", C, B)                                # sharded on index 3 (k)
+    U, S, V = svd1(M, "ai|bk", chi_i, 2)
+    sq = gtn.sqrt(S)
+    Y = E_("abx,xc->abc", U, sq)                                 # replicated
+    X = E_("ax,xbc->abc", sq, V)                                 # sharded on index 2 (k)
+    X = _blk(gather_leg(X._bt, 2, *full_k))
+    Q1 = E_("iax,xbj->ijab", U1, Y)                              # replicated (D = U2 = U1)
+    Q2 = E_("kya,ylb->abkl", X, A)                               # sharded on index 3 (T's j leg)
+    Q = E_("ijab,abkl->ijkl", Q1, Q2)                            # sharded on index 3
+    del Q1, Q2
+    U, S, V = svd1(Q, "ij|kl", dcut, 3)
+    sq = gtn.sqrt(S)
+    H = E_("abx,xc->abc", U, sq)                                 # replicated
+    G = E_("ax,xbc->abc", sq, V)                                 # sharded on index 2 (T's j leg)
+    G = _blk(gather_leg(G._bt, 2, *full_j))
+    H = E_("lai->ila", H)
+    G = E_("kaj->ajk", G)
+    new_full = (H._bt.e[0], H._bt.o[0])
+    _need(new_full[0] % w == 0 and new_full[1] % w == 0, "the new bond (%d even + %d odd)" % new_full)
+    Hr = _blk(slice_leg(H._bt, 0))
+    Tn = E_("ila,ajk->ijkl", Hr, G)                              # sharded on index 0 (new bond)
+    acc = Tn._bt.sumsq()
+    all_reduce_(acc)
+    Tnorm = math.sqrt(float(acc.item()))
+    out = Tn * (1.0 / Tnorm)
+    out._shard_full = new_full
+    return out, Tnorm
+
+
+def atrg2dx(Tl, dcut, intermediate_dcut=None):
+    """One ATRG step along x (reference atrg2dx, gauge2d.py:1871-1889: swap the legs, atrg2dy, swap back) on a site
+    tensor sharded along its FIRST leg; returns (T' sharded along its SECOND leg, Tnorm) -- ready for atrg2dy."""
+    Ts = _swap_xy(Tl)                                            # the sharded leg moves from index 0 to index 1
+    Ts._shard_full = Tl._shard_full
+    out, Tnorm = atrg2dy(Ts, dcut, intermediate_dcut)
+    res = _swap_xy(out)                                          # sharded on index 1 now
+    res._shard_full = out._shard_full
+    return res, Tnorm

@@ -71,6 +71,23 @@ def _worker(rank, world, port, q):
             f_l = g.logZ(sharded.unshard(Tl), "anti-periodic")
             rows.append((abs(tn_l - tn_s) / tn_s, abs(f_l - f_s) / abs(f_s)))
         out["z2_chi32"] = rows
+        # ---- ATRG, alternating x / y steps, against the real reference (golden "atrg_chain")
+        aref = z["atrg_chain"]
+        T = gtn.dense(z["stepgraph_input"], statistics=tuple(int(s) for s in z["stepgraph_stats"])).toblock()
+        logNorm = 0.0
+        for i in range(2):
+            T, Tn = (g.atrg2dx if aref[i, 5] else g.atrg2dy)(T, T, 16)
+            logNorm = 2 * logNorm + math.log(Tn)
+        sharded.broadcast_tensor(T, 0)
+        Tl = sharded.shard(T, 0 if aref[2, 5] else 1)
+        rows = []
+        for i in range(2, 8):
+            use_x = bool(aref[i, 5])
+            Tl, Tn = (sharded.atrg2dx if use_x else sharded.atrg2dy)(Tl, 16)
+            logNorm = 2 * logNorm + math.log(Tn)
+            F = (g.logZ(sharded.unshard(Tl, leg=1 if use_x else 0), "anti-periodic") + logNorm) / 2 ** (i + 1)
+            rows.append((abs(Tn - aref[i, 0]) / aref[i, 0], abs(F - complex(aref[i, 1], aref[i, 2])) / abs(F)))
+        out["atrg"] = rows
         out["stats"] = dict(sharded.STATS)
         q.put((rank, out))
     finally:
@@ -96,7 +113,9 @@ def test_gpu_sharded_trg_chain_two_ranks(gtn):
     for rank, out in res.items():
         for dT, dF in out["perturbed"]:
             assert dT <= 1e-10 and dF <= 1e-10, (rank, out["perturbed"])
+        for dT, dF in out["atrg"]:
+            assert dT <= 1e-10 and dF <= 1e-10, (rank, "atrg", out["atrg"])
         for dT, dF in out["z2_chi32"]:
             assert dT <= 1e-6 and dF <= 1e-6, (rank, out["z2_chi32"])
         assert out["stats"]["allreduce_bytes"] > 0 and out["stats"]["allgather_bytes"] > 0
-    print("sharded parity:", res[0]["perturbed"], res[0]["z2_chi32"])
+    print("sharded parity: trg", res[0]["perturbed"], "z2 chi32", res[0]["z2_chi32"], "atrg", res[0]["atrg"])

@@ -69,7 +69,26 @@ def _worker(rank, world, port, q):
             full = sharded.unshard(Tl)
             F = (g.logZ(full, "anti-periodic") + logNorm) / 2 ** (i + 1)
             rows.append((Tn, F, abs(Tn - ref[i, 0]) / ref[i, 0], abs(F - complex(ref[i, 1], ref[i, 2])) / abs(F)))
-        q.put((rank, rows, dict(sharded.STATS)))
+        # ---- ATRG: alternating x / y steps (example.py:178-188), real-reference golden "atrg_chain"
+        aref = z["atrg_chain"]
+        T = gtn.dense(z["stepgraph_input"], statistics=tuple(int(s) for s in z["stepgraph_stats"])).toblock()
+        logNorm = 0.0
+        for i in range(2):                                   # 8^4 -> 16x8x16x8 -> 16^4: single process
+            fn = g.atrg2dx if aref[i, 5] else g.atrg2dy
+            T, Tn = fn(T, T, 16)
+            logNorm = 2 * logNorm + math.log(Tn)
+        sharded.broadcast_tensor(T, 0)
+        leg = 0 if aref[2, 5] else 1                         # an x step takes the first leg sharded, a y step the second
+        Tl = sharded.shard(T, leg)
+        arows = []
+        for i in range(2, 6):
+            use_x = bool(aref[i, 5])
+            Tl, Tn = (sharded.atrg2dx if use_x else sharded.atrg2dy)(Tl, 16)
+            logNorm = 2 * logNorm + math.log(Tn)
+            full = sharded.unshard(Tl, leg=1 if use_x else 0)
+            F = (g.logZ(full, "anti-periodic") + logNorm) / 2 ** (i + 1)
+            arows.append((abs(Tn - aref[i, 0]) / aref[i, 0], abs(F - complex(aref[i, 1], aref[i, 2])) / abs(F)))
+        q.put((rank, rows, dict(sharded.STATS), arows))
     finally:
         dist.destroy_process_group()
 
@@ -84,8 +103,10 @@ def test_sharded_trg_chain_world2_vs_reference():
         p.start()
     res = {}
     for _ in range(world):
-        rank, rows, stats = q.get(timeout=600)
+        rank, rows, stats, arows = q.get(timeout=900)
         res[rank] = (rows, stats)
+        for dT, dF in arows:
+            assert dT <= 1e-10 and dF <= 1e-10, (rank, "atrg", arows)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
