@@ -807,6 +807,7 @@ def _svd_core(mats, ks, cutoff, kind, speculative=False, resume=None):
         if _engine_mod.CAPTURING_STEP[0]:
             raise _engine_mod.NotCapturable("the full Jacobi SVD synchronises with the host")
         usv = batched_svd(mats)
+        usv = [_engine_mod.refine_null_band(m, r) for m, r in zip(mats, usv)]
         SVD_PATH_STATS["full"] += 1
     return usv, None
 

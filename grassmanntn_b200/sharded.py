@@ -237,6 +237,8 @@ class ShardedTruncPlan(E._TruncPlan):
         self.graphable = False                       # collectives between the launches: eager schedule
         torch.cuda.current_stream().synchronize() if dev.type == "cuda" else None
 
+    _allreduce = staticmethod(lambda t: all_reduce_(t))      # rank certificate: sums over the column blocks
+
     # ---- launch sequences --------------------------------------------------------------------------
     def _reduce_handles(self, handles):
         """all-reduce the (consecutive) workspace matrices `handles` in one collective"""
@@ -420,7 +422,7 @@ def truncated_svd_sharded(mats, ks, site=None):
             svals, res, kept_host = plan.read()
         except _cabi.GtnError:
             return None
-        ok, worst, reject = E._trunc_certificate(svals, res, kept_host, ks, L_)
+        ok, worst, reject = E._trunc_certificate(svals, res, kept_host, ks, L_, rank_check=plan.rank_certificate)
         E.truncated_svd_batch.last_iters = it
         if E.DEBUG_TRUNC and rank() == 0:
             print("[trunc sharded] it", it, "worst %.2e" % worst, "ok", ok, "reject", reject, flush=True)
@@ -474,9 +476,10 @@ def broadcast_tensor(T, src=0):
     return T
 
 
-def svd_many_sharded(objs, string, cutoff, site=None):
+def svd_many_sharded(objs, string, cutoff, site=None, gathered_fallback=True):
     """gtn.svd_many for tensors sharded along a COLUMN leg of the partition: U replicated, V sharded like the input.
-    Returns None when the truncated path does not apply (the caller gathers and runs the single-GPU decomposition)."""
+    When the column-sharded truncated path does not apply or fails its certificate, the sector matrices are gathered on
+    their owner ranks and decomposed there (_svd_gathered); with gathered_fallback=False None is returned instead."""
     import grassmanntn_b200 as gtn
     from . import _ops, _planner
     left, right = _planner.split_partition(string, "svd")
@@ -486,19 +489,79 @@ def svd_many_sharded(objs, string, cutoff, site=None):
     ks = _ops._sector_cuts(ctxs, cutoff, "block")
     w = world()
     full_min = [min(m.shape[0], m.shape[1] * w) for m in mats]
-    if not all(k >= 1 and 3 * k // 2 + 8 <= E.TRUNC_LMAX and 4 * min(E.subspace_rows(k), E.TRUNC_LMAX) <= fm
-               for k, fm in zip(ks, full_min)):
-        return None
-    usv = truncated_svd_sharded(mats, ks, site=site)
+    usv = None
+    if all(k >= 1 and 3 * k // 2 + 8 <= E.TRUNC_LMAX and 4 * min(E.subspace_rows(k), E.TRUNC_LMAX) <= fm
+           for k, fm in zip(ks, full_min)):
+        usv = truncated_svd_sharded(mats, ks, site=site)
+        if usv is not None:
+            _ops.SVD_PATH_STATS["truncated"] += 1
     if usv is None:
-        return None
-    _ops.SVD_PATH_STATS["truncated"] += 1
+        if not gathered_fallback:
+            return None
+        STATS["gathered_svds"] = STATS.get("gathered_svds", 0) + 1
+        usv = _svd_gathered(mats, ks, cutoff, site=site)
     outs, k = [], 0
     for c, o in zip(ctxs, objs):
         n = len(c["mats"])
         U, S, V, _ = _ops._decompose_finish(c, usv[k:k + n], cutoff, "svd", "block")
         outs.append(tuple(gtn.block._from_bt(x) for x in (U, S, V)))
         k += n
+    return outs
+
+
+def _svd_gathered(mats, ks, cutoff, site=None):
+    """Fallback for sector matrices whose column-sharded subspace iteration cannot be certified (flat spectrum at the
+    cut, numerically rank-deficient sectors, matrices too small for the truncated path): the column blocks of problem
+    b are gathered on rank b % W, which runs the single-GPU decomposition (_ops._svd_core: truncated SVD with
+    certificate, else the full Jacobi SVD), and the first k triplets are broadcast.  Different problems are solved
+    concurrently by different owners.  Returns [(U (p x k), s (host), Vh (k x q_r, local columns))]."""
+    from . import _ops
+    w, r = world(), rank()
+    dev, dt = mats[0].device, mats[0].dtype
+    full = {}
+    for b, m in enumerate(mats):                                  # column blocks to the owners
+        p, q = m.shape
+        owner = b % w
+        mc = m.contiguous()
+        if w == 1:
+            full[b] = mc
+            continue
+        parts = [torch.empty(p, q, dtype=dt, device=dev) for _ in range(w)] if r == owner else None
+        with E.prof_region("nccl_gather", 0, _nbytes(mc) * w):
+            dist.gather(_real(mc), [_real(t) for t in parts] if parts is not None else None, dst=owner)
+        STATS["allgather_bytes"] += _nbytes(mc) * w
+        STATS["collectives"] += 1
+        if r == owner:
+            full[b] = torch.cat(parts, dim=1)                     # columns ordered [rank][local column]
+            del parts
+    mine = sorted(full)
+    res = {}
+    if mine:
+        E.SVD_SITE[0] = (site, "gathered")
+        usv, _ = _ops._svd_core([full[b] for b in mine], [ks[b] for b in mine], cutoff, "svd")
+        for j, b in enumerate(mine):
+            U, sv, Vh = usv[j]
+            kk = min(ks[b], mats[b].shape[0], mats[b].shape[1] * w)
+            res[b] = (U[:, :kk].contiguous(), np.asarray(sv[:kk], dtype=np.float64), Vh[:kk, :].contiguous())
+    del full
+    outs = []
+    for b, m in enumerate(mats):                                  # first k triplets from the owners
+        p, q = m.shape
+        kk = min(ks[b], p, q * w)
+        if w == 1:
+            outs.append(res[b])
+            continue
+        owner = b % w
+        if r == owner:
+            U, sv, Vh = res[b]
+            sd = torch.from_numpy(sv).to(dev)
+        else:
+            U = torch.empty(p, kk, dtype=dt, device=dev)
+            Vh = torch.empty(kk, q * w, dtype=dt, device=dev)
+            sd = torch.empty(kk, dtype=torch.float64, device=dev)
+        for t in (U, Vh, sd):
+            _broadcast(t, owner)
+        outs.append((U, sd.cpu().numpy(), Vh.view(kk, w, q)[:, r, :].contiguous()))
     return outs
 
 

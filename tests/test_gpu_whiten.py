@@ -1,7 +1,8 @@
 """gtn_chol_whiten (pivoted Cholesky whitening of the l x l Gram matrices of the subspace iteration) in its three
 variants -- register tiles (n <= 80), packed lower triangle in shared memory (80 < n <= 128, chi = 128 runs), global
 scratch (n > 128) -- against numpy: T G T^H = I on the detected rank, zero rows beyond it, rank detection on a
-rank-deficient matrix, split-K partial sums, complex128 and float64.  Tolerance 1e-9 relative to cond(G) ~ 1e6 inputs."""
+rank-deficient matrix, split-K partial sums, complex128 and float64.  Tolerance eps * cond(G) (numpy's own Cholesky
+whitening of the same matrices lands within a factor 50 below that), floor 1e-9."""
 import ctypes as C
 
 import numpy as np
@@ -70,5 +71,9 @@ def test_chol_whiten_variants(gtn, n, cplx):
         for T, Gm, r in zip(Ts, (G, G2), kept):
             assert r == rank, (n, rank, nsplit, r)
             W = T @ Gm @ T.conj().T
-            assert np.abs(W[:r, :r] - np.eye(r)).max() <= 1e-9, (n, rank, nsplit, np.abs(W[:r, :r] - np.eye(r)).max())
-            assert np.abs(T[r:, :]).max() == 0.0
+            lam = np.linalg.eigvalsh(Gm)[::-1]
+            tol = max(1e-9, 2.3e-16 * lam[0] / lam[r - 1])     # a Cholesky whitening is good to eps * cond(G)
+            err = np.abs(W[:r, :r] - np.eye(r)).max()
+            assert err <= tol, (n, rank, nsplit, err, tol)
+            if r < n:
+                assert np.abs(T[r:, :]).max() == 0.0

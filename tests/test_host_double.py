@@ -235,3 +235,28 @@ def test_perturbed_z2_chain_truncated_vs_reference(gtn_host_trunc):
         assert abs(F - complex(ref[i, 1], ref[i, 2])) <= 1e-10 * abs(F), (i, F)
     from grassmanntn_b200 import _ops
     assert _ops.SVD_PATH_STATS["truncated"] >= 8
+
+
+def test_rank_deficient_sectors_chi64_rank_certificate(gtn_host_trunc):
+    """TRG at chi = 64 on the Z2 tensor, first two steps against the oracle port (make_chain_goldens.py chi64).  The
+    sector matrices of the second step (512 x 512) have exact rank 16 < k = 32: the number of values that pass the
+    reference's rank rule must not be read off the noisy Ritz values -- the truncated path has to certify it through
+    the deflated matrix (_engine.deflated_norm_bound) and come out with the reference's bond dimensions (32, 32)."""
+    import math
+    import os
+    from grassmanntn_b200 import _engine as E, _ops
+    gtn = gtn_host_trunc
+    ref = np.load(os.path.join(CH.G, "chains.npz"))["oracle_trg_chi64"]
+    g = gtn.gauge2d
+    T = g.zcap(g.load_initial_tensor().toblock())
+    before, calls = dict(_ops.SVD_PATH_STATS), dict(E.RANK_CHECK_STATS)
+    logNorm = 0.0
+    for i in range(2):
+        T, Tn = g.trg(T, 64)
+        logNorm = 2 * logNorm + math.log(Tn)
+        F = (g.logZ(T, CH.BC) + logNorm) / 2 ** (i + 1)
+        assert tuple(T.effective_shape[:2]) == (int(ref[i, 3]), int(ref[i, 4])), (i, T.effective_shape)
+        assert abs(Tn - ref[i, 0]) <= 1e-10 * ref[i, 0], (i, Tn, ref[i, 0])
+        assert abs(F - complex(ref[i, 1], ref[i, 2])) <= 1e-10 * abs(F), (i, F)
+    assert _ops.SVD_PATH_STATS["truncated"] > before["truncated"]
+    assert E.RANK_CHECK_STATS["certified"] > calls["certified"]
