@@ -42,6 +42,15 @@ class SvdOut(C.Structure):
     _fields_ = [("s_off", C.c_int64), ("u_off", C.c_int64)]
 
 
+class SvdInfo(C.Structure):
+    _fields_ = [("start_iters", C.c_int32), ("iters", C.c_int32), ("checks", C.c_int32), ("sweeps", C.c_int32),
+                ("launches", C.c_int32), ("reserved", C.c_int32), ("worst", C.c_double), ("rate", C.c_double)]
+
+
+GTN_OP_SECTOR_SVD_TRUNC, GTN_OP_SECTOR_EIGH_TRUNC = 0, 1
+GTN_ERR_NOT_CONVERGED = -3
+
+
 class GtnError(RuntimeError):
     pass
 
@@ -77,6 +86,9 @@ def _load():
         "gtn_pow_rcond": (i32, [vp, i64, i32, dbl, dbl, vp]),
         "gtn_scale": (i32, [vp, i64, i32, dbl, dbl, vp]),
         "gtn_odd_checker": (i32, [vp, i64, i64, i32, vp, vp]),
+        "gtn_workspace_bytes": (i64, [i32, i32, i32, vp, vp, vp]),
+        "gtn_sector_svd_trunc": (i32, [vp, vp, vp, i32, i32, vp, dbl, vp, vp, vp, vp, vp, i64, vp, vp]),
+        "gtn_sector_eigh_trunc": (i32, [vp, vp, vp, i32, i32, vp, dbl, vp, vp, vp, vp, vp, vp, i64, vp, vp]),
         "gtn_version": (i32, []),
         "gtn_build_arch": (C.c_char_p, []),
     }

@@ -851,7 +851,7 @@ def batched_svd(mats):
     odev = _to_dev_bytes(bytes(oarr))
     st = _stream()
     rn2 = torch.empty(max(soff, 1), dtype=torch.float64, device=dev)
-    fro2 = torch.empty(nprob, dtype=torch.float64, device=dev)
+    fro2 = torch.empty(2 * nprob, dtype=torch.float64, device=dev)      # double buffered by round parity
     rn_off = torch.tensor([pr[4] for pr in probs], dtype=torch.int64).to(dev, non_blocking=True)
     check(lib.gtn_jacobi_init(_ptr(W), _ptr(Z), code, _ptr(pdev), nprob, maxp, _ptr(rn2), _ptr(fro2), _ptr(rn_off),
                               st), "gtn_jacobi_init")
@@ -917,10 +917,29 @@ def batched_svd(mats):
 batched_svd.last_sweeps = 0
 
 
+def orthonormal_rows_jacobi(mats):
+    """Orthonormal rows spanning the row spaces of `mats` (p x q, p <= q) from their one-sided Jacobi SVDs: the rows of
+    Vh.  Rows whose singular value is at or below 1e-14 s_0 come out of the kernel as normalised rounding noise that
+    was never orthogonalised against the others (dead rows are not rotated): they are set to zero -- like the
+    rows beyond the detected rank in the Cholesky whitening -- so that the result is orthonormal on its support."""
+    outs = []
+    for (U, sv, Vh) in batched_svd(mats):
+        n_good = int(np.sum(sv > 1e-14 * sv[0])) if len(sv) and sv[0] > 0 else 0
+        Vh = Vh.contiguous()
+        if n_good < Vh.shape[0]:
+            Vh[n_good:].zero_()
+        outs.append(Vh)
+    return outs
+
+
 # ------------------------------------------------------------------------------------------------
 #  truncated SVD: randomized subspace iteration (GEMM-bound) + small Jacobi + residual certificate
 # ------------------------------------------------------------------------------------------------
 TRUNC_TOL = 1e-11          # certificate: max_i ||W^H u_i - s_i v_i|| <= TRUNC_TOL * s_0
+# singular values at or below RANK_NOISE * s_0 are within 10x of the null-space noise of the Jacobi kernel and of the
+# projected matrix (measured up to 1.2e-14 s_0): whether they pass the reference's rank rule s_i / s_0 > 1e-14 is decided
+# by the rank certificate (deflated_norm_bound), not by their computed values
+RANK_NOISE = 1e-13
 TRUNC_MAX_ITERS = 20
 TRUNC_LMAX = 320           # widest subspace (rows of the projected matrix); gtn_chol_whiten handles <= 512
 _rand_cache = {}
@@ -1015,7 +1034,7 @@ RANK_CHECK_STATS = {"calls": 0, "certified": 0}
 
 def refine_null_band(M, usv):
     """Full-SVD results (batched_svd) whose smallest values that pass the reference's rank rule lie inside the noise
-    band (1e-14, 1e-11] s_0 of the Jacobi kernel: when the deflated matrix certifies that nothing beyond the values
+    band (1e-14, 1e-13] s_0 of the Jacobi kernel: when the deflated matrix certifies that nothing beyond the values
     above the band can pass the rule (deflated_norm_bound), the values in the band are lowered to that bound -- the
     rank then equals LAPACK's on the same matrix.  Not conclusive: the result is left as the kernel delivered it."""
     U, sv, Vh = usv
@@ -1023,9 +1042,9 @@ def refine_null_band(M, usv):
         return usv
     s0 = float(sv[0])
     nnz = int(np.sum(sv / (s0 + 1e-14) > 1e-14))
-    if nnz == 0 or sv[nnz - 1] > TRUNC_TOL * s0:
+    if nnz == 0 or sv[nnz - 1] > RANK_NOISE * s0:
         return usv
-    nD = int(np.sum(sv > TRUNC_TOL * s0))
+    nD = int(np.sum(sv > RANK_NOISE * s0))
     thr = 1e-14 * (s0 + 1e-14)
     RANK_CHECK_STATS["calls"] += 1
     Mc = M.contiguous()
@@ -1121,6 +1140,8 @@ def subspace_rows(k):
 
 _trunc_fail = {}
 _trunc_rate = {}
+_trunc_robust = {}         # (batch shape, call site) -> True: the Gram-whitened iteration dropped directions here
+ROBUST_MIN_DIM = 1024      # sectors at least this large retry with Jacobi orthonormalisation before the full SVD
 SVD_SITE = [None]          # call site of the decomposition being run (set by _ops.decompose_many)
 FORCE_VERIFY_FAIL = [None]  # test hook: callable(SpeculativeSVD) -> True makes verify() report a failed certificate
 CAPTURING_STEP = [False]   # a caller is capturing a whole coarse-graining step: enqueue the steady-state schedule inline
@@ -1180,7 +1201,7 @@ class _TruncPlan:
         self.vh_delta = ws.off(self.hVk[0]) - ws.off(self.hB[0])
         assert all(ws.off(v) - ws.off(h) == self.vh_delta for v, h in zip(self.hVk, self.hB))
         self.rn2 = torch.empty(sumL, dtype=torch.float64, device=dev)
-        self.fro2 = torch.empty(nb, dtype=torch.float64, device=dev)
+        self.fro2 = torch.empty(2 * nb, dtype=torch.float64, device=dev)
         self.rn_off = i64(self.soff)
         self.offd = torch.zeros(2 * nb, dtype=torch.float64, device=dev)
         self.sw = torch.zeros(4, dtype=torch.int32, device=dev)
@@ -1260,9 +1281,15 @@ class _TruncPlan:
     def orth(self, src, dst, side, passes, robust=False):
         ws = self.ws
         if robust:
-            res = batched_svd([ws.view(h) for h in src])
+            # orthonormal rows from the one-sided Jacobi SVD of the panels themselves: no Gram matrix, so directions
+            # down to eps * s_0 survive (a Gram matrix resolves sqrt(1e-13) = 3e-7 s_0).  Second pass: rows that died
+            # below the kernel's 2e-15 threshold in the first pass come out of it as unit noise vectors and are
+            # orthogonalised like any other row in the second.
+            mats_ = [ws.view(h) for h in src]
+            for _ in range(passes):
+                mats_ = orthonormal_rows_jacobi(mats_)
             for b in range(self.nb):
-                ws.view(dst[b]).copy_(res[b][2])
+                ws.view(dst[b]).copy_(mats_[b])
             return
         hC = self.hCp if side == "p" else self.hCq
         hS = self.hSp if side == "p" else self.hSq
@@ -1478,14 +1505,20 @@ def _trunc_certificate(svals, res, kept_host, ks, L_, rank_check=None):
         # (b) fewer triplets than requested AND the Gram whitening could not resolve every direction: a
         #     small-but-valid singular direction may have been dropped.
         # Both are settled by the norm of the deflated matrix; without that certificate the full SVD decides.
-        band = kk > 0 and s[kk - 1] <= TRUNC_TOL * s0
+        band = kk > 0 and s[kk - 1] <= RANK_NOISE * s0
         dropped = nnz < ks[b] and kept_host is not None and kept_host[b] < L_[b] and nnz >= kept_host[b]
         if band or dropped:
-            nD = int(np.sum(s > TRUNC_TOL * s0))
+            nD = int(np.sum(s > RANK_NOISE * s0))
             thr = 1e-14 * (abs(s0) + 1e-14)
             if rank_check is None or nD == 0 or nD >= len(s):
+                if DEBUG_TRUNC:
+                    print("[trunc] sector", b, "rank undecidable here: band", band, "dropped", dropped, "nD", nD, flush=True)
                 return False, worst, True
             bound = rank_check(b, nD, thr)
+            if DEBUG_TRUNC:
+                print("[trunc] sector", b, "rank certificate: band", band, "dropped", dropped, "nD", nD, "of k", ks[b],
+                      "bound/s0 %.2e" % (bound / max(s0, 1e-300)), "s[nD-1:nD+3]/s0",
+                      np.array2string(s[max(nD - 1, 0): nD + 3] / max(s0, 1e-300), precision=2), flush=True)
             if not bound <= thr:
                 return False, worst, True
             s[nD:] = np.minimum(s[nD:], bound)
@@ -1607,6 +1640,63 @@ class SpeculativeSVD:
         return self.ok
 
 
+ONE_CALL = bool(int(__import__("os").environ.get("GTN_ONE_CALL", "1")))
+ONE_CALL_STATS = {"calls": 0, "accepted": 0}
+
+
+def _onecall_arrays(P_, Q_, ks):
+    nb = len(P_)
+    return (C.c_int64 * nb)(*P_), (C.c_int64 * nb)(*Q_), (C.c_int32 * nb)(*ks)
+
+
+def _onecall_bytes(P_, Q_, ks, dt):
+    m_, n_, k_ = _onecall_arrays(P_, Q_, ks)
+    return int(lib.gtn_workspace_bytes(_cabi.GTN_OP_SECTOR_SVD_TRUNC, dtype_code(dt), len(P_), m_, n_, k_))
+
+
+def _truncated_onecall(mats, ks, key, P_, Q_):
+    """truncated_svd_batch through the one-call C ABI (include/gtn_b200.h: gtn_sector_svd_trunc): subspace iteration,
+    certificate checks and rank certificate run inside the library; returns the same [(U, s, Vh)] or None."""
+    dev, dt = mats[0].device, mats[0].dtype
+    nb, code = len(mats), dtype_code(dt)
+    m_, n_, k_ = _onecall_arrays(P_, Q_, ks)
+    nbytes = int(lib.gtn_workspace_bytes(_cabi.GTN_OP_SECTOR_SVD_TRUNC, code, nb, m_, n_, k_))
+    if nbytes <= 0:
+        raise _cabi.GtnError("gtn_workspace_bytes failed with status %d" % nbytes)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    src = [m.contiguous() for m in mats]
+    U = [torch.empty(p, k, dtype=dt, device=dev) for p, k in zip(P_, ks)]
+    Vh = [torch.empty(k, q, dtype=dt, device=dev) for q, k in zip(Q_, ks)]
+    ptrs = lambda ts: (C.c_void_p * nb)(*[t.data_ptr() for t in ts])
+    S = (C.c_double * sum(ks))()
+    rank = (C.c_int32 * nb)()
+    info = _cabi.SvdInfo()
+    info.start_iters = int(_trunc_iters_hint.get(key) or 0)
+    info.rate = float(_trunc_rate.get(key, 0.0))
+    ONE_CALL_STATS["calls"] += 1
+    rc = lib.gtn_sector_svd_trunc(ptrs(src), m_, n_, nb, code, k_, 1e-14, ptrs(U), S, ptrs(Vh), rank, _ptr(ws), nbytes,
+                                  C.byref(info), _stream())
+    count(int(info.launches))
+    truncated_svd_batch.last_iters = int(info.iters)
+    batched_svd.last_sweeps = int(info.sweeps)
+    if DEBUG_TRUNC:
+        print("[trunc one-call] rc", rc, "iters", info.iters, "checks", info.checks, "worst %.2e" % info.worst,
+              "start", info.start_iters, "launches", info.launches, flush=True)
+    if rc == _cabi.GTN_ERR_NOT_CONVERGED:
+        return None
+    check(rc, "gtn_sector_svd_trunc")
+    ONE_CALL_STATS["accepted"] += 1
+    if info.rate > 0:
+        _trunc_rate[key] = float(info.rate)
+    _trunc_accept(key, int(info.iters), float(info.worst), spare=1, clean=(info.checks == 1))
+    out, o = [], 0
+    sv = np.frombuffer(S, dtype=np.float64).copy()
+    for b in range(nb):
+        out.append((U[b], sv[o: o + ks[b]], Vh[b]))
+        o += ks[b]
+    return out
+
+
 def truncated_svd_batch(mats, ks, robust=False, speculative=False, resume=None):
     """Top-k_b singular triplets of every matrix in `mats` by randomized subspace iteration:
          Yh = G Wh ; Qh = orth_rows(Yh) ; [Zh = Qh W ; Ph = orth_rows(Zh) ; Yh = Ph Wh ; Qh = orth_rows(Yh)]*
@@ -1631,6 +1721,16 @@ def truncated_svd_batch(mats, ks, robust=False, speculative=False, resume=None):
     L_ = [min(p, q, subspace_rows(k), TRUNC_LMAX) for p, q, k in zip(P_, Q_, ks)]
     pkey = (tuple(P_), tuple(Q_), tuple(ks), str(dt), str(dev))
     key = (pkey, SVD_SITE[0])               # iteration hints / failure memory are per call site
+    if robust:
+        key = key + ("robust",)
+    elif _trunc_robust.get(key) and not speculative and resume is None and not CAPTURING_STEP[0]:
+        # this site's spectrum spans more than the Gram whitening resolves: straight to the Jacobi-orthonormalised run
+        return truncated_svd_batch(mats, ks, robust=True)
+    if (ONE_CALL and not robust and resume is None and not CAPTURING_STEP[0] and not PROF.enabled
+            and _onecall_bytes(P_, Q_, ks, dt) > TRUNC_PLAN_CACHE_BYTES):
+        # large sectors (chi >= 128: no cached workspace, no recorded graph): the whole driver loop runs behind
+        # ONE C-ABI call (gtn_sector_svd_trunc, csrc/gtn_sector.cu); this host only keeps the iteration memory
+        return _truncated_onecall(mats, ks, key, P_, Q_)
     fails = _trunc_fail.get(key, 0)
     if fails >= 2 and not robust:
         # this shape keeps failing the certificate (flat spectrum): go straight to the full SVD, but
@@ -1656,7 +1756,7 @@ def truncated_svd_batch(mats, ks, robust=False, speculative=False, resume=None):
     hint = _trunc_iters_hint.get(key)
     # steady state: as many iterations as the last accepted run needed, one fewer when that run passed
     # with a margin of one iteration's convergence factor (a failed check costs ~4 iterations' worth).
-    start_it = (hint or 0) if not robust else 0
+    start_it = hint or 0
     replayed = False
     if CAPTURING_STEP[0]:
         # the caller records its whole step as ONE CUDA graph: the schedule 'start, n iterations, check' is enqueued

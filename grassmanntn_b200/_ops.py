@@ -802,6 +802,17 @@ def _svd_core(mats, ks, cutoff, kind, speculative=False, resume=None):
             if isinstance(usv, _engine_mod.SpeculativeSVD):
                 SVD_PATH_STATS["truncated"] += 1
                 return usv.outs, usv
+            if usv is None and not _engine_mod.CAPTURING_STEP[0] \
+                    and min(min(m.shape) for m in mats) >= _engine_mod.ROBUST_MIN_DIM:
+                # the spectrum inside the cut spans more than a Gram matrix resolves (s_k < 3e-7 s_0: the whitening
+                # dropped directions) or the iteration stalled: before paying for the full SVD of a large sector,
+                # repeat the iteration with its panels orthonormalised by the Jacobi kernels
+                usv = truncated_svd_batch(mats, ks, robust=True)
+                if usv is not None:
+                    SVD_PATH_STATS["truncated_robust"] = SVD_PATH_STATS.get("truncated_robust", 0) + 1
+                    pk = (tuple(m.shape[0] for m in mats), tuple(m.shape[1] for m in mats), tuple(ks),
+                          str(mats[0].dtype), str(mats[0].device))
+                    _engine_mod._trunc_robust[(pk, _engine_mod.SVD_SITE[0])] = True
             SVD_PATH_STATS["truncated" if usv is not None else "truncated_rejected"] += 1
     if usv is None:
         if _engine_mod.CAPTURING_STEP[0]:

@@ -102,11 +102,20 @@ __device__ __forceinline__ void jacobi_pair_step(typename Elem<CPLX>::T* __restr
                                                  const gtn_svd_problem* __restrict__ probs, int prob, int k,
                                                  int round, double tol, double* __restrict__ offdiag,
                                                  double* __restrict__ rn2, const double* __restrict__ fro2,
-                                                 const int64_t* __restrict__ rn_off) {
+                                                 const int64_t* __restrict__ rn_off, int nprob) {
   using T = typename Elem<CPLX>::T;
   const gtn_svd_problem pr = probs[prob];
   const int p = pr.p, q = pr.q;
   const int P = (p + 1) & ~1;
+  // The running maximum of the squared row norms (dead-row threshold below) is double buffered by round parity:
+  // a round READS the value completed by the previous round and accumulates its own maximum into the other buffer,
+  // so what a CTA sees never depends on how far its neighbours of the same round have got -- rotation decisions,
+  // and with them every bit of the result, are reproducible from run to run and from GPU to GPU.  (Round 0 of a
+  // sweep reads the buffer that is one sweep old: a lower bound of the maximum, which only delays declaring a row
+  // dead.)  The carry is done before any early exit.
+  const double* fro_rd = fro2 + (round & 1) * nprob;
+  double* fro_wr = const_cast<double*>(fro2) + ((round + 1) & 1) * nprob;
+  if (k == 0 && threadIdx.x == 0) atomic_max_pos(fro_wr + prob, fro_rd[prob]);
   if (P < 2 || round >= P - 1) return;
     if (k >= P / 2) return;
   int i, j;
@@ -123,7 +132,7 @@ __device__ __forceinline__ void jacobi_pair_step(typename Elem<CPLX>::T* __restr
   double* rn = rn2 + rn_off[prob];
   {
     const double as = rn[i], bs = rn[j];
-    const double dead = 4e-30 * fro2[prob];      // fro2[] holds max_i |row_i|^2 (monotone)
+    const double dead = 4e-30 * fro_rd[prob];    // max_i |row_i|^2 as of the end of the previous round (monotone)
     if (fmin(as, bs) <= dead) return;
   }
 
@@ -165,7 +174,7 @@ __device__ __forceinline__ void jacobi_pair_step(typename Elem<CPLX>::T* __restr
     }
   }
   __shared__ double red[4][JT / 32];
-  __shared__ double rotp[5];
+  __shared__ double rotp[6];
   a = warp_sum(a); b = warp_sum(b); cr = warp_sum(cr);
   if (CPLX) ci = warp_sum(ci);
   if ((tid & 31) == 0) {
@@ -176,19 +185,27 @@ __device__ __forceinline__ void jacobi_pair_step(typename Elem<CPLX>::T* __restr
     double A = 0, B = 0, CR = 0, CI = 0;
 #pragma unroll
     for (int w = 0; w < JT / 32; ++w) { A += red[0][w]; B += red[1][w]; CR += red[2][w]; CI += red[3][w]; }
-    double cs = 1.0, sn = 0.0, phr = 1.0, phi = 0.0, act = 0.0, tc = 0.0, off2 = 0.0;
+    double cs = 1.0, sn = 0.0, phr = 1.0, phi = 0.0, act = 0.0, tc = 0.0, off2 = 0.0, exact = 0.0;
     rn[i] = A; rn[j] = B;
     if (jacobi_rotation(A, B, CR, CI, tol, cs, sn, phr, phi, tc, &off2)) {
       atomic_max_pos(offdiag + prob, off2);
       act = 1.0;
-      rn[i] = fmax(A - tc, 0.0); rn[j] = B + tc;
-      atomic_max_pos(const_cast<double*>(fro2) + prob, fmax(rn[i], rn[j]));
+      // the squared norms after the rotation by their update formula -- exact to eps * (A + B) only: when a row
+      // collapses by more than ~1e-3 in one rotation (nearly parallel rows: every rank-deficient or steeply decaying
+      // sector), its new norm is recomputed from the rotated elements below, otherwise a row that still carries
+      // directions at 1e-8 ... 1e-15 s_0 could be stored as 0, pass the dead-row test and never be rotated again
+      const double ni = fmax(A - tc, 0.0), nj = fmax(B + tc, 0.0);
+      rn[i] = ni; rn[j] = nj;
+      if (ni < 1e-6 * (A + B) || nj < 1e-6 * (A + B)) exact = 1.0;
+      atomic_max_pos(fro_wr + prob, fmax(ni, nj));
     }
-    rotp[0] = cs; rotp[1] = sn; rotp[2] = phr; rotp[3] = phi; rotp[4] = act;
+    rotp[0] = cs; rotp[1] = sn; rotp[2] = phr; rotp[3] = phi; rotp[4] = act; rotp[5] = exact;
   }
   __syncthreads();
   if (rotp[4] == 0.0) return;
   const double cs = rotp[0], sn = rotp[1], phr = rotp[2], phi = rotp[3];
+  const bool exact = rotp[5] != 0.0;
+  double na = 0.0, nb2 = 0.0;
   if (cached) {
 #pragma unroll
     for (int u = 0; u < CACHE; ++u) {
@@ -197,6 +214,11 @@ __device__ __forceinline__ void jacobi_pair_step(typename Elem<CPLX>::T* __restr
         rot(xc[u], yc[u], cs, sn, phr, phi);
         Elem<CPLX>::st(x + e, xc[u]);
         Elem<CPLX>::st(y + e, yc[u]);
+        if (exact) {
+          if constexpr (CPLX) {
+            na += xc[u].re * xc[u].re + xc[u].im * xc[u].im; nb2 += yc[u].re * yc[u].re + yc[u].im * yc[u].im;
+          } else { na += xc[u] * xc[u]; nb2 += yc[u] * yc[u]; }
+        }
       }
     }
   } else {
@@ -205,6 +227,21 @@ __device__ __forceinline__ void jacobi_pair_step(typename Elem<CPLX>::T* __restr
       rot(xv, yv, cs, sn, phr, phi);
       Elem<CPLX>::st(x + e, xv);
       Elem<CPLX>::st(y + e, yv);
+      if (exact) {
+        if constexpr (CPLX) { na += xv.re * xv.re + xv.im * xv.im; nb2 += yv.re * yv.re + yv.im * yv.im; }
+        else { na += xv * xv; nb2 += yv * yv; }
+      }
+    }
+  }
+  if (exact) {                          // (block-uniform: rotp[5] is shared)
+    na = warp_sum(na); nb2 = warp_sum(nb2);
+    if ((tid & 31) == 0) { red[0][tid >> 5] = na; red[1][tid >> 5] = nb2; }
+    __syncthreads();
+    if (tid == 0) {
+      double A2 = 0, B2 = 0;
+#pragma unroll
+      for (int w = 0; w < JT / 32; ++w) { A2 += red[0][w]; B2 += red[1][w]; }
+      rn[i] = A2; rn[j] = B2;
     }
   }
   T* zx = Zb + pr.z_off + int64_t(i) * p;
@@ -223,7 +260,7 @@ __global__ void __launch_bounds__(JT)
                         const gtn_svd_problem* __restrict__ probs, int round, double tol,
                         double* __restrict__ offdiag, double* __restrict__ rn2,
                         const double* __restrict__ fro2, const int64_t* __restrict__ rn_off) {
-  jacobi_pair_step<CPLX>(Wb, Zb, probs, blockIdx.y, blockIdx.x, round, tol, offdiag, rn2, fro2, rn_off);
+  jacobi_pair_step<CPLX>(Wb, Zb, probs, blockIdx.y, blockIdx.x, round, tol, offdiag, rn2, fro2, rn_off, gridDim.y);
 }
 
 // grid-wide barrier on a monotonically increasing counter (all CTAs are co-resident: cooperative
@@ -262,7 +299,7 @@ __global__ void __launch_bounds__(JT)
     double* off = offdiag2 + (sweep & 1) * nprob;
     double* off_next = offdiag2 + ((sweep + 1) & 1) * nprob;
     for (int round = 0; round < P - 1; ++round) {
-      jacobi_pair_step<CPLX>(Wb, Zb, probs, prob, k, round, tol, off, rn2, fro2, rn_off);
+      jacobi_pair_step<CPLX>(Wb, Zb, probs, prob, k, round, tol, off, rn2, fro2, rn_off, nprob);
       grid_barrier(bar, nblocks, epoch);
       if (round == 0 && k == 0 && threadIdx.x == 0) off_next[prob] = 0.0;
     }
@@ -400,7 +437,7 @@ extern "C" int gtn_jacobi_init(const void* W, void* Z, int dtype, const gtn_svd_
   if (nprob <= 0 || max_p <= 0) return GTN_OK;
   dim3 grid(max_p, nprob), block(128);
   cudaStream_t s = (cudaStream_t)stream;
-  cudaMemsetAsync(fro2_dev, 0, sizeof(double) * nprob, s);
+  cudaMemsetAsync(fro2_dev, 0, sizeof(double) * 2 * nprob, s);      // two buffers (round parity), see jacobi_pair_step
   if (dtype == GTN_C128)
     jacobi_init_kernel<true><<<grid, block, 0, s>>>((const c128*)W, (c128*)Z, probs_dev, rownorm2_dev, fro2_dev, rn_off_dev);
   else if (dtype == GTN_F64)

@@ -225,7 +225,7 @@ class ShardedTruncPlan(E._TruncPlan):
             i64 = lambda v: torch.tensor(list(v), dtype=torch.int64).to(dev)
             self.jrn_off = i64(self.jsoff)
             self.jrn2 = torch.empty(soff, dtype=torch.float64, device=dev)
-            self.jfro2 = torch.empty(nm, dtype=torch.float64, device=dev)
+            self.jfro2 = torch.empty(2 * nm, dtype=torch.float64, device=dev)
             self.joffd = torch.zeros(2 * nm, dtype=torch.float64, device=dev)
             self.jsw = torch.zeros(4, dtype=torch.int32, device=dev)
             self.js = torch.empty(soff, dtype=torch.float64, device=dev)
@@ -260,9 +260,46 @@ class ShardedTruncPlan(E._TruncPlan):
         self._reduce_handles(self.hYh)
         self.orth(self.hYh, self.hQh, "p", 2 if last else 1, robust)
 
+    def _orth_robust(self, src, dst, side, passes):
+        """orthonormal rows from the one-sided Jacobi SVD of the panels (no Gram matrix: full dynamic range).  The
+        replicated l x p panels are decomposed by their owner ranks (problem b on rank b % W); the column-sharded
+        l x q_r panels are first all-gathered (l x q numbers: isometry-sized).  The result is broadcast, every rank
+        keeps its columns -- one owner, not replicas, because the rotation order of the kernel is timing dependent."""
+        ws, w, r = self.ws, self.w, rank()
+        dt, dev = self.dt, self.dev
+        full, shapes = {}, []
+        for b in range(self.nb):
+            loc = ws.view(src[b])
+            l, n = loc.shape
+            shapes.append((l, n))
+            owner = b % w
+            if side == "q" and w > 1:
+                g_ = torch.empty(w * l * n, dtype=dt, device=dev)
+                _all_gather(g_, loc.reshape(-1))
+                if r == owner:
+                    full[b] = g_.view(w, l, n).permute(1, 0, 2).reshape(l, w * n).contiguous()
+                del g_
+            elif r == owner:
+                full[b] = loc
+        outs = {}
+        if full:
+            order = sorted(full)
+            mats_ = [full[b] for b in order]
+            for _ in range(passes):
+                mats_ = E.orthonormal_rows_jacobi(mats_)
+            outs = dict(zip(order, mats_))
+        for b in range(self.nb):
+            l, n = shapes[b]
+            owner = b % w
+            ncols = n * w if (side == "q" and w > 1) else n
+            out = outs[b].contiguous() if r == owner else torch.empty(l, ncols, dtype=dt, device=dev)
+            if w > 1:
+                _broadcast(out, owner)
+            ws.view(dst[b]).copy_(out.view(l, w, n)[:, r, :] if (side == "q" and w > 1) else out)
+
     def orth(self, src, dst, side, passes, robust=False):
         if robust:
-            raise E.NotCapturable("robust orthonormalisation is not available on sharded sector matrices")
+            return self._orth_robust(src, dst, side, passes)
         ws = self.ws
         hC = self.hCp if side == "p" else self.hCq
         hS = self.hSp if side == "p" else self.hSq
@@ -390,10 +427,12 @@ class ShardedTruncPlan(E._TruncPlan):
 _plans = {}
 
 
-def truncated_svd_sharded(mats, ks, site=None):
+def truncated_svd_sharded(mats, ks, site=None, robust=False):
     """Top-k_b triplets of column-sharded matrices: mats[b] = W_b[:, C_r] on rank r (same shapes on every rank).
     Returns [(U (p x l, replicated), s (host), Vh (l x q_r, local columns))] or None when the certificate cannot be
-    met (flat spectrum at the cut) -- the caller then leaves the sharded path for that decomposition."""
+    met (flat spectrum at the cut) -- the caller then leaves the sharded path for that decomposition.
+    robust=True: panels orthonormalised by the Jacobi kernels instead of the Gram whitening (spectra that span more
+    than 3e-7 inside the cut); tried automatically when the plain run is rejected, and remembered per site."""
     dev, dt = mats[0].device, mats[0].dtype
     w = world()
     P_ = [m.shape[0] for m in mats]
@@ -401,6 +440,19 @@ def truncated_svd_sharded(mats, ks, site=None):
     L_ = [min(p, q * w, E.subspace_rows(k), E.TRUNC_LMAX) for p, q, k in zip(P_, Q_, ks)]
     pkey = ("sharded", tuple(P_), tuple(Q_), tuple(ks), str(dt), str(dev), w)
     key = (pkey, site)
+    if not robust:
+        out = None if E._trunc_robust.get(key) else _truncated_svd_sharded(mats, ks, key, pkey, P_, Q_, L_, False)
+        if out is None:
+            out = _truncated_svd_sharded(mats, ks, key + ("robust",), pkey, P_, Q_, L_, True)
+            if out is not None:
+                E._trunc_robust[key] = True
+                STATS["robust_svds"] = STATS.get("robust_svds", 0) + 1
+        return out
+    return _truncated_svd_sharded(mats, ks, key + ("robust",), pkey, P_, Q_, L_, True)
+
+
+def _truncated_svd_sharded(mats, ks, key, pkey, P_, Q_, L_, robust):
+    dev, dt = mats[0].device, mats[0].dtype
     plan = _plans.get(pkey)
     if plan is None:
         if len(_plans) >= 4:
@@ -412,9 +464,9 @@ def truncated_svd_sharded(mats, ks, site=None):
     prev_worst, prev_it, next_check = None, None, 0
     for it in range(E.TRUNC_MAX_ITERS + 1):
         if it == 0:
-            plan.start(2 if start_it == 0 else 1)
+            plan.start(2 if start_it == 0 else 1, robust)
         else:
-            plan.iterate(it >= start_it and it >= next_check)
+            plan.iterate(it >= start_it and it >= next_check, robust)
         if it < start_it or it < next_check:
             continue
         plan.check_enqueue()
@@ -422,10 +474,12 @@ def truncated_svd_sharded(mats, ks, site=None):
             svals, res, kept_host = plan.read()
         except _cabi.GtnError:
             return None
+        if robust:
+            kept_host = None
         ok, worst, reject = E._trunc_certificate(svals, res, kept_host, ks, L_, rank_check=plan.rank_certificate)
         E.truncated_svd_batch.last_iters = it
         if E.DEBUG_TRUNC and rank() == 0:
-            print("[trunc sharded] it", it, "worst %.2e" % worst, "ok", ok, "reject", reject, flush=True)
+            print("[trunc sharded] it", it, "worst %.2e" % worst, "ok", ok, "reject", reject, "robust", robust, flush=True)
         if reject:
             return None
         if prev_worst is not None and prev_worst > 0 and worst > 0 and it > prev_it:

@@ -7,7 +7,8 @@
  * family of those call sites; the citation says which (file:line relative to the reference
  * repository root).  All pointers are DEVICE pointers unless the name ends in _host, all sizes
  * are element counts, every call takes the CUDA stream to launch on, returns 0 on success or a
- * negative gtn_status / positive cudaError_t, never throws and never allocates.
+ * negative gtn_status / positive cudaError_t, never throws and never allocates (the one workspace-taking call,
+ * gtn_sector_svd_trunc, has an explicit size query: gtn_workspace_bytes).
  *
  * Data types: GTN_F64 = IEEE double, GTN_C128 = interleaved (re, im) doubles (numpy complex128,
  * torch.complex128).
@@ -176,7 +177,8 @@ typedef struct {
 } gtn_svd_problem;
 
 /* rownorm2_dev: double[sum p_b] (problem b at rn_off_dev[b]) receives the squared row norms,
- * fro2_dev: double[nprob] the largest squared row norm seen so far (a lower bound of s_0^2); both
+ * fro2_dev: double[2 * nprob] the largest squared row norm seen so far (a lower bound of s_0^2), double buffered by
+ * round parity so that a round only reads what the previous round completed (bitwise reproducible results); both
  * are maintained by the sweeps and let a CTA skip a row pair without reading it when one of the
  * rows has decayed below 2e-15 * s_0 (rank-deficient sectors: such rows are discarded by the
  * reference's rank rule s_i/s_0 > 1e-14 anyway). */
@@ -244,6 +246,52 @@ int gtn_chol_whiten(const void* G, void* T, int dtype, const int64_t* g_off_dev,
 int gtn_gram_rotate(const void* G, void* T, int dtype, const int64_t* g_off_dev,
                     const int64_t* t_off_dev, const int32_t* n_dev, int nprob, int max_n, int nsplit,
                     double rel_thr, double tol, int max_sweeps, int32_t* sweeps_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * One-call truncated decomposition of a batch of parity-sector matrices.
+ *
+ * Replaces, per batch: np.linalg.svd (LAPACK gesdd) + the rank rule s_i / (s_0 + numer_cutoff) > numer_cutoff + the
+ * cut to the first k triplets in SortedSVD (__init__.py:3931-3951), BlockSVD (:3998-4003) and decompose_block
+ * (:5083-5088); gtn_sector_eigh_trunc adds SortedEig's signed eigenvalues (:4340-4341) for Hermitian sectors.
+ *
+ * M[b]: DEVICE pointer of the row-major m[b] x n[b] sector matrix (not modified); k[b] <= min(m[b], n[b]) triplets
+ * wanted.  Outputs: U_out[b] (m[b] x k[b], row-major), Vh_out[b] (k[b] x n[b]) on the device; S_host (sum_b k[b]
+ * doubles, problem b after problem b-1, descending) and rank_host[b] = number of those values that pass the rank rule
+ * on the HOST -- the call synchronises `stream` once per certificate check (the decision to stop iterating is the
+ * only host-dependent step).  M, U_out, Vh_out are HOST arrays of nb device pointers.
+ * The top-k triplets come from randomized subspace iteration on all matrices at once (grouped DMMA GEMMs, pivoted
+ * Cholesky whitening, one-sided Jacobi SVD of the l x n projected matrices) and are returned only with a certificate:
+ * residuals ||M^H u_i - s_i v_i|| <= 1e-11 s_0 for the kept triplets, no discarded Ritz value + residual above the
+ * smallest kept value, and -- for numerically rank-deficient sectors -- a norm bound of the deflated matrix
+ * M - U_D U_D^H M below numer_cutoff * s_0.  Returns GTN_OK, or GTN_ERR_NOT_CONVERGED when the certificate cannot be
+ * met (flat spectrum at the cut: the caller runs the full SVD, gtn_jacobi_*), or an error.
+ * Nothing is allocated: `workspace` (256-byte aligned device memory) must hold gtn_workspace_bytes(op, ...) bytes.
+ * info (may be NULL): in  start_iters = iterations to run before the first certificate check (the count the last
+ * accepted run of this shape needed; 0 = check right after the range finder), rate = convergence factor measured by
+ * an earlier call (0 = unknown); out  iters, checks, sweeps, worst (largest kept residual / s_0), rate.
+ * ------------------------------------------------------------------------------------------ */
+#define GTN_OP_SECTOR_SVD_TRUNC 0
+#define GTN_OP_SECTOR_EIGH_TRUNC 1
+typedef struct {
+  int32_t start_iters;
+  int32_t iters;
+  int32_t checks;
+  int32_t sweeps;
+  int32_t launches; /* out: kernels launched by the call */
+  int32_t reserved;
+  double worst;
+  double rate;
+} gtn_svd_info;
+int64_t gtn_workspace_bytes(int op, int dtype, int nb, const int64_t* m, const int64_t* n, const int32_t* k);
+int gtn_sector_svd_trunc(const void* const* M, const int64_t* m, const int64_t* n, int nb, int dtype,
+                         const int32_t* k, double numer_cutoff, void* const* U_out, double* S_host,
+                         void* const* Vh_out, int32_t* rank_host, void* workspace, int64_t workspace_bytes,
+                         gtn_svd_info* info, void* stream);
+/* lam_host: interleaved (re, im) doubles, sum_b k[b] entries: lam_c = sum_i s_i (Vh U)_ic. */
+int gtn_sector_eigh_trunc(const void* const* M, const int64_t* m, const int64_t* n, int nb, int dtype,
+                          const int32_t* k, double numer_cutoff, void* const* U_out, double* S_host,
+                          void* const* Vh_out, double* lam_host, int32_t* rank_host, void* workspace,
+                          int64_t workspace_bytes, gtn_svd_info* info, void* stream);
 
 /* Diagnostic: clock64 stamps of CTA 0 of the last gtn_chol_whiten ([0..3]: start, factorised,
  * inverted, stored) and gtn_gram_rotate ([4..7]: start, factorised, rotated, stored) launches.

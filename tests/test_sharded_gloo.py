@@ -73,6 +73,16 @@ def _worker(rank, world, port, q):
             frows.append((abs(Tn - ref[i, 0]) / ref[i, 0], abs(F - complex(ref[i, 1], ref[i, 2])) / abs(F)))
         sharded.truncated_svd_sharded = saved_trunc
         assert sharded.STATS.get("gathered_svds", 0) == 2
+        # ---- forced robust mode: panels orthonormalised by the owner's Jacobi SVD + broadcast instead of the Gram whitening
+        sharded.truncated_svd_sharded = lambda m_, k_, site=None: saved_trunc(m_, k_, site=site, robust=True)
+        Tf, lnf = Tl, logNorm
+        for i in range(2, 4):
+            Tf, Tn = sharded.trg(Tf, 16)
+            lnf = 2 * lnf + math.log(Tn)
+            F = (g.logZ(sharded.unshard(Tf), "anti-periodic") + lnf) / 2 ** (i + 1)
+            frows.append((abs(Tn - ref[i, 0]) / ref[i, 0], abs(F - complex(ref[i, 1], ref[i, 2])) / abs(F)))
+        sharded.truncated_svd_sharded = saved_trunc
+        assert sharded.STATS.get("gathered_svds", 0) == 2
         rows = []
         for i in range(2, 6):
             Tl, Tn = sharded.trg(Tl, 16)
