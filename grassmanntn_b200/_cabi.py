@@ -83,6 +83,7 @@ def _load():
         "gtn_rowsum": (i32, [vp, vp, i64, i64, i32, vp]),
         "gtn_dot": (i32, [vp, vp, i64, i32, vp, vp, i32, vp]),
         "gtn_row_sumsq": (i32, [vp, vp, i64, i64, i32, vp]),
+        "gtn_sum_slices": (i32, [vp, vp, i64, i32, i32, vp]),
         "gtn_pow_rcond": (i32, [vp, i64, i32, dbl, dbl, vp]),
         "gtn_scale": (i32, [vp, i64, i32, dbl, dbl, vp]),
         "gtn_odd_checker": (i32, [vp, i64, i64, i32, vp, vp]),

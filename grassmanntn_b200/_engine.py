@@ -705,6 +705,9 @@ GEMM_FAMILY = {0: "gemm_ldgsts_64x64", 1: "gemm_skinny_32x32", 3: "gemm_skinny_3
                12: "gemm_tma_128x64"}
 
 
+SPLIT_K = bool(int(__import__("os").environ.get("GTN_SPLIT_K", "1")))
+
+
 class GemmPlan:
     """Device-resident group list of one grouped GEMM launch and the tile configuration it runs in:
        12 / 4  TMA-staged 128x64 / 64x64 tiles (large products: every side >= 64, enough tiles to fill the GPU,
@@ -712,14 +715,18 @@ class GemmPlan:
        1       32x32 tiles with a deep K step (skinny products and Gram matrices of the subspace iteration);
        0       64x64 cp.async tiles (everything else: ragged block sectors, misaligned float64 views)."""
 
-    def __init__(self, groups, dtype, config=None):
+    def __init__(self, groups, dtype, config=None, splitk=True):
         self.n = len(groups)
         self.tiles = 0
         self.flops = 0
         self.bytes = 0
+        self.slices = 1
         if self.n == 0:
             return
         cplx = dtype == torch.complex128
+        if splitk and config is None and SPLIT_K:
+            groups = self._split_k(groups, dtype)
+            self.n = len(groups)
         for g in groups:
             b = g.get("batch", 1)
             self.flops += (8 if cplx else 2) * b * g["m"] * g["n"] * g["k"]
@@ -753,6 +760,45 @@ class GemmPlan:
         self.host = arr                      # the TMA path encodes its tensor maps from the host copy
         self.dev = _to_dev_bytes(bytes(arr))
 
+    def _split_k(self, groups, dtype):
+        """Gram-type launches -- a handful of output tiles over a very long contracted range (the environment matrices
+        of hotrg3dz: 64 x 64 outputs, K = 131072 per sector: 4 CTAs at work for a millisecond) -- are cut into
+        `slices` ranges of K that write consecutive copies of the output; gtn_sum_slices adds them in a fixed order.
+        Only for compact outputs (ldc = n, the groups tile one contiguous span) with beta = 0 and no batch."""
+        if any(g.get("beta", 0.0) != 0.0 or g.get("batch", 1) != 1 or g.get("flags", 0) or g["ldc"] != g["n"]
+               for g in groups):
+            return groups
+        tiles = sum(-(-g["m"] // 32) * -(-g["n"] // 32) for g in groups)
+        kmax = max(g["k"] for g in groups)
+        if tiles * 4 > 148 or kmax < 4096:
+            return groups
+        lo = min(g["c_off"] for g in groups)
+        span = sum(g["m"] * g["n"] for g in groups)
+        if max(g["c_off"] + g["m"] * g["n"] for g in groups) - lo != span:
+            return groups
+        if dtype != torch.complex128 and span % 2:
+            return groups
+        slices = int(min(64, max(2, 296 // tiles), kmax // 1024))
+        if slices < 2:
+            return groups
+        out = []
+        for s_ in range(slices):
+            for g in groups:
+                kc = -(-g["k"] // slices)
+                k0 = min(s_ * kc, g["k"])
+                kk = min(kc, g["k"] - k0)
+                h = dict(g)
+                h["a_off"], h["b_off"] = g["a_off"] + k0, g["b_off"] + k0 * g["ldb"]
+                h["c_off"] = s_ * span + (g["c_off"] - lo)
+                if kk <= 0:
+                    h["k"], h["alpha"] = 1, 0.0
+                    h["a_off"], h["b_off"] = g["a_off"], g["b_off"]
+                else:
+                    h["k"] = kk
+                out.append(h)
+        self.slices, self.span, self.c_lo = slices, span, lo
+        return out
+
     # measured on the B200 (scripts/gemm_bench.py, profiles/r2_gemm_bench.json): rate of a configuration on a large
     # problem without a partial last wave, relative to cuBLAS ZGEMM; CTAs resident per GPU; tile shape
     _CFG = {12: (0.975, 148, 128, 64), 4: (0.975, 296, 64, 64), 1: (0.91, 296, 32, 32), 0: (0.95, 296, 64, 64)}
@@ -783,6 +829,17 @@ class GemmPlan:
     def run(self, A, B, Cm):
         if self.n == 0 or self.tiles == 0:
             return
+        if self.slices > 1:
+            tmp = torch.empty(self.slices * self.span, dtype=Cm.dtype, device=Cm.device)
+            self._launch(A, B, tmp)
+            with prof_region("sum_slices", 1, (self.slices + 1) * self.span * tmp.element_size()):
+                dst = C.c_void_p(Cm.data_ptr() + self.c_lo * Cm.element_size())
+                check(lib.gtn_sum_slices(_ptr(tmp), dst, self.span, self.slices, dtype_code(Cm.dtype), _stream()),
+                      "gtn_sum_slices")
+            return
+        self._launch(A, B, Cm)
+
+    def _launch(self, A, B, Cm):
         with prof_region(self.family, 1, self.bytes, self.flops):
             if self.config & 4:
                 check(lib.gtn_grouped_gemm_tma(_ptr(A), _ptr(B), _ptr(Cm), dtype_code(A.dtype), self.host, _ptr(self.dev),
@@ -1247,7 +1304,11 @@ class _TruncPlan:
                                                 _ptr(self.n_dev), nb, self.maxL, rel_thr, _ptr(self.kept[slot]),
                                                 _ptr(self.evals), _ptr(self.e_off), _stream()), "gtn_small_eigh_whiten")
         else:
-            with prof_region("chol_whiten", 1):
+            # algorithmic model: pivoted Cholesky n^3/3 + inverse of the factor n^3/3 multiply-adds per matrix (8 real
+            # flops each for complex128, 2 for float64); the NS Gram slices read once, T written once
+            fl = (8 if self.dt == torch.complex128 else 2) * sum(2 * l ** 3 // 3 for l in self.L_)
+            by = ws.buf.element_size() * sum((self.NS + 1) * l * l for l in self.L_)
+            with prof_region("chol_whiten", 1, by, fl):
                 check(lib.gtn_chol_whiten(_ptr(ws.buf), _ptr(ws.buf), code, _ptr(self.g_off), _ptr(self.t_off),
                                           _ptr(self.n_dev), nb, self.maxL, self.NS, rel_thr, _ptr(self.kept[slot]),
                                           _ptr(self.chol_scratch) if self.chol_scratch is not None else None,
@@ -1333,7 +1394,10 @@ class _TruncPlan:
             else:
                 _ws_ctranspose(ws, list(zip(self.hB, self.hCq)))
                 self._gram(self.hB, self.hCq)
-            with prof_region("gram_rotate", 1):
+            # (Cholesky part only: n^3/3 multiply-adds; the shared-memory Jacobi sweeps on the factor are data dependent)
+            fl = (8 if dt == torch.complex128 else 2) * sum(l ** 3 // 3 for l in self.L_)
+            by = ws.buf.element_size() * sum((self.NS + 1) * l * l for l in self.L_)
+            with prof_region("gram_rotate", 1, by, fl):
                 check(lib.gtn_gram_rotate(Wp, Wp, code, _ptr(self.g_off), _ptr(self.t_off), _ptr(self.n_dev), nb,
                                           self.maxL, self.NS, 1e-15, ROTATE_TOL, 30, _ptr(self.rot_sweeps), st),
                       "gtn_gram_rotate")

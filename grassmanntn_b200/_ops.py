@@ -795,7 +795,9 @@ def _svd_core(mats, ks, cutoff, kind, speculative=False, resume=None):
     """returns (usv, pending): pending is an _engine.SpeculativeSVD when the truncated path was replayed
     without reading its certificate back (usv[b][1] is then a DEVICE vector of Ritz values)"""
     usv = None
-    if cutoff is not None and kind == "svd" and TRUNCATED_SVD:
+    if cutoff is not None and kind in ("svd", "eig") and TRUNCATED_SVD:
+        # (eig: the Hermitian sector's SVD U S Vh from the same truncated solver; the signed eigenvalues
+        # lam_k = sum_i s_i (Vh U)_ik are formed from its triplets in _decompose_finish, reference :4340-4341)
         from ._engine import TRUNC_LMAX as LM, subspace_rows
         if all(k >= 1 and 3 * k // 2 + 8 <= LM and 4 * min(subspace_rows(k), LM) <= min(m.shape) for k, m in zip(ks, mats)):
             usv = truncated_svd_batch(mats, ks, speculative=speculative, resume=resume)

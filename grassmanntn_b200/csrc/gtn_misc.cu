@@ -230,6 +230,35 @@ extern "C" int gtn_rowsum(const void* x, void* y, int64_t rows, int64_t cols, in
   return (int)cudaGetLastError();
 }
 
+// y[i] = alpha * sum_s x[s * n + i] (doubles; slices added in index order: deterministic) -- completes a split-K GEMM
+__global__ void __launch_bounds__(RT) sum_slices_kernel(const double* __restrict__ x, double* __restrict__ y,
+                                                        int64_t nd, int nslices) {
+  const int64_t stride = int64_t(gridDim.x) * RT;
+  const int64_t n2 = nd >> 1;
+  for (int64_t i = int64_t(blockIdx.x) * RT + threadIdx.x; i < n2; i += stride) {
+    double2 acc = __ldg(reinterpret_cast<const double2*>(x) + i);
+    for (int s = 1; s < nslices; ++s) {
+      const double2 v = __ldg(reinterpret_cast<const double2*>(x + int64_t(s) * nd) + i);
+      acc.x += v.x; acc.y += v.y;
+    }
+    reinterpret_cast<double2*>(y)[i] = acc;
+  }
+  if ((nd & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    double acc = x[nd - 1];
+    for (int s = 1; s < nslices; ++s) acc += x[int64_t(s) * nd + nd - 1];
+    y[nd - 1] = acc;
+  }
+}
+
+extern "C" int gtn_sum_slices(const void* x, void* y, int64_t n, int nslices, int dtype, void* stream) {
+  if (n <= 0 || nslices < 1) return GTN_OK;
+  if (dtype != GTN_C128 && dtype != GTN_F64) return GTN_ERR_BAD_ARG;
+  const int64_t nd = dtype == GTN_C128 ? 2 * n : n;
+  if ((nd & 1) && nslices > 1) return GTN_ERR_BAD_ARG;      // 16-byte loads: slices must start 16-byte aligned
+  sum_slices_kernel<<<grid_for(nd / 2 + 1), RT, 0, (cudaStream_t)stream>>>((const double*)x, (double*)y, nd, nslices);
+  return (int)cudaGetLastError();
+}
+
 extern "C" int gtn_row_sumsq(const void* x, double* y, int64_t rows, int64_t cols, int dtype, void* stream) {
   if (rows <= 0) return GTN_OK;
   if (rows > 2147483647LL) return GTN_ERR_BAD_ARG;

@@ -457,10 +457,11 @@ def hotrg3dz(T1, T2, dcut=64, intermediate_dcut=None, iternum=None, error_test=F
     X1, P1, Q1, Y1 = split3(T1)
     X2, P2, Q2, Y2 = (X1, P1, Q1, Y1) if same else split3(T2)
 
-    def isometry(A1, A2, first, chain, h1, g1, h2, g2):
-        AA = E(first, A1, A2)
-        for sub in chain:
-            AA = E(sub, AA)
+    def isometry(A1, A2, fused, h1, g1, h2, g2):
+        # the reference forms the outer product and then moves the legs by four single swaps (gauge2d.py:1964-1968,
+        # :2027-2031), each a full pass over the chi^2 D^4 tensor; Grassmann reorderings compose, so the product is
+        # written straight into the final leg order (same signs, bit for bit: one launch instead of five)
+        AA = E(fused, A1, A2)
         cA = AA.hconjugate(h1)
         Ma = E(g1, cA, AA)
         Ua, Sa, _ = Ma.eig('(I J)(i j)', dcut)
@@ -469,31 +470,23 @@ def hotrg3dz(T1, T2, dcut=64, intermediate_dcut=None, iternum=None, error_test=F
         Ub, Sb, _ = Mb.eig('(I J)(i j)', dcut)
         return AA, (Ua if Sa.shape[0] < Sb.shape[0] else Ub)
 
-    XX, Ux = isometry(X1, X2, 'i1 i3 a, j1 j3 b -> i1 i3 ab j1 j3',
-                      ['i1 i3 ab j1 j3 -> i1 i3 ab j3 j1', 'i1 i3 ab j3 j1 -> i1 i3 j3 ab j1',
-                       'i1 i3 j3 ab j1 -> i3 j3 i1 ab j1', 'i3 j3 i1 ab j1 -> i3 j3 ab i1 j1'],
+    XX, Ux = isometry(X1, X2, 'i1 i3 a, j1 j3 b -> i3 j3 ab i1 j1',
                       '(i3 j3 ab)(i1 j1)', ' I1 J1 i3 j3 ab, i3 j3 ab i1 j1 -> I1 J1 i1 j1',
                       '(i3 j3)(ab i1 j1)', ' I3 J3 ab i1 j1, ab i1 j1 i3 j3  -> I3 J3 i3 j3')
     cUx = Ux.hconjugate('ij|a')
-    XX = E('i3 j3 ab i1 j1 -> j3 i3 ab i1 j1', XX)
-    XX = E('j3 i3 ab i1 j1 -> j3 i3 ab j1 i1', XX)
-    Xp = E('s i3 j3,j3 i3 kl j1 i1 -> s kl j1 i1', cUx, XX)
-    Xp = E('s kl j1 i1, i1 j1 t -> s kl t', Xp, Ux)
-    Xp = E('s kl t -> t s kl', Xp)
+    # (reference :1994-1998: two more swaps of XX, then the contraction, then a leg rotation of the result -- folded
+    # into the index strings of the contractions themselves)
+    Xp = E('s i3 j3, i3 j3 kl i1 j1 -> s kl j1 i1', cUx, XX)
+    Xp = E('s kl j1 i1, i1 j1 t -> t s kl', Xp, Ux)
     Xp = E('t s kl , kam -> t s al m', Xp, P1)
     Xp = E('t s al m , lbm -> t s ab m', Xp, P2)
 
-    YY, Uy = isometry(Y2, Y1, 'b j2 j4, a i2 i4 -> j2 j4 ba i2 i4',
-                      ['j2 j4 ba i2 i4 -> j2 j4 i4 ba i2', 'j2 j4 i4 ba i2 -> j4 i4 j2 ba i2',
-                       'j4 i4 j2 ba i2 -> j4 i4 ba i2 j2', 'j4 i4 ba i2 j2 -> i4 j4 ba i2 j2'],
+    YY, Uy = isometry(Y2, Y1, 'b j2 j4, a i2 i4 -> i4 j4 ba i2 j2',
                       '(i4 j4 ba)(i2 j2)', ' I2 J2 i4 j4 ba, i4 j4 ba i2 j2 -> I2 J2 i2 j2',
                       '(i4 j4)(ba i2 j2)', ' I4 J4 ba i2 j2, ba i2 j2 i4 j4  -> I4 J4 i4 j4')
     cUy = Uy.hconjugate('ij|a')
-    YY = E('i4 j4 b a i2 j2 -> j4 i4 b a i2 j2', YY)
-    YY = E('j4 i4 b a i2 j2 -> j4 i4 b a j2 i2', YY)
-    Yp = E('s i4 j4,j4 i4 lk j2 i2 -> s lk j2 i2', cUy, YY)
-    Yp = E('s lk j2 i2, i2 j2 t -> s lk t', Yp, Uy)
-    Yp = E('s lk t -> lk t s', Yp)
+    Yp = E('s i4 j4, i4 j4 lk i2 j2 -> s lk j2 i2', cUy, YY)
+    Yp = E('s lk j2 i2, i2 j2 t -> lk t s', Yp, Uy)
     Yp = E('nak, lk t s -> n la t s', Q1, Yp)
     Yp = E('nbl, n la t s -> n ba t s', Q2, Yp)
     T = E(' t1 t3 kl m, n lk t2 t4 -> t1 t2 t3 t4 mn ', Xp, Yp)

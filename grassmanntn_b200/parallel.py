@@ -175,12 +175,12 @@ def broadcast_usv(results, nprob, device, dtype):
     every rank (isometries broadcast from their owners)."""
     import numpy as np
     w, r = dist.get_world_size(), dist.get_rank()
-    shapes = [None] * w
-    mine = {i: (tuple(u.shape), len(s), tuple(v.shape)) for i, (u, s, v) in results.items()}
-    dist.all_gather_object(shapes, mine)
-    meta = {}
-    for d in shapes:
-        meta.update(d)
+    # shapes of the owners' results: one small integer all-reduce (every problem has exactly one owner), no pickling
+    table = torch.zeros(nprob, 5, dtype=torch.int64, device=device)
+    for i, (u, s, v) in results.items():
+        table[i] = torch.tensor([u.shape[0], u.shape[1], len(s), v.shape[0], v.shape[1]], dtype=torch.int64)
+    dist.all_reduce(table)
+    meta = {i: ((int(t[0]), int(t[1])), int(t[2]), (int(t[3]), int(t[4]))) for i, t in enumerate(table.cpu().tolist())}
     out = []
     for i in range(nprob):
         ush, ns, vsh = meta[i]

@@ -39,6 +39,7 @@ from . import _cabi, _engine as E
 from ._cabi import check, count, lib
 from ._engine import BT, FERMI, PermutePlan, _cached, _ptr, _row_strides, _stream, build_job, dtype_code, lin_leg
 
+GATHER_MAX_DIM = 16384     # largest sector (smaller side) the owner-gathered fallback decomposes on one GPU
 STATS = {"allreduce_bytes": 0, "allgather_bytes": 0, "broadcast_bytes": 0, "collectives": 0}
 
 
@@ -572,6 +573,11 @@ def _svd_gathered(mats, ks, cutoff, site=None):
     from . import _ops
     w, r = world(), rank()
     dev, dt = mats[0].device, mats[0].dtype
+    if max(min(m.shape[0], m.shape[1] * w) for m in mats) > GATHER_MAX_DIM:
+        import grassmanntn_b200 as gtn
+        gtn.error("Error[sharded]: the truncated decomposition of a %d x %d sector did not meet its certificate and the "
+                  "sector is too large for the single-GPU fallback (full SVD)."
+                  % (mats[0].shape[0], mats[0].shape[1] * w))
     full = {}
     for b, m in enumerate(mats):                                  # column blocks to the owners
         p, q = m.shape

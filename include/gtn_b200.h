@@ -315,6 +315,13 @@ int gtn_sumabs(const void* x, int64_t n, int dtype, double* out_dev, int zero_fi
  * multiply).  y has `rows` elements of the same dtype. */
 int gtn_rowsum(const void* x, void* y, int64_t rows, int64_t cols, int dtype, void* stream);
 
+/* y[i] = sum_{s < nslices} x[s * n + i], slices added in index order (deterministic): completes a split-K grouped
+ * GEMM whose slices were written to consecutive copies of the output (Gram-type contractions with a handful of output
+ * tiles and a very long contracted range, e.g. the environment matrices of hotrg3dz, gauge2d.py:1964-1992; the
+ * reference contracts them inside oe.contract, __init__.py:2295).  x and y 16-byte aligned; GTN_F64 needs an even n when
+ * nslices > 1 (every slice starts 16-byte aligned). */
+int gtn_sum_slices(const void* x, void* y, int64_t n, int nslices, int dtype, void* stream);
+
 /* out = sum_i a_i * b_i (no conjugation; out has one element of `dtype`).  The fully contracted
  * einsum ('ijkl,klij', 'IJIK,iKiJ': the trace-preservation checks of gauge2d.py:1738, :1856) after
  * the operands were packed with their signs -- the degenerate 1 x K x 1 case of oe.contract

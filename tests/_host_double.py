@@ -146,6 +146,11 @@ class HostLib:
         _arr(y, rows, dt)[:] = _arr(x, rows * cols, dt).reshape(rows, cols).sum(axis=1)
         return 0
 
+    def gtn_sum_slices(self, x, y, n, nslices, code, stream):
+        dt = np.complex128 if code == 1 else np.float64
+        _arr(y, n, dt)[:] = _arr(x, n * nslices, dt).reshape(nslices, n).sum(axis=0)
+        return 0
+
     def gtn_row_sumsq(self, x, y, rows, cols, code, stream):
         v = _arr(x, rows * cols, self._dt(code)).reshape(rows, cols)
         _arr(y, rows, np.float64)[:] = np.sum(np.abs(v) ** 2, axis=1)

@@ -128,6 +128,8 @@ SWEEP = [
     ("ajk,jib->aibk", [((32, 32, 32), (1, 1, -1)), ((32, 32, 32), (-1, 1, -1))], False),
     ("ijkl,klij", [((32,) * 4, (1, 1, 1, 1)), ((32,) * 4, (-1, -1, -1, -1))], False),
     ("ijkl,klmn->ijmn", [((40, 38, 42, 36), (1, 1, 1, 1)), ((42, 36, 40, 38), (-1, -1, 1, 1))], True),
+    # Gram-type contraction (a few output tiles, K = 8192 per sector): the split-K path (GemmPlan._split_k + gtn_sum_slices)
+    ("abcx,abcy->xy", [((32, 32, 16, 8), (1, 1, 1, 1)), ((32, 32, 16, 8), (-1, -1, -1, 1))], False),
 ]
 
 

@@ -208,6 +208,33 @@ def test_eig_reconstruction_D16(gtn):
     assert np.abs(_np(R) - _np(Hm)).max() <= 1e-10 * np.abs(_np(Hm)).max()
 
 
+def test_truncated_eig_vs_oracle_D16(gtn):
+    """eig with a cut far below the sector size (128 x 128 sectors, 8 eigenpairs each) goes through the truncated
+    solver (subspace iteration + certificate): eigenvalues against the oracle's LAPACK path to 1e-10, and the kept
+    part reproduces the Hermitian tensor's best approximation"""
+    from grassmanntn_b200 import _ops
+    rng = np.random.RandomState(17)
+    # a decaying Hermitian tensor: H = A diag A^H built from a random tensor and a geometric spectrum in its bond
+    a, A = _mk(gtn, (16, 16, 16), (1, 1, -1), rng)
+    w = 0.8 ** np.arange(16)
+    Wd = O.Dense(np.diag(w).astype(complex), (1, -1))
+    Wg = gtn.dense(np.diag(w).astype(complex), statistics=(1, -1))
+    h = O.einsum('abx,xy->aby', a, Wd)
+    H = gtn.einsum('abx,xy->aby', A, Wg)
+    hh = O.einsum('abx,xcd->abcd', h, O.hconjugate(h, 'ab|x'))
+    HH = gtn.einsum('abx,xcd->abcd', H, H.hconjugate('ab|x'))
+    before = dict(_ops.SVD_PATH_STATS)
+    U, L, V = HH.eig('ab|cd', 16)
+    assert _ops.SVD_PATH_STATS["truncated"] > before["truncated"]
+    u, l, v = O.eig(hh, 'ab|cd', 16)
+    lg, lr = np.sort(np.abs(np.diag(_np(L))))[::-1], np.sort(np.abs(np.diag(l.data)))[::-1]
+    assert L.shape == l.shape
+    assert np.abs(lg - lr).max() <= 1e-10 * lr[0]
+    R = gtn.einsum('abx,xy,ycd->abcd', U, L, V)
+    r = O.einsum('abx,xy,ycd->abcd', u, l, v)
+    assert np.abs(_np(R) - r.data).max() <= 1e-9 * np.abs(r.data).max()
+
+
 def test_graph_replay_equals_eager_launches(gtn):
     """the steady-state truncated-SVD schedule replayed as a CUDA graph must give what the same launches
     give one by one (same kernels, same order): Tnorm of a TRG chain on the Z2 tensor, both ways"""

@@ -206,7 +206,7 @@ def test_host_hotrg3dz_z2_chi64_vs_reference(gtn_host_trunc):
 import test_chains as CH  # noqa: E402
 
 
-@pytest.mark.parametrize("case", [0, 3, 4, 8, 10])
+@pytest.mark.parametrize("case", [0, 3, 4, 8, 10, 11])
 def test_einsum_sweep_large_dims(gtn_host, case):
     CH.test_gpu_einsum_sweep_large_dims_vs_oracle(gtn_host, case)
 
@@ -260,3 +260,7 @@ def test_rank_deficient_sectors_chi64_rank_certificate(gtn_host_trunc):
         assert abs(F - complex(ref[i, 1], ref[i, 2])) <= 1e-10 * abs(F), (i, F)
     assert _ops.SVD_PATH_STATS["truncated"] > before["truncated"]
     assert E.RANK_CHECK_STATS["certified"] > calls["certified"]
+
+
+def test_truncated_eig_vs_oracle_D16(gtn_host_trunc):
+    GE.test_truncated_eig_vs_oracle_D16(gtn_host_trunc)
