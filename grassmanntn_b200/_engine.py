@@ -40,15 +40,22 @@ class _Profiler:
     def __init__(self):
         self.enabled = False
         self.records = []
+        self.descs = []
+        self.detail = []
 
     def start(self):
         self.enabled = True
         self.records = []
+        self.descs = []
 
-    def stop(self):
+    def stop(self, detail=False):
         self.enabled = False
         torch.cuda.synchronize()
         out = {}
+        if detail:
+            self.detail = [(name, s.elapsed_time(e), flops, nbytes, desc) for (name, s, e, _, nbytes, flops), desc
+                           in zip(self.records, self.descs)]
+        self.descs = []
         for name, s, e, launches, nbytes, flops in self.records:
             d = out.setdefault(name, dict(ms=0.0, calls=0, launches=0, bytes=0, flops=0))
             d["ms"] += s.elapsed_time(e)
@@ -64,8 +71,9 @@ PROF = _Profiler()
 
 
 class prof_region:
-    def __init__(self, name, launches=1, nbytes=0, flops=0):
+    def __init__(self, name, launches=1, nbytes=0, flops=0, desc=None):
         self.a = (name, launches, nbytes, flops)
+        self.desc = desc
 
     def __enter__(self):
         if PROF.enabled:
@@ -82,6 +90,7 @@ class prof_region:
             e = torch.cuda.Event(enable_timing=True)
             e.record()
             PROF.records.append((self.a[0], self.s, e, self.a[1], self.a[2], self.a[3]))
+            PROF.descs.append(self.desc)
         return False
 
 
@@ -731,6 +740,8 @@ class GemmPlan:
             b = g.get("batch", 1)
             self.flops += (8 if cplx else 2) * b * g["m"] * g["n"] * g["k"]
             self.bytes += (16 if cplx else 8) * b * (g["m"] * g["k"] + g["k"] * g["n"] + g["m"] * g["n"])
+        self.desc = "%d groups, first %dx%dx%d, slices %d" % (self.n, groups[0]["m"], groups[0]["n"], groups[0]["k"],
+                                                               self.slices)
         arr = (GemmGroup * self.n)()
         for k, g in enumerate(groups):
             a = arr[k]
@@ -840,7 +851,7 @@ class GemmPlan:
         self._launch(A, B, Cm)
 
     def _launch(self, A, B, Cm):
-        with prof_region(self.family, 1, self.bytes, self.flops):
+        with prof_region(self.family, 1, self.bytes, self.flops, self.desc):
             if self.config & 4:
                 check(lib.gtn_grouped_gemm_tma(_ptr(A), _ptr(B), _ptr(Cm), dtype_code(A.dtype), self.host, _ptr(self.dev),
                                                self.n, self.tiles, self.config, _stream()), "gtn_grouped_gemm_tma")
@@ -1033,7 +1044,7 @@ def _ctranspose_t(src, r, c, ld, dst):
     def build():
         legs = [lin_leg(r, ld, 1), lin_leg(c, 1, r)]
         return PermutePlan([build_job(legs, conj=(src.dtype == torch.complex128), in_order=[0, 1], out_order=[1, 0])])
-    _cached(("ctrans_t", r, c, ld, str(src.dtype)), build).run(src, dst)
+    _cached(("ctrans_t", r, c, ld, str(src.dtype)), build).run(src.view(-1), dst.view(-1))
 
 
 def _sumsq_t(t):

@@ -29,6 +29,7 @@ _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 _CORE_FILES = ("__init__.py", "_ops.py", "_engine.py")
 from ._engine import prof_region
 
+COMPACT_PACK = bool(int(os.environ.get("GTN_COMPACT_PACK", "1")))
 NUMER_CUTOFF = 1.0e-14      # reference __init__.py:30 (module global numer_cutoff)
 SVD_PATH_STATS = {"truncated": 0, "truncated_rejected": 0, "full": 0}
 TRUNCATED_SVD = True        # randomized subspace path for truncated decompositions (with certificate)
@@ -53,13 +54,25 @@ def _label_legs(bt, labels):
     return info
 
 
-def _pack_jobs(bt, labels, info, groups, lays, assigned, out_elems_mult=None):
+def _compact_sizes(layR, layC):
+    """(elements per batch index, base of the odd sector) of the compact packing of an even operand:
+    [A_ee (R_e x C_e)][A_oo (R_o x C_o)] back to back -- the zero quadrants of [[A_ee, 0], [0, A_oo]] are not stored"""
+    (_, re_), (_, ro) = layR.sector(0), layR.sector(1)
+    (_, ce), (_, co) = layC.sector(0), layC.sector(1)
+    return re_ * ce + ro * co, re_ * ce
+
+
+def _pack_jobs(bt, labels, info, groups, lays, assigned, out_elems_mult=None, compact=False):
     """Jobs that copy every live block of `bt` into the packed buffer.
     groups: dict name -> list of labels for 'B' (batch), 'R', 'C', 'T'; lays: GroupLayout per name.
-    assigned: (alpha labels, beta labels, Q pairs) evaluated by this operand."""
+    assigned: (alpha labels, beta labels, Q pairs) evaluated by this operand.
+    compact (Grassmann-even operand, no traced legs): the two parity sectors are stored back to back as dense
+    R_s x C_s matrices (half the bytes of the full R x C matrix; at D = chi = 256 the difference is 32 GiB)."""
     alpha_l, beta_l, q_pairs = assigned
     tot = {k: lays[k].total for k in lays}
     mult = {"T": 1, "C": tot["T"], "R": tot["T"] * tot["C"], "B": tot["T"] * tot["C"] * tot["R"]}
+    if compact:
+        csz, codd = _compact_sizes(lays["R"], lays["C"])
     uniq = list(dict.fromkeys(labels))
     where = {}
     for g, lst in groups.items():
@@ -81,6 +94,13 @@ def _pack_jobs(bt, labels, info, groups, lays, assigned, out_elems_mult=None):
         gp = {g: tuple(par[ch] for ch in lst if info[ch][0] in FERMI) for g, lst in groups.items()}
         used.add(tuple(gp[g] for g in ("B", "R", "C", "T")))
         out_base = sum(lays[g].offset[gp[g]] * mult[g] for g in lays)
+        if compact:
+            sec = sum(gp["R"]) % 2
+            assert sum(gp["C"]) % 2 == sec, "compact packing needs a Grassmann-even operand"
+            (r0, _), (c0, cl) = lays["R"].sector(sec), lays["C"].sector(sec)
+            mult = {"T": 1, "C": 1, "R": cl, "B": csz}
+            out_base = (lays["B"].offset[gp["B"]] * csz + (codd if sec else 0)
+                        + (lays["R"].offset[gp["R"]] - r0) * cl + (lays["C"].offset[gp["C"]] - c0))
         bshape = bt.block_shape(pat)
         bstr = _row_strides(bshape)
         legs, beta = [], []
@@ -104,15 +124,29 @@ def _pack_jobs(bt, labels, info, groups, lays, assigned, out_elems_mult=None):
     return jobs, used
 
 
+def _alloc(fn, n, dtype, dev):
+    """large temporaries: when the caching allocator cannot serve the request from its free pool, return the cached
+    blocks to the driver and try once more (a 64 GiB pack at D = chi = 256 next to 30 GiB of cached, unused blocks)"""
+    try:
+        return fn(n, dtype=dtype, device=dev)
+    except torch.OutOfMemoryError:
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+        return fn(n, dtype=dtype, device=dev)
+
+
 class PackPlan:
     """cached launch plan that packs every live block of an operand layout into [B][R][C][T]
     (then sums the T axis away)."""
 
-    def __init__(self, bt, labels, info, groups, assigned, restrict_even=None):
+    def __init__(self, bt, labels, info, groups, assigned, restrict_even=None, compact=False):
         self.lays = lays = {g: group_layout([info[ch] for ch in groups[g]]) for g in ("B", "R", "C", "T")}
-        jobs, used = _pack_jobs(bt, labels, info, groups, lays, assigned)
+        self.compact = bool(compact and restrict_even and COMPACT_PACK and not groups["T"] and bt.is_even())
+        jobs, used = _pack_jobs(bt, labels, info, groups, lays, assigned, compact=self.compact)
         self.plan = PermutePlan(jobs)
         self.total = lays["B"].total * lays["R"].total * lays["C"].total * lays["T"].total
+        if self.compact:
+            self.total = lays["B"].total * _compact_sizes(lays["R"], lays["C"])[0]
         need = 1
         for g in ("B", "R", "C", "T"):
             need *= len(lays[g].pats)
@@ -130,7 +164,7 @@ class PackPlan:
 
     def run(self, bt):
         dev = bt.buf.device
-        buf = (torch.empty if self.full else torch.zeros)(max(self.total, 1), dtype=bt.dtype, device=dev)
+        buf = _alloc(torch.empty if self.full else torch.zeros, max(self.total, 1), bt.dtype, dev)
         self.plan.run(bt.buf, buf)
         if self.reduce:
             red = torch.empty(max(self.rows, 1), dtype=bt.dtype, device=dev)
@@ -322,8 +356,8 @@ def _plan_pair(inputs, output, ops, prog):
     gL = {"B": batch, "R": L[3], "C": K, "T": L[4]}
     gR = {"B": batch, "R": K, "C": R[3], "T": R[4]}
     even = L[0].is_even() and R[0].is_even()
-    ppL = PackPlan(L[0], L[1], info, gL, asg["L"], restrict_even=even)
-    ppR = PackPlan(R[0], R[1], info, gR, asg["R"], restrict_even=even)
+    ppL = PackPlan(L[0], L[1], info, gL, asg["L"], restrict_even=even, compact=True)
+    ppR = PackPlan(R[0], R[1], info, gR, asg["R"], restrict_even=even, compact=True)
     layL, layR = ppL.lays, ppR.lays
     layM, layK, layN, layB = layL["R"], layL["C"], layR["C"], layL["B"]
     Mtot, Ktot, Ntot, Btot = layM.total, layK.total, layN.total, layB.total
@@ -352,9 +386,18 @@ def _plan_pair(inputs, output, ops, prog):
                 e ^= par[x] & par[y]
             pat = tuple(pM) + tuple(pN)
             res.off[pat] = acc
-            groups.append(dict(a_off=layM.offset[pM] * Ktot + k0, b_off=k0 * Ntot + layN.offset[pN], c_off=acc,
-                               lda=Ktot, ldb=Ntot, ldc=n, m=m, n=n, k=kl, batch=Btot,
-                               bsa=Mtot * Ktot, bsb=Ktot * Ntot, bsc=m * n, alpha=-1.0 if e else 1.0))
+            g_ = dict(a_off=layM.offset[pM] * Ktot + k0, b_off=k0 * Ntot + layN.offset[pN], c_off=acc,
+                      lda=Ktot, ldb=Ntot, ldc=n, m=m, n=n, k=kl, batch=Btot,
+                      bsa=Mtot * Ktot, bsb=Ktot * Ntot, bsc=m * n, alpha=-1.0 if e else 1.0)
+            sec = sum(pM) % 2
+            if ppL.compact:          # [A_ee][A_oo] back to back: sector-local row offset, lda = K of the sector
+                szL, oddL = _compact_sizes(layM, layK)
+                g_.update(a_off=(oddL if sec else 0) + (layM.offset[pM] - layM.sector(sec)[0]) * kl, lda=kl, bsa=szL)
+            if ppR.compact:
+                szR, oddR = _compact_sizes(layK, layN)
+                n0, nl = layN.sector(sec)
+                g_.update(b_off=(oddR if sec else 0) + (layN.offset[pN] - n0), ldb=nl, bsb=szR)
+            groups.append(g_)
             acc += Btot * m * n
     plan = GemmPlan(groups, A.dtype)
     shard_cache = {}
@@ -373,7 +416,7 @@ def _plan_pair(inputs, output, ops, prog):
         bufL, bufR = ppL.run(Lop), ppR.run(Rop)
         r = BT(res_meta[0], res_meta[1], res_meta[2], A_.dtype)
         r.off = dict(res_off)
-        r.buf = torch.empty(max(acc, 1), dtype=A_.dtype, device=A_.buf.device)
+        r.buf = _alloc(torch.empty, max(acc, 1), A_.dtype, A_.buf.device)
         if Ktot == 0:
             r.buf.zero_()
         elif Mtot == 1 and Ntot == 1 and Btot == 1 and len(groups) == 1:

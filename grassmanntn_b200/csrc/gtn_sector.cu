@@ -128,7 +128,8 @@ struct Layout {
   std::vector<int> soff;
   // byte offsets of the typed tail
   int64_t o_sdev, o_rn2, o_res2, o_nscr, o_fro2, o_offd, o_out, o_acc, o_kept, o_order, o_sw, o_ndev, o_goff, o_toff,
-      o_rnoff, o_probs, o_outs, o_chol, o_meta, total_bytes;
+      o_rnoff, o_probs, o_probs_g, o_probs_r, o_outs, o_chol, o_meta, total_bytes;
+  bool prerotate = false;                 // wide subspaces (l > 80): Gram pre-rotation of the projected matrix
   int64_t chol_elems = 0;
 
   Mat add(int64_t r, int64_t c) {
@@ -184,6 +185,9 @@ struct Layout {
     o_kept = take(8 * nb); o_order = take(4 * sumL); o_sw = take(16); o_ndev = take(4 * nb);
     o_goff = take(8 * nb); o_toff = take(8 * nb); o_rnoff = take(8 * nb);
     o_probs = take(sizeof(gtn_svd_problem) * nb); o_outs = take(sizeof(gtn_svd_out) * nb);
+    o_probs_g = take(sizeof(gtn_svd_problem) * nb); o_probs_r = take(sizeof(gtn_svd_problem) * nb);
+    prerotate = true;
+    for (int b = 0; b < nb; ++b) prerotate = prerotate && L[b] > 80;
     chol_elems = gtn_chol_whiten_scratch_elems(maxL);
     o_chol = take(16 * chol_elems * nb);
     o_meta = take(kMetaBytes);
@@ -298,11 +302,14 @@ struct Driver {
     const int nb = lay.nb;
     std::vector<int64_t> goff(nb), toff(nb), rnoff(nb);
     std::vector<int32_t> nd(nb);
-    std::vector<gtn_svd_problem> pr(nb);
+    std::vector<gtn_svd_problem> pr(nb), pg(nb), prr(nb);
     std::vector<gtn_svd_out> ou(nb);
     for (int b = 0; b < nb; ++b) {
       goff[b] = lay.T1[b].off; toff[b] = lay.T2[b].off; rnoff[b] = lay.soff[b]; nd[b] = lay.L[b];
       pr[b].w_off = lay.B[b].off; pr[b].z_off = lay.Z[b].off; pr[b].p = lay.L[b]; pr[b].q = (int32_t)lay.Q[b];
+      // pre-rotation: Jacobi on the l x l Gram matrix (in T2, rotations into UbH), then on B' = T B (in Sq)
+      pg[b].w_off = lay.T2[b].off; pg[b].z_off = lay.UbH[b].off; pg[b].p = lay.L[b]; pg[b].q = lay.L[b];
+      prr[b] = pr[b]; prr[b].w_off = lay.Sq[b].off;
       ou[b].s_off = lay.soff[b]; ou[b].u_off = lay.Ub[b].off;
     }
     auto up = [&](int64_t off, const void* src, size_t bytes) {
@@ -311,6 +318,7 @@ struct Driver {
     up(lay.o_goff, goff.data(), 8 * nb); up(lay.o_toff, toff.data(), 8 * nb); up(lay.o_rnoff, rnoff.data(), 8 * nb);
     up(lay.o_ndev, nd.data(), 4 * nb);
     up(lay.o_probs, pr.data(), sizeof(gtn_svd_problem) * nb); up(lay.o_outs, ou.data(), sizeof(gtn_svd_out) * nb);
+    up(lay.o_probs_g, pg.data(), sizeof(gtn_svd_problem) * nb); up(lay.o_probs_r, prr.data(), sizeof(gtn_svd_problem) * nb);
     for (int b = 0; b < nb; ++b) {
       const int64_t n = (int64_t)lay.L[b] * lay.Q[b] * (lay.dtype == GTN_C128 ? 2 : 1);
       randn_kernel<<<296, 256, 0, st>>>((double*)elem(lay.G[b]), (n + 1) / 2, 0x243F6A8885A308D3ull + 7919ull * b + (uint64_t)n);
@@ -382,6 +390,36 @@ struct Driver {
     int64_t* rnoff = at<int64_t>(lay.o_rnoff);
     gtn_svd_problem* probs = at<gtn_svd_problem>(lay.o_probs);
     int32_t* sw = at<int32_t>(lay.o_sw);
+    const std::vector<Mat>* Bsrc = &lay.B;
+    if (lay.prerotate && persistent) {
+      // Gram pre-rotation for wide subspaces (l > 80, where gtn_gram_rotate's shared-memory Jacobi does not fit): the
+      // Jacobi kernel diagonalises G = B B^H first -- l^2 numbers per round instead of l q -- and its accumulated
+      // rotations T make the rows of B' = T B orthogonal to the accuracy a Gram matrix allows; the Jacobi SVD of the
+      // l x q matrix then needs 2 sweeps instead of 8.  Qh is rotated along (Qh' = T Qh), so that B' = Qh' W and
+      // everything downstream is unchanged; the singular values never go through G.
+      ctranspose_all(lay.B, lay.Cq);
+      gram(lay.B, lay.Cq);
+      for (int b = 0; b < nb && !err; ++b) {
+        note(gtn_sum_slices(elem(lay.T1[b]), elem(lay.T2[b]), (int64_t)lay.L[b] * lay.L[b], lay.NS, lay.dtype, st));
+        ++launches;
+      }
+      gtn_svd_problem* pg = at<gtn_svd_problem>(lay.o_probs_g);
+      note(gtn_jacobi_init(ws, ws, lay.dtype, pg, nb, lay.maxL, rn2, fro2, rnoff, st));
+      const int rcg = gtn_jacobi_persistent(ws, ws, lay.dtype, pg, nb, lay.maxL, kJacobiTol, offd, rn2, fro2, rnoff,
+                                            kJacobiMaxSweeps, sw, st, 1e-6);
+      launches += 2;
+      if (rcg == 0) {
+        gemm_all(lay.UbH, lay.B, lay.Sq);
+        gemm_all(lay.UbH, lay.Qh, lay.Sp);
+        for (int b = 0; b < nb && !err; ++b)
+          note((int)cudaMemcpyAsync(elem(lay.Qh[b]), elem(lay.Sp[b]), (int64_t)lay.L[b] * lay.P[b] * lay.esz,
+                                    cudaMemcpyDeviceToDevice, st));
+        probs = at<gtn_svd_problem>(lay.o_probs_r);
+        Bsrc = &lay.Sq;
+      } else if (rcg != GTN_ERR_UNSUPPORTED) {
+        note(rcg);
+      }
+    }
     note(gtn_jacobi_init(ws, ws, lay.dtype, probs, nb, lay.maxL, rn2, fro2, rnoff, st));
     ++launches;
     host_sweeps = -1;
@@ -411,7 +449,7 @@ struct Driver {
     }
     if (err) return;
     double* s_dev = at<double>(lay.o_sdev);
-    char* vh_ptr = ws + (lay.Vk[0].off - lay.B[0].off) * (int64_t)lay.esz;      // Vh_out is addressed with W's offsets
+    char* vh_ptr = ws + (lay.Vk[0].off - (*Bsrc)[0].off) * (int64_t)lay.esz;    // Vh_out is addressed with W's offsets
     note(gtn_jacobi_finish(ws, ws, ws, vh_ptr, s_dev, lay.dtype, probs, at<gtn_svd_out>(lay.o_outs),
                            at<int32_t>(lay.o_order), at<double>(lay.o_nscr), nb, lay.maxL, (int)lay.maxQ, st));
     launches += 2;

@@ -39,6 +39,8 @@ from . import _cabi, _engine as E
 from ._cabi import check, count, lib
 from ._engine import BT, FERMI, PermutePlan, _cached, _ptr, _row_strides, _stream, build_job, dtype_code, lin_leg
 
+BIG_PREROTATE = bool(int(__import__("os").environ.get("GTN_BIG_PREROTATE", "1")))
+BIG_PREROTATE_MIN_L = 80    # (gtn_gram_rotate serves l <= 80 on the single-GPU path)
 GATHER_MAX_DIM = 16384     # largest sector (smaller side) the owner-gathered fallback decomposes on one GPU
 STATS = {"allreduce_bytes": 0, "allgather_bytes": 0, "broadcast_bytes": 0, "collectives": 0}
 
@@ -333,6 +335,32 @@ class ShardedTruncPlan(E._TruncPlan):
             l, q = self.L_[b], self.Q_[b]
             jws.view(self.jB[b]).view(l, w, q).copy_(self.gbuf[b].view(w, l, q).permute(1, 0, 2))
         self.jacobi_ok.fill_(1.0)
+        rot = {}
+        if self.mine and BIG_PREROTATE and min(self.L_[b] for b in self.mine) > BIG_PREROTATE_MIN_L:
+            # Pre-rotation for wide subspaces (l > 80: chi >= 128, where gtn_gram_rotate's shared-memory Jacobi does not
+            # fit): the Jacobi kernels diagonalise the l x l Gram matrix G = B B^H first (cheap: l^2 numbers per round
+            # instead of l q), B' = U_G^H B then has rows orthogonal to the accuracy a Gram matrix allows and the Jacobi
+            # SVD of the l x q matrix needs 2 sweeps instead of 8 (12 -> 5 ms per check at chi = 128, the largest
+            # unsharded piece of a sharded step); B = U_G B' = (U_G Ub') S Vh: the singular values never go through G.
+            gs = []
+            for b in self.mine:
+                l, Qf = self.L_[b], self.Qfull[b]
+                Bm = jws.view(self.jB[b])
+                Bh = torch.empty(Qf * l, dtype=dt, device=dev)
+                E._ctranspose_t(Bm, l, Qf, Qf, Bh)
+                G = torch.empty(l * l, dtype=dt, device=dev)
+                E._gemm_t(Bm, Qf, Bh, l, G, l, l, l, Qf)
+                gs.append(G.view(l, l))
+            for b, (Ug, _, _) in zip(self.mine, E.batched_svd(gs)):
+                l, Qf = self.L_[b], self.Qfull[b]
+                Ug = Ug.contiguous()
+                Th = torch.empty(l * l, dtype=dt, device=dev)
+                E._ctranspose_t(Ug, l, l, l, Th)                                # T = U_G^H
+                Bm = jws.view(self.jB[b])
+                Bp = torch.empty(l * Qf, dtype=dt, device=dev)
+                E._gemm_t(Th, l, Bm, Qf, Bp, Qf, l, Qf, l)
+                Bm.view(-1).copy_(Bp)
+                rot[b] = Ug
         if self.mine:
             nm = len(self.mine)
             Wp = _ptr(jws.buf)
@@ -375,6 +403,12 @@ class ShardedTruncPlan(E._TruncPlan):
             count(2)
             for k, b in enumerate(self.mine):
                 self.s_dev[self.soff[b]: self.soff[b] + self.L_[b]].copy_(self.js[self.jsoff[k]: self.jsoff[k] + self.L_[b]])
+                if b in rot:                                                    # Ub = U_G Ub'
+                    l = self.L_[b]
+                    Ub = jws.view(self.jU[b])
+                    tmp = torch.empty(l * l, dtype=dt, device=dev)
+                    E._gemm_t(rot[b], l, Ub, l, tmp, l, l, l, l)
+                    Ub.view(-1).copy_(tmp)
         # ---- Ub, s, Vh from the owners
         if w > 1:
             all_ok = self.jacobi_ok.clone()
@@ -735,9 +769,11 @@ def atrg2dy(Tl, dcut, intermediate_dcut=None):
     Y = E_("abx,xc->abc", U, sq)                                 # replicated
     X = E_("ax,xbc->abc", sq, V)                                 # sharded on index 2 (k)
     X = _blk(gather_leg(X._bt, 2, *full_k))
-    Q1 = E_("iax,xbj->ijab", U1, Y)                              # replicated (D = U2 = U1)
+    # (reference: Q1[i,j,a,b]; written here in the GEMM's natural leg order [i a][b j] -- the same Grassmann tensor, one
+    #  full pass and one chi^2 D^2-sized temporary fewer: 32 GiB at D = chi = 256 -- and contracted through its labels)
+    Q1 = E_("iax,xbj->iabj", U1, Y)                              # replicated (D = U2 = U1)
     Q2 = E_("kya,ylb->abkl", X, A)                               # sharded on index 3 (T's j leg)
-    Q = E_("ijab,abkl->ijkl", Q1, Q2)                            # sharded on index 3
+    Q = E_("iabj,abkl->ijkl", Q1, Q2)                            # sharded on index 3
     del Q1, Q2
     U, S, V = svd1(Q, "ij|kl", dcut, 3)
     sq = gtn.sqrt(S)

@@ -84,6 +84,7 @@ def _worker(rank, world, port, q):
         sharded.truncated_svd_sharded = saved_trunc
         assert sharded.STATS.get("gathered_svds", 0) == 2
         rows = []
+        sharded.BIG_PREROTATE_MIN_L = 0          # exercise the Gram pre-rotation of the owner's Jacobi SVD (l > 80 on the GPU)
         for i in range(2, 6):
             Tl, Tn = sharded.trg(Tl, 16)
             logNorm = 2 * logNorm + math.log(Tn)
@@ -110,6 +111,10 @@ def _worker(rank, world, port, q):
             F = (g.logZ(full, "anti-periodic") + logNorm) / 2 ** (i + 1)
             arows.append((abs(Tn - aref[i, 0]) / aref[i, 0], abs(F - complex(aref[i, 1], aref[i, 2])) / abs(F)))
         q.put((rank, rows, dict(sharded.STATS), arows + frows))
+    except BaseException:                          # a dead rank would leave its peers waiting in a collective
+        import traceback
+        q.put((rank, "error", traceback.format_exc(), None))
+        os._exit(1)
     finally:
         dist.destroy_process_group()
 
@@ -125,6 +130,10 @@ def test_sharded_trg_chain_world2_vs_reference():
     res = {}
     for _ in range(world):
         rank, rows, stats, arows = q.get(timeout=900)
+        if rows == "error":
+            for p in procs:
+                p.kill()
+            pytest.fail("rank %d raised:\n%s" % (rank, stats))
         res[rank] = (rows, stats)
         for dT, dF in arows:
             assert dT <= 1e-10 and dF <= 1e-10, (rank, "atrg", arows)
