@@ -758,6 +758,7 @@ def atrg2dy(Tl, dcut, intermediate_dcut=None):
         return res[0]
     Tr = E_("ijkl->lijk", Tl)                                   # [l,i,j,k], sharded on index 2
     U1, S1, V1 = svd1(Tr, "li|jk", chi_i, 1)
+    del Tr
     A = V1                                                       # [a, j in R_r, k]
     B = E_("lia,ab->lib", U1, S1)                                # replicated
     C = E_("ab,bjk->ajk", S1, V1)                                # sharded on j
@@ -765,6 +766,7 @@ def atrg2dy(Tl, dcut, intermediate_dcut=None):
     C = _blk(slice_leg(C._bt, 2))                                # ... and re-cut along k
     M = E_("ajk,jib->aibk", C, B)                                # sharded on index 3 (k)
     U, S, V = svd1(M, "ai|bk", chi_i, 2)
+    del M, C, B
     sq = gtn.sqrt(S)
     Y = E_("abx,xc->abc", U, sq)                                 # replicated
     X = E_("ax,xbc->abc", sq, V)                                 # sharded on index 2 (k)
@@ -776,6 +778,7 @@ def atrg2dy(Tl, dcut, intermediate_dcut=None):
     Q = E_("iabj,abkl->ijkl", Q1, Q2)                            # sharded on index 3
     del Q1, Q2
     U, S, V = svd1(Q, "ij|kl", dcut, 3)
+    del Q
     sq = gtn.sqrt(S)
     H = E_("abx,xc->abc", U, sq)                                 # replicated
     G = E_("ax,xbc->abc", sq, V)                                 # sharded on index 2 (T's j leg)
