@@ -45,6 +45,9 @@ def main(argv=None, force_block=False):
     parse.add_argument('--trg', '--TRG', dest="trg", default=False, action='store_true')
     parse.add_argument('--block', default=force_block, action='store_true', help="block format (example_block.py)")
     parse.add_argument('--tensor', default=None, help=".npz with the initial site tensor (data, statistics, encoder, format)")
+    parse.add_argument('--from-ab', dest="from_ab", default=False, action='store_true',
+                       help="build the initial tensor on the GPU from the A / B tensors (the compression stages of the "
+                            "reference's tensor_preparation: gauge2d.tensor_from_AB) instead of loading the compressed fixture")
     parse.add_argument('--log', default=None, help="JSON-lines run log")
     parse.add_argument('--checkpoint', default=None, help="directory for per-step tensor checkpoints")
     parse.add_argument('--resume', default=False, action='store_true')
@@ -61,7 +64,11 @@ def main(argv=None, force_block=False):
           % (args.beta, args.mass, args.mu, args.charge, args.spacing, args.Nf, args.K, args.Dcutz, args.Dcutxy, bc,
              "trg" if args.trg else "atrg", ", block" if args.block else ""))
     t0 = time.time()
-    T = gauge.load_initial_tensor(args.tensor)
+    if args.from_ab:
+        T, terr = gauge.tensor_from_AB(*gauge.load_AB_tensors())
+        print(" compression error:", '{:.3g}'.format(float(terr)))
+    else:
+        T = gauge.load_initial_tensor(args.tensor)
     if args.block:
         T = T.toblock()
     shp = (lambda X: X.effective_shape) if args.block else (lambda X: X.shape)

@@ -308,6 +308,10 @@ def _plan_pair(inputs, output, ops, prog):
     cls = {}
     for ch in dict.fromkeys(la + lb):
         cA, cB, co = la.count(ch), lb.count(ch), out.count(ch)
+        if info[ch][0] == 0 and (cA > 1 or cB > 1) and (cA and cB or co):
+            # a bosonic index repeated inside one operand addresses that operand's diagonal (the pack tables add the
+            # strides of its occurrences), e.g. 'IJIJijij,jiji' of tensor_preparation (reference gauge2d.py:32)
+            cA, cB = min(cA, 1), min(cB, 1)
         if cA == 2 and cB == 0 and co == 0:
             cls[ch] = "tA"
         elif cB == 2 and cA == 0 and co == 0:
@@ -327,7 +331,7 @@ def _plan_pair(inputs, output, ops, prog):
     M = [ch for ch in out if cls[ch] == "M"]
     N = [ch for ch in out if cls[ch] == "N"]
     batch = [ch for ch in out if cls[ch] == "batch"]
-    K = [ch for ch in la if cls[ch] == "K"]
+    K = [ch for ch in dict.fromkeys(la) if cls[ch] == "K"]
     tA = [ch for ch in dict.fromkeys(la) if cls[ch] == "tA"]
     tB = [ch for ch in dict.fromkeys(lb) if cls[ch] == "tB"]
     # left operand = the one whose free legs come first in the output

@@ -29,6 +29,17 @@ def load_initial_tensor(path=None):
     return gtn.dense(z["data"], statistics=stats, encoder=str(z["encoder"]), format=str(z["format"]))
 
 
+def load_AB_tensors(path=None):
+    """The site tensor A[i,j,k,l] (bosonic) and the link tensor B[I,J,K,L,i,j,k,l] of the same model as produced by the
+    reference's get_ABtensors (symbolic Berezin integration, gauge2d.py:139-257; tests/golden/make_z2_prep_golden.py):
+    the inputs of tensor_from_AB."""
+    z = np.load(path or os.path.join(_GOLDEN, "z2_prep.npz"))
+    B = np.zeros(tuple(int(x) for x in z["B_shape"]), dtype=complex)
+    B[tuple(z["B_coords"].T.astype(np.int64))] = z["B_vals"]
+    return (gtn.dense(np.asarray(z["A"]).astype(complex), statistics=tuple(int(s) for s in z["A_stats"])),
+            gtn.dense(B, statistics=tuple(int(s) for s in z["B_stats"])))
+
+
 SPECULATE = bool(int(os.environ.get("GTN_SPECULATE", "1")))
 SPEC_STATS = {"speculated": 0, "failed": 0}       # decompositions run speculatively / whose certificate then failed
 
@@ -497,6 +508,105 @@ def hotrg3dz(T1, T2, dcut=64, intermediate_dcut=None, iternum=None, error_test=F
         err = (Z1 - Z2).norm / Z1.norm
     T, Tnorm = _normalised(T)
     return (T, Tnorm, err) if error_test else (T, Tnorm)
+
+
+# ------------------------------------------------------------------------------------------------
+#  initial-tensor pipeline: the compression stages of tensor_preparation
+#  (reference gauge2d.py:22-66) on the GPU ops.  The symbolic construction of A and B (get_ABtensors: sympy Berezin
+#  integrals, reference gauge2d.py:139-257) stays with the reference; its output arrays go in as gtn.dense.
+# ------------------------------------------------------------------------------------------------
+def _env_isometry(Qp, hp, Qm, hm, gram, part, cutoff):
+    """Isometry onto the dominant subspace of a leg: eigen-decompositions of the two environment Gram matrices
+    Mp = Qp^dagger Qp and Mm = Qm Qm^dagger (the leg as the last / first group of Qp / Qm); the one with the smaller
+    bond wins (reference gauge2d.py:1225-1243, :1313-1338, :1533-1541).  Returns (U, U^dagger)."""
+    E = gtn.einsum
+    Mp = E(gram, Qp.hconjugate(hp), Qp)
+    Mm = E(gram, Qm, Qm.hconjugate(hm))
+    Up, Lp, cUp = Mp.eig(part, cutoff)
+    Um, Lm, cUm = Mm.eig(part, cutoff)
+    return (Up, cUp) if Lp.shape[0] < Lm.shape[0] else (Um, cUm)
+
+
+def fcompress_B(B, cutoff=64, mute=True):
+    """First compression of the link tensor B[I,J,K,L,i,j,k,l] (fermionic legs only; reference gauge2d.py:1198-1291):
+    one isometry per direction, applied to the forward leg and, conjugated, to the backward leg."""
+    E = gtn.einsum
+    g7 = 'I abcdefg,abcdefg J -> IJ'
+    U1, _ = _env_isometry(E('IJKLijkl -> JKLijkl I', B), 'abcdefg|x', E('IJKLijkl -> K IJLijkl', B), 'x|abcdefg',
+                          g7, 'I|J', cutoff)
+    B = E('IA,IJKLijkl->AJKLijkl', U1, B)
+    B = E('CK,AJKLijkl->AJCLijkl', U1.hconjugate('I|J'), B)
+    U2, cU2 = _env_isometry(E('IJKLijkl -> IKLijkl J', B), 'abcdefg|x', E('IJKLijkl -> L IJKijkl', B), 'x|abcdefg',
+                            g7, 'I|J', cutoff)
+    B = E('JB,AJCLijkl->ABCLijkl', U2, B)
+    B = E('DL,ABCLijkl->ABCDijkl', cU2, B)
+    return B
+
+
+def _boson_delta(n):
+    import numpy as _np
+    return gtn.dense(_np.eye(n), statistics=(0, 0))
+
+
+def compress_B(B, cutoff=64, mute=True):
+    """Second compression of B: every fermionic leg is joined with its bosonic partner (copied through a delta) and
+    truncated (reference gauge2d.py:1293-1467).  Returns (B[A,B,C,D], [U1, U2, U3, U4])."""
+    E = gtn.einsum
+    d = _boson_delta(B.shape[4])
+    g9 = 'Ii abcdefg,abcdefg Jj -> IiJj'
+    # per direction: (delta leg, Qp string, Qm string): the reference's four hand-unrolled blocks
+    dirs = [('k', 'JKLjklm Ii', 'Kk IJLijlm'), ('l', 'IKLiklm Jj', 'Ll IJKijkm'),
+            ('i', 'JKLjklm Ii', 'Kk IJLijlm'), ('j', 'IKLiklm Jj', 'Ll IJKijkm')]
+    Us = []
+    for leg, sp, sm in dirs:
+        Qp = E('IJKLijkl,%sm -> %s' % (leg, sp), B, d)
+        Qm = E('IJKLijkl,%sm -> %s' % (leg, sm), B, d)
+        U, _ = _env_isometry(Qp, 'JKLjklm|Ii', Qm, 'Kk|IJLijlm', g9, 'Ii|Jj', cutoff)
+        Us.append(U)
+        del Qp, Qm
+    U1, U2, U3, U4 = Us
+    Bf = E('IJKLijkl,IiA->AJKLjkl', B, U1)
+    Bf = E('AJKLjkl,JjB->ABKLkl', Bf, U2)
+    Bf = E('ABKLkl,CKk->ABCLl', Bf, U3.hconjugate('ij|k'))
+    Bf = E('ABCLl,DLl->ABCD', Bf, U4.hconjugate('ij|k'))
+    return Bf, Us
+
+
+def compress_A(A, Upack, mute=True):
+    """Site tensor A dressed with the isometries of compress_B (reference gauge2d.py:1469-1501)."""
+    E = gtn.einsum
+    U1, U2, U3, U4 = Upack
+    d = _boson_delta(A.shape[0])
+    Ix = E('KXj,XjI->KIj', U1.hconjugate('ij|k'), U3)
+    Iy = E('LYj,YjJ->LJj', U2.hconjugate('ij|k'), U4)
+    return E('ijkl,KIl,LJk,km,ln->IJKLijklmn', A, Ix, Iy, d, d)
+
+
+def compress_T(T, cutoff=64, mute=True):
+    """Final compression of T[I,J,K,L,i,j,k,l,m,n] along x, then y (reference gauge2d.py:1503-1585)."""
+    E = gtn.einsum
+    U, _ = _env_isometry(E('IJKLijklmn -> JKLjklmn Ii', T), 'abcdefgh|xy', E('IJKLijklmn -> Kk IJLijlmn', T),
+                         'xy|abcdefgh', 'Ii abcdefgh, abcdefgh Jj -> IiJj', 'Ii|Jj', cutoff)
+    Tf = E('IJKLijklmn,IiA,CKk->ACJLjlmn', T, U, U.hconjugate('ij|k'))
+    U, _ = _env_isometry(E('IKJLjlmn -> IKLlmn Jj', Tf), 'abcdef|xy', E('IKJLjlmn -> Ll IKJjmn', Tf), 'xy|abcdef',
+                         'Ii abcdef, abcdef Jj -> IiJj', 'Ii|Jj', cutoff)
+    return E('ACJLjlmn,JjB,DLl->ABCDmn', Tf, U, U.hconjugate('ij|k'))
+
+
+def tensor_from_AB(A, B, cutoff=64):
+    """tensor_preparation (reference gauge2d.py:22-66) from the A / B tensors on: B compression (1), (2), A compression,
+    T formation, T compression.  Returns (T, trace_error) with trace_error = |1 - z4 / z1| of the reference (:32, :57-59)."""
+    import numpy as _np
+    E = gtn.einsum
+    nphi = A.shape[0]
+    z1 = E("IJIJijij,jiji", B, A)
+    B = fcompress_B(B, cutoff)
+    B, Us = compress_B(B, cutoff)
+    A = compress_A(A, Us)
+    T = E('IJXYijklmn,XYKL->IJKLijklmn', A, B)
+    T = compress_T(T, cutoff)
+    z4 = E("IJIJij,ij", T, gtn.dense(_np.full((nphi, nphi), 1.0), statistics=(0, 0)))
+    return T, abs(1 - z4 / z1)
 
 
 def logZhotrg3dz(T1, T2, boundary_conditions="periodic"):

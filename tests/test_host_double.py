@@ -264,3 +264,15 @@ def test_rank_deficient_sectors_chi64_rank_certificate(gtn_host_trunc):
 
 def test_truncated_eig_vs_oracle_D16(gtn_host_trunc):
     GE.test_truncated_eig_vs_oracle_D16(gtn_host_trunc)
+
+
+# ---- initial-tensor compression pipeline (tests/test_tensor_prep.py) through the host double
+import test_tensor_prep as TP  # noqa: E402
+
+
+def test_tensor_preparation_vs_reference(gtn_host_trunc):
+    TP.run_pipeline(gtn_host_trunc)
+
+
+def test_bosonic_diagonal_einsum(gtn_host):
+    TP.test_gpu_bosonic_diagonal_einsum(gtn_host)
