@@ -1013,6 +1013,7 @@ __global__ void __launch_bounds__(NT)
 // scattered into T.
 constexpr int PK_MAXN = 128;
 constexpr int PK_T = 1024;
+static_assert(PK_T / 32 == 32 && PK_MAXN == 128, "the packed Cholesky kernel unrolls over 4 groups of 32 rows / columns");
 __device__ __forceinline__ int tri(int i) { return (i * (i + 1)) >> 1; }
 // G[i][j] of the Hermitian matrix held as packed lower triangle
 __device__ __forceinline__ c128 herm_get(const c128* Gp, int i, int j) {
@@ -1099,18 +1100,33 @@ __global__ void __launch_bounds__(PK_T)
       }
     }
     // G[i][j] -= v[i] conj(v[j]) / pivot over the free rows i >= j: one warp per row, lanes along the row
-    for (int i = warp; i < n; i += PK_T / 32) {
-      if ((done[i >> 5] >> (i & 31)) & 1u) continue;
+    // (both loops unrolled over the NW = 4 groups of 32 indices: the done masks are then addressed statically -- the
+    //  kernel is instruction-issue bound, ncu: 4.0 M warp instructions per matrix at l = 128, 13 % of them FP64 --
+    //  and the pivot column entries of this lane are loaded once per pivot instead of once per row)
+    c128 vj[NW];
+    bool fj[NW];
+#pragma unroll
+    for (int t = 0; t < NW; ++t) {
+      const int j = lane + 32 * t;
+      fj[t] = j < n && !((done[t] >> lane) & 1u);
+      if (fj[t]) vj[t] = v[j];
+    }
+#pragma unroll
+    for (int u = 0; u < NW; ++u) {
+      const int i = warp + 32 * u;                               // PK_T / 32 == 32 warps: rows warp, warp + 32, ...
+      if (i >= n || ((done[u] >> warp) & 1u)) continue;
       c128 a = v[i];
       a.re *= inv2; a.im *= inv2;
       c128* row = Gp + tri(i);
-      for (int j = lane; j <= i; j += 32) {
-        if ((done[j >> 5] >> (j & 31)) & 1u) continue;
-        const c128 b = v[j];
-        c128 g = row[j];
-        g.re -= a.re * b.re + a.im * b.im;
-        g.im -= a.im * b.re - a.re * b.im;
-        row[j] = g;
+#pragma unroll
+      for (int t = 0; t < NW; ++t) {
+        const int j = lane + 32 * t;
+        if (t <= u && j <= i && fj[t]) {
+          c128 g = row[j];
+          g.re -= a.re * vj[t].re + a.im * vj[t].im;
+          g.im -= a.im * vj[t].re - a.re * vj[t].im;
+          row[j] = g;
+        }
       }
     }
     __syncthreads();
@@ -1123,46 +1139,57 @@ __global__ void __launch_bounds__(PK_T)
   __syncthreads();
   const int r = rank;
   if (stamp) gtn_phase_clk[1] = clock64();
-  // ---- Li = L_r^{-1}, L_r[i][j] = G_j[perm[i]][perm[j]] * invs[j] (i >= j); one column per warp
-  c128* col = colbuf + warp * (n + 1);
-  for (int c0 = 0; c0 < r; c0 += PK_T / 32) {
-    const int c = c0 + warp;
-    const bool live = c < r;
-    for (int i = c0; i < r; ++i) {               // block-uniform trip count; columns c > i just idle
-      const int pi = perm[i];
+  // ---- X = L_r^{-1} IN PLACE, row by row: L_r[a][b] = G_b[perm[a]][perm[b]] * invs[b] (a >= b) sits at the packed slot
+  // of (perm[a], perm[b]); row a of X only needs row a of L_r and the rows of X above it,
+  //     X[a][b] = -invs[a] * sum_{j = b .. a-1} L_r[a][j] X[j][b]   (b < a),   X[a][a] = invs[a],
+  // so X[a][b] overwrites L_r[a][b] once every column has read row a (one barrier before, one after the stores).  All
+  // 128 columns advance together, 8 lanes per column splitting the sum: 128 sequential steps of ~n/16 multiply-adds
+  // per lane, instead of the 320 steps of one-column-per-warp forward substitution (4 blocks of 32 columns) this
+  // replaces (l = 128: 641 k cycles of the kernel's 1.48 M; profiles/r2d_whiten_probe_before.txt).
+  // X is stored so that herm_get(Gp, perm[a], perm[b]) returns it (conjugated when perm[a] < perm[b]).
+  {
+    const int b = tid >> 3, sub = tid & 7;
+    for (int a = 0; a < r; ++a) {
+      const int pa = perm[a];
       double sr = 0.0, si = 0.0;
-      if (live && i > c) {
-        for (int j = c + lane; j < i; j += 32) {
-          c128 l = herm_get(Gp, pi, perm[j]);
-          const double s_ = invs[j];
+      if (b < a) {
+        const int pb = perm[b];
+        for (int jj = b + sub; jj < a; jj += 8) {
+          const int pj = perm[jj];
+          c128 l = herm_get(Gp, pa, pj);
+          const double s_ = invs[jj];
           l.re *= s_; l.im *= s_;
-          const c128 x = col[j];
-          sr -= l.re * x.re - l.im * x.im;
-          si -= l.re * x.im + l.im * x.re;
+          const c128 x = herm_get(Gp, pj, pb);
+          sr += l.re * x.re - l.im * x.im;
+          si += l.re * x.im + l.im * x.re;
         }
       }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
+      for (int o = 4; o > 0; o >>= 1) {
         sr += __shfl_xor_sync(0xffffffffu, sr, o);
         si += __shfl_xor_sync(0xffffffffu, si, o);
       }
-      if (live && i >= c && lane == 0) {
-        if (i == c) sr += 1.0;
-        const double d = invs[i];
-        c128 o; o.re = sr * d; o.im = si * d;
-        col[i] = o;
+      __syncthreads();
+      if (sub == 0 && b <= a && b < r) {
+        const double d = invs[a];
+        c128 o;
+        if (b == a) { o.re = d; o.im = 0.0; }
+        else { o.re = -sr * d; o.im = -si * d; }
+        const int pb = perm[b];
+        if (pa >= pb) Gp[tri(pa) + pb] = o;
+        else { o.im = -o.im; Gp[tri(pb) + pa] = o; }
       }
-      __syncwarp();
+      __syncthreads();
     }
-    if (live) {
-      const int pc = perm[c];                    // T[i][perm[c]] = Li[i][c]
-      for (int i = c + lane; i < r; i += 32) {
-        const c128 v = col[i];
-        T* dst = Tout + int64_t(i) * n + pc;
+    // T[a][perm[b]] = X[a][b]
+    for (int e = tid; e < r * r; e += PK_T) {
+      const int a = e / r, bb = e - a * r;
+      if (bb <= a) {
+        const c128 v = herm_get(Gp, perm[a], perm[bb]);
+        T* dst = Tout + int64_t(a) * n + perm[bb];
         if constexpr (CPLX) { T t; t.re = v.re; t.im = v.im; Elem<CPLX>::st(dst, t); } else Elem<CPLX>::st(dst, v.re);
       }
     }
-    __syncwarp();
   }
   if (tid == 0) kept[blockIdx.x] = r;
   if (stamp) { gtn_phase_clk[2] = clock64(); gtn_phase_clk[3] = clock64(); }

@@ -9,7 +9,7 @@ from grassmanntn_b200 import _engine as E
 from grassmanntn_b200._cabi import check, lib
 from test_gpu_whiten import _gram
 dev = torch.device("cuda")
-for n in (48, 80, 96, 128, 160):
+for n in ([int(a) for a in sys.argv[1:]] or [48, 80, 96, 128, 160]):
     nb, ns = 4, 4
     Gs = [_gram(n, n, True, 10 + b, cond=1e4) for b in range(nb)]
     Gbuf = torch.zeros(nb * ns * n * n, dtype=torch.complex128, device=dev)
