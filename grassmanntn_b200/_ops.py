@@ -589,15 +589,30 @@ def _decompose_prepare(bt, nl, kind):
             if Mx.shape[0] != Mx.shape[1]:
                 _err("Error[SortedEig]: The input matrix is not Hermitian!")
             nrm2 = torch.zeros(2, dtype=torch.float64, device=dev)
-            # Hermiticity check ||M - M^H|| / ||M|| <= 1e-14 (reference :4316-4321), on device buffers
-            D = (Mx - Mx.conj().transpose(0, 1)).contiguous()
+            # Hermiticity check ||M - M^H|| / ||M|| <= 1e-14 (reference :4316-4321) on the library's own kernels:
+            # [M ; -M^H] (one copy, one conj-transposing sign+permute launch with scale -1), added by gtn_sum_slices
+            nn = Mx.shape[0]
+            two = torch.empty(2 * nn * nn, dtype=Mx.dtype, device=dev)
+            two[: nn * nn].copy_(Mx.reshape(-1))
+
+            def build_ct(nn=nn, cplx=Mx.dtype == torch.complex128):
+                legs = [lin_leg(nn, nn, 1), lin_leg(nn, 1, nn)]
+                return PermutePlan([build_job(legs, conj=cplx, in_order=[0, 1], out_order=[1, 0])])
+            _cached(("eig_herm_ct", nn, str(Mx.dtype)), build_ct).run(two[: nn * nn], two[nn * nn:], scale=-1.0)
+            D = torch.empty(nn * nn, dtype=Mx.dtype, device=dev)
+            if nn * nn % 2 and Mx.dtype != torch.complex128:        # (gtn_sum_slices needs 16-byte aligned slices)
+                D = two[: nn * nn] + two[nn * nn:]
+            else:
+                check(lib.gtn_sum_slices(_ptr(two), _ptr(D), nn * nn, 2, dtype_code(Mx.dtype), _stream()), "gtn_sum_slices")
+                count()
             check(lib.gtn_sumsq(_ptr(D), D.numel(), dtype_code(D.dtype), _ptr(nrm2[0:]), 0, _stream()), "gtn_sumsq")
             check(lib.gtn_sumsq(_ptr(Mx), Mx.numel(), dtype_code(Mx.dtype), _ptr(nrm2[1:]), 0, _stream()), "gtn_sumsq")
             count(2)
             dn, mn = [math.sqrt(v) for v in nrm2.cpu().tolist()]
             if mn >= NUMER_CUTOFF and dn / mn > NUMER_CUTOFF:
                 _err("Error[SortedEig]: The input matrix is not Hermitian!")
-    return dict(locals())
+    return dict(bt=bt, nl=nl, this_fmt=this_fmt, Rl=Rl, Cl=Cl, fR=fR, fC=fC, layR=layR, layC=layC, sectors=sectors,
+                rows=rows, cols=cols, alpha=alpha, beta=beta, Q=Q, fpos_R=fpos_R, fpos_C=fpos_C, dev=dev, mats=mats)
 
 
 def _decompose_finish(ctx, usv, cutoff, kind, rule, spec=False):

@@ -113,6 +113,53 @@ def from_host(h, device=None):
     return dense._from_bt(bt, h.encoder or "canonical")
 
 
+def stream_steps(host_inputs, step, prepare=None, n_out=2):
+    """Run `step(T) -> (T', value)` over a sequence of HostTensors, STREAMING: the H2D copy of input i + 1 and the D2H
+    copy of result i - 1 overlap the computation of step i (one copy-in stream, the caller's current stream for the
+    computation, one copy-out stream; inputs prefetched one step ahead, `n_out` pinned result buffers in rotation).
+    Every step still moves its own input from pinned host memory and its own result back -- only the waiting is gone
+    (PCIe is full duplex: 2 x 2 GiB per chi = 128 step hide behind the 0.36 s of kernels).
+    prepare(T) (optional) is applied to every uploaded tensor before `step` (e.g. restoring shard metadata).
+    Returns [(HostTensor of T', value)] in order; the HostTensors of steps older than n_out are reused."""
+    cur = torch.cuda.current_stream()
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+    outs = [None] * n_out
+    out_done = [None] * n_out
+    results = []
+    n = len(host_inputs)
+
+    def upload(i):
+        with torch.cuda.stream(s_in):
+            X = from_host(host_inputs[i])
+            ev = torch.cuda.Event()
+            ev.record(s_in)
+        return X, ev
+    nxt = upload(0) if n else None
+    for i in range(n):
+        X, ev = nxt
+        nxt = upload(i + 1) if i + 1 < n else None          # prefetch: overlaps this step's kernels
+        cur.wait_event(ev)
+        bt_in = _bt_of(X)[0]
+        bt_in.buf.record_stream(cur)
+        if prepare is not None:
+            prepare(X)
+        Y, val = step(X)
+        done = torch.cuda.Event()
+        done.record(cur)
+        k = i % n_out
+        if out_done[k] is not None:
+            out_done[k].synchronize()                        # the pinned buffer's previous copy-out has landed
+        s_out.wait_event(done)
+        with torch.cuda.stream(s_out):
+            outs[k] = to_host(Y, out=outs[k])
+            _bt_of(Y)[0].buf.record_stream(s_out)
+            out_done[k] = torch.cuda.Event()
+            out_done[k].record(s_out)
+        results.append((outs[k], val))
+    s_out.synchronize()
+    return results
+
+
 def save_tensor(path, T, **meta):
     """Write T (dense or block) and JSON-serialisable metadata to `path` (.npz), atomically."""
     bt, kind, encoder = _bt_of(T)

@@ -98,3 +98,32 @@ def test_gpu_checkpoint_and_resume(gtn, tmp_path, method, cut):
     assert [r["process"] for r in recs][0] == "_ini" and len(recs) == 4
     with pytest.raises(ValueError):
         g.coarse_grain(T0, cgsteps=3, dcut=8, method=method, checkpoint_dir=d, resume=True)
+
+
+@pytest.mark.gpu
+def test_gpu_stream_steps_equals_serial(gtn):
+    """checkpoint.stream_steps (H2D of step i + 1 and D2H of step i - 1 overlapping the kernels of step i, three
+    streams, rotating pinned buffers) returns what the same steps give one after the other"""
+    import torch
+    from grassmanntn_b200 import checkpoint as ck
+    g = gtn.gauge2d
+    T = g.zcap(g.load_initial_tensor()).toblock()
+    chain = []
+    for _ in range(4):                                   # four different inputs: the first tensors of the chi = 16 chain
+        chain.append(ck.to_host(T))
+        T, _ = g.trg(T, 16)
+    torch.cuda.synchronize()
+    serial = []
+    for h in chain:
+        Y, tn = g.trg(ck.from_host(h), 16)
+        serial.append((float(tn), float(Y.norm), Y._bt.key()))
+    res = ck.stream_steps(chain, lambda X: g.trg(X, 16), n_out=4)
+    assert len(res) == 4
+    for (h, tn), (tn_s, nrm_s, key_s) in zip(res, serial):
+        assert abs(float(tn) - tn_s) <= 1e-12 * tn_s
+        Y = ck.from_host(h)
+        assert Y._bt.key() == key_s and abs(float(Y.norm) - nrm_s) <= 1e-12 * nrm_s
+    # rotation with fewer pinned buffers than steps: the last results are intact
+    res2 = ck.stream_steps(chain, lambda X: g.trg(X, 16), n_out=2)
+    assert abs(float(res2[-1][1]) - serial[-1][0]) <= 1e-12 * serial[-1][0]
+    assert abs(float(ck.from_host(res2[-1][0]).norm) - serial[-1][1]) <= 1e-12 * serial[-1][1]
