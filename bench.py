@@ -750,7 +750,7 @@ def einsum_sweep(gtn, torch, O):
         if gm:
             ent["gemm_TFLOPs"] = sum(v["flops"] for v in gm) / (sum(v["ms"] for v in gm) * 1e-3) / 1e12
             ent["gemm_family"] = [k for k in pr if k.startswith("gemm")]
-        res[sub] = ent
+        res[sub if sub not in res else "%s %s" % (sub, "x".join(str(x) for x in ops[0][0]))] = ent
     return res
 
 

@@ -7,9 +7,10 @@ chi = 128..256 runs resumable and comparable:
 * `save_tensor` / `load_tensor` -- one `.npz` per tensor holding the parity-blocked device buffer exactly as it
   lives in HBM (`_engine.BT`: one contiguous buffer + block offsets; only the stored, i.e. even-parity, blocks),
   its statistics / even / odd dimensions / format, the container kind (dense | block, encoder) and free-form
-  metadata.  Loading restores the same tensor bits; the continuation agrees with an uninterrupted run to rounding
-  (the adaptive state of the truncated SVD -- iteration counts, recorded graphs -- is not checkpointed, and the
-  Jacobi rotation order is not bitwise reproducible run to run).
+  metadata.  Loading restores the same tensor bits; the continuation agrees with an uninterrupted run to rounding:
+  the kernels themselves are bitwise reproducible (tests/test_gpu_edges.py::test_chain_is_bitwise_reproducible), but
+  the adaptive state of the truncated SVD -- iteration counts, recorded graphs -- is not checkpointed, so a resumed
+  run may iterate a different number of times than the uninterrupted one.
 * `RunLog` -- JSON-lines file, one record per coarse-graining step with the columns example.py prints
   (reference example.py:158-196): process, volume, F (real, imag), shape, trace error, Tnorm, seconds.
 * `gauge2d.coarse_grain(..., log=, checkpoint_dir=, resume=)` uses both.
@@ -101,13 +102,18 @@ def to_host(T, out=None, pinned=True):
     return h
 
 
-def from_host(h, device=None):
-    """HostTensor -> device tensor of the container kind it was taken from (one asynchronous H2D copy)."""
+def from_host(h, device=None, out_buf=None):
+    """HostTensor -> device tensor of the container kind it was taken from (one asynchronous H2D copy; into the device
+    buffer `out_buf` when given -- a streaming caller rotates its own buffers instead of allocating per step)."""
     from . import block, dense
     bt = _engine.BT(h.stats, h.e, h.o, h.dtype, h.fmt)
     bt.off, bt.zero = dict(h.off), set(h.zero)
     dev = device if device is not None else _engine.require_cuda()
-    bt.buf = h.buf.to(dev, non_blocking=True)
+    if out_buf is not None and out_buf.numel() == h.buf.numel() and out_buf.dtype == h.buf.dtype:
+        out_buf.copy_(h.buf, non_blocking=True)
+        bt.buf = out_buf
+    else:
+        bt.buf = h.buf.to(dev, non_blocking=True)
     if h.kind == "block":
         return block._from_bt(bt, h.shape)
     return dense._from_bt(bt, h.encoder or "canonical")
@@ -127,10 +133,19 @@ def stream_steps(host_inputs, step, prepare=None, n_out=2):
     out_done = [None] * n_out
     results = []
     n = len(host_inputs)
+    dev_in = [None, None]                    # two device input buffers in rotation (no allocation per step)
+    in_free = [None, None]                   # event: the step that consumed the buffer has finished
 
     def upload(i):
+        k = i % 2
+        h = host_inputs[i]
         with torch.cuda.stream(s_in):
-            X = from_host(host_inputs[i])
+            if dev_in[k] is None or dev_in[k].numel() != h.buf.numel() or dev_in[k].dtype != h.buf.dtype:
+                dev_in[k] = torch.empty(h.buf.numel(), dtype=h.buf.dtype, device=_engine.require_cuda())
+                dev_in[k].record_stream(cur)
+            if in_free[k] is not None:
+                s_in.wait_event(in_free[k])
+            X = from_host(h, out_buf=dev_in[k])
             ev = torch.cuda.Event()
             ev.record(s_in)
         return X, ev
@@ -139,13 +154,12 @@ def stream_steps(host_inputs, step, prepare=None, n_out=2):
         X, ev = nxt
         nxt = upload(i + 1) if i + 1 < n else None          # prefetch: overlaps this step's kernels
         cur.wait_event(ev)
-        bt_in = _bt_of(X)[0]
-        bt_in.buf.record_stream(cur)
         if prepare is not None:
             prepare(X)
         Y, val = step(X)
         done = torch.cuda.Event()
         done.record(cur)
+        in_free[i % 2] = done
         k = i % n_out
         if out_done[k] is not None:
             out_done[k].synchronize()                        # the pinned buffer's previous copy-out has landed

@@ -27,8 +27,13 @@ __device__ __forceinline__ double block_sum(double v) {
   return r;   // valid in thread 0
 }
 
+constexpr int SUMSQ_SLOTS = 16, SUMSQ_MAXGRID = 148 * 8;
+__device__ double g_sumsq_part[SUMSQ_SLOTS][SUMSQ_MAXGRID];
+__device__ unsigned int g_sumsq_count[SUMSQ_SLOTS];
+
 __global__ void __launch_bounds__(RT) sumsq_kernel(const double* __restrict__ x, int64_t ndoubles,
-                                                   double* __restrict__ out) {
+                                                   double* __restrict__ out, double* __restrict__ part,
+                                                   unsigned int* __restrict__ counter) {
   double acc = 0;
   const int64_t stride = int64_t(gridDim.x) * RT;
   const int64_t n2 = ndoubles >> 1;
@@ -39,7 +44,24 @@ __global__ void __launch_bounds__(RT) sumsq_kernel(const double* __restrict__ x,
   }
   if ((ndoubles & 1) && blockIdx.x == 0 && threadIdx.x == 0) acc += x[ndoubles - 1] * x[ndoubles - 1];
   acc = block_sum(acc);
-  if (threadIdx.x == 0) atomicAdd(out, acc);
+  // Deterministic completion: every CTA parks its partial sum, the CTA that arrives last adds all of them in index
+  // order and accumulates into `out` -- the result does not depend on the order in which the CTAs finish (an
+  // atomicAdd per CTA made the last bits of Tnorm, and with them every later step, differ from run to run).  The
+  // scratch belongs to a slot chosen by the launching stream, so launches on different streams do not share one.
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+    part[blockIdx.x] = acc;
+    __threadfence();
+    last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  double tot = 0;
+  for (unsigned b = threadIdx.x; b < gridDim.x; b += RT) tot += *reinterpret_cast<volatile double*>(part + b);
+  // (fixed assignment of partials to threads and a fixed reduction tree: order independent of timing)
+  tot = block_sum(tot);
+  if (threadIdx.x == 0) { *out += tot; *counter = 0u; }
 }
 
 // sum of |x_i| (complex modulus for GTN_C128): the reference's Grassmann-evenness test is an L1 mean
@@ -206,7 +228,18 @@ extern "C" int gtn_sumsq(const void* x, int64_t n, int dtype, double* out_dev, i
   if (zero_first) cudaMemsetAsync(out_dev, 0, sizeof(double), s);
   if (n <= 0) return GTN_OK;
   const int64_t nd = dtype == GTN_C128 ? 2 * n : n;
-  sumsq_kernel<<<grid_for(nd / 2 + 1), RT, 0, s>>>((const double*)x, nd, out_dev);
+  // scratch slot of this stream (launches on one stream are ordered; different streams get different slots unless
+  // more than SUMSQ_SLOTS streams hash alike)
+  static double* part_base = nullptr;
+  static unsigned int* count_base = nullptr;
+  if (!part_base) {
+    cudaGetSymbolAddress((void**)&part_base, g_sumsq_part);
+    cudaGetSymbolAddress((void**)&count_base, g_sumsq_count);
+  }
+  const uintptr_t h = reinterpret_cast<uintptr_t>(stream);
+  const int slot = (int)(((h >> 4) ^ (h >> 12) ^ (h >> 20)) % SUMSQ_SLOTS);
+  sumsq_kernel<<<grid_for(nd / 2 + 1), RT, 0, s>>>((const double*)x, nd, out_dev, part_base + slot * SUMSQ_MAXGRID,
+                                                   count_base + slot);
   return (int)cudaGetLastError();
 }
 

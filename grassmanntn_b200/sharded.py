@@ -14,7 +14,7 @@ contiguous range of the even and of the odd block indices).  Everything a TRG st
         Yh = G W^H   (l x p)   = sum_r G[:, C_r] W[:, C_r]^H        all-reduce, then orthonormalised on every rank
         Zh = Qh W    (l x q_r)   local columns;  its l x l Gram matrix = sum_r Zh_r Zh_r^H      all-reduce
         B  = Qh W    (l x q_r)   local;  the l x q rows are all-gathered, the one-sided Jacobi SVD of problem b runs
-                                 on rank b % W (rotation order is timing dependent: one owner, not replicas) and
+                                 on rank b % W (one owner per problem: W problems in flight instead of W replicas of each) and
                                  Ub, s, Vh are broadcast; every rank keeps its columns of Vh
         certificate rows  Vk W^H - S Uh  (l x p): partial sums over columns, all-reduce
     U (p x l) comes out replicated, V (l x q_r) sharded like the input.  Per iteration 2 x l x (p + l) numbers cross
@@ -267,7 +267,7 @@ class ShardedTruncPlan(E._TruncPlan):
         """orthonormal rows from the one-sided Jacobi SVD of the panels (no Gram matrix: full dynamic range).  The
         replicated l x p panels are decomposed by their owner ranks (problem b on rank b % W); the column-sharded
         l x q_r panels are first all-gathered (l x q numbers: isometry-sized).  The result is broadcast, every rank
-        keeps its columns -- one owner, not replicas, because the rotation order of the kernel is timing dependent."""
+        keeps its columns (one owner per panel, so different panels are decomposed concurrently on different ranks)."""
         ws, w, r = self.ws, self.w, rank()
         dt, dev = self.dt, self.dev
         full, shapes = {}, []

@@ -235,6 +235,32 @@ def test_truncated_eig_vs_oracle_D16(gtn):
     assert np.abs(_np(R) - r.data).max() <= 1e-9 * np.abs(r.data).max()
 
 
+def test_chain_is_bitwise_reproducible(gtn):
+    """Two executions of the same chain from the same engine state give the same BITS (round-1 review: the Jacobi
+    rotation order depended on atomics timing and the norm on the order of atomicAdds).  Now: the dead-row threshold of
+    the Jacobi kernels is double buffered by round parity, the sum of squares is completed in index order by the last
+    CTA, split-K slices are added in index order."""
+    import torch
+    from grassmanntn_b200 import _engine as E, gauge2d as g
+    def chain():
+        for d in (E._trunc_iters_hint, E._trunc_rate, E._trunc_fail, E._trunc_probe, E._trunc_robust):
+            d.clear()
+        E.drop_graphs()
+        T = g.zcap(g.load_initial_tensor()).toblock()
+        norms = []
+        for _ in range(5):
+            T, n = g.trg(T, 32)[:2]
+            norms.append(float(n))
+        for _ in range(2):
+            T, n = g.atrg2dy(T, T, 32)[:2]
+            norms.append(float(n))
+        return norms, T._bt.buf.clone()
+    n1, b1 = chain()
+    n2, b2 = chain()
+    assert n1 == n2, (n1, n2)
+    assert torch.equal(b1, b2)
+
+
 def test_graph_replay_equals_eager_launches(gtn):
     """the steady-state truncated-SVD schedule replayed as a CUDA graph must give what the same launches
     give one by one (same kernels, same order): Tnorm of a TRG chain on the Z2 tensor, both ways"""
