@@ -90,6 +90,13 @@ def _load():
         "gtn_workspace_bytes": (i64, [i32, i32, i32, vp, vp, vp]),
         "gtn_sector_svd_trunc": (i32, [vp, vp, vp, i32, i32, vp, dbl, vp, vp, vp, vp, vp, i64, vp, vp]),
         "gtn_sector_eigh_trunc": (i32, [vp, vp, vp, i32, i32, vp, dbl, vp, vp, vp, vp, vp, vp, i64, vp, vp]),
+        "gtn_comm_available": (i32, []),
+        "gtn_comm_unique_id": (i32, [vp]),
+        "gtn_comm_init": (i32, [vp, i32, i32, vp]),
+        "gtn_comm_destroy": (i32, [vp]),
+        "gtn_allreduce": (i32, [vp, vp, i64, i32, i32, vp]),
+        "gtn_allgather": (i32, [vp, vp, vp, i64, i32, vp]),
+        "gtn_broadcast": (i32, [vp, vp, i64, i32, i32, vp]),
         "gtn_version": (i32, []),
         "gtn_build_arch": (C.c_char_p, []),
     }

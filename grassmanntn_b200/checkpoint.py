@@ -119,6 +119,9 @@ def from_host(h, device=None, out_buf=None):
     return dense._from_bt(bt, h.encoder or "canonical")
 
 
+_stream_outs = {}
+
+
 def stream_steps(host_inputs, step, prepare=None, n_out=2):
     """Run `step(T) -> (T', value)` over a sequence of HostTensors, STREAMING: the H2D copy of input i + 1 and the D2H
     copy of result i - 1 overlap the computation of step i (one copy-in stream, the caller's current stream for the
@@ -126,10 +129,12 @@ def stream_steps(host_inputs, step, prepare=None, n_out=2):
     Every step still moves its own input from pinned host memory and its own result back -- only the waiting is gone
     (PCIe is full duplex: 2 x 2 GiB per chi = 128 step hide behind the 0.36 s of kernels).
     prepare(T) (optional) is applied to every uploaded tensor before `step` (e.g. restoring shard metadata).
-    Returns [(HostTensor of T', value)] in order; the HostTensors of steps older than n_out are reused."""
+    Returns [(HostTensor of T', value)] in order; the HostTensors of steps older than n_out are reused (also by the
+    next call: copy out what has to outlive it)."""
     cur = torch.cuda.current_stream()
     s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
-    outs = [None] * n_out
+    # pinned result buffers are kept between calls (page-locking 2 GiB takes longer than the step it would hide)
+    outs = _stream_outs.setdefault(n_out, [None] * n_out)
     out_done = [None] * n_out
     results = []
     n = len(host_inputs)

@@ -39,6 +39,7 @@ from . import _cabi, _engine as E
 from ._cabi import check, count, lib
 from ._engine import BT, FERMI, PermutePlan, _cached, _ptr, _row_strides, _stream, build_job, dtype_code, lin_leg
 
+FUSED_ALLREDUCE = bool(int(__import__("os").environ.get("GTN_FUSED_ALLREDUCE", "1")))
 BIG_PREROTATE = bool(int(__import__("os").environ.get("GTN_BIG_PREROTATE", "1")))
 BIG_PREROTATE_MIN_L = 80    # (gtn_gram_rotate serves l <= 80 on the single-GPU path)
 GATHER_MAX_DIM = 16384     # largest sector (smaller side) the owner-gathered fallback decomposes on one GPU
@@ -61,25 +62,68 @@ def _nbytes(t):
     return t.numel() * t.element_size()
 
 
-def all_reduce_(t):
+# ---- collectives: the library's own NCCL wrappers (include/gtn_b200.h gtn_comm_*, csrc/gtn_comm.cu) on the caller's
+#      stream when the process group runs on NCCL; torch.distributed otherwise (gloo: the CPU tests of the host logic)
+NATIVE_COMM = bool(int(__import__("os").environ.get("GTN_NATIVE_COMM", "1")))
+_native = {"comm": None, "tried": False}
+
+
+def native_comm():
+    """the C-ABI communicator of this process (created on first use: rank 0's unique id travels through the existing
+    torch.distributed group, the host's own means), or None when the group is not on NCCL / GPUs"""
+    if _native["tried"]:
+        return _native["comm"]
+    _native["tried"] = True
+    if not (NATIVE_COMM and world() > 1 and dist.get_backend() == "nccl" and lib.gtn_comm_available()):
+        return None
+    import ctypes as C
+    dev = torch.device("cuda", torch.cuda.current_device())
+    idbuf = (C.c_char * 128)()
+    if rank() == 0:
+        check(lib.gtn_comm_unique_id(idbuf), "gtn_comm_unique_id")
+    t = torch.frombuffer(bytearray(bytes(idbuf)), dtype=torch.uint8).to(dev)
+    dist.broadcast(t, src=0)
+    raw = bytes(t.cpu().numpy().tobytes())
+    comm = C.c_void_p()
+    check(lib.gtn_comm_init(raw, rank(), world(), C.byref(comm)), "gtn_comm_init")
+    _native["comm"] = comm
+    return comm
+
+
+def all_reduce_(t, op=0):
+    """in-place sum (op 0) / max (1) / min (2) over the ranks"""
     if world() > 1:
+        comm = native_comm()
         with E.prof_region("nccl_allreduce", 0, _nbytes(t)):
-            dist.all_reduce(_real(t))
+            if comm is not None and t.dtype in (torch.float64, torch.complex128) and t.is_contiguous():
+                check(lib.gtn_allreduce(comm, _ptr(t), t.numel(), dtype_code(t.dtype), op, _stream()), "gtn_allreduce")
+            else:
+                dist.all_reduce(_real(t), op=(dist.ReduceOp.SUM, dist.ReduceOp.MAX, dist.ReduceOp.MIN)[op])
         STATS["allreduce_bytes"] += _nbytes(t)
         STATS["collectives"] += 1
     return t
 
 
 def _all_gather(out, mine):
+    comm = native_comm()
     with E.prof_region("nccl_allgather", 0, _nbytes(out)):
-        dist.all_gather_into_tensor(_real(out), _real(mine))
+        if comm is not None and mine.dtype in (torch.float64, torch.complex128) and mine.is_contiguous() \
+                and out.is_contiguous():
+            check(lib.gtn_allgather(comm, _ptr(mine), _ptr(out), mine.numel(), dtype_code(mine.dtype), _stream()),
+                  "gtn_allgather")
+        else:
+            dist.all_gather_into_tensor(_real(out), _real(mine))
     STATS["allgather_bytes"] += _nbytes(out)
     STATS["collectives"] += 1
 
 
 def _broadcast(t, src):
+    comm = native_comm()
     with E.prof_region("nccl_broadcast", 0, _nbytes(t)):
-        dist.broadcast(_real(t), src=src)
+        if comm is not None and t.dtype in (torch.float64, torch.complex128) and t.is_contiguous():
+            check(lib.gtn_broadcast(comm, _ptr(t), t.numel(), dtype_code(t.dtype), src, _stream()), "gtn_broadcast")
+        else:
+            dist.broadcast(_real(t), src=src)
     STATS["broadcast_bytes"] += _nbytes(t)
     STATS["collectives"] += 1
 
@@ -237,6 +281,7 @@ class ShardedTruncPlan(E._TruncPlan):
             self.jmaxL = max(L_[b] for b in self.mine)
             self.jmaxQ = max(self.Qfull[b] for b in self.mine)
         self.jacobi_ok = torch.ones(1, dtype=torch.float64, device=dev)
+        self._fused_ok = None                        # fused GEMM + all-reduce over peer memory: None = not tried yet
         self.graphable = False                       # collectives between the launches: eager schedule
         torch.cuda.current_stream().synchronize() if dev.type == "cuda" else None
 
@@ -250,17 +295,66 @@ class ShardedTruncPlan(E._TruncPlan):
         a1 = ws.off(handles[-1]) + ws.items[handles[-1]][1] * ws.items[handles[-1]][2]
         all_reduce_(ws.buf[a0:a1])
 
+    def _gemm_allreduce(self, ha, hb, hc):
+        """hc_b = sum over ranks of ha_b . hb_b (the l x p panels whose contracted index is the sharded column index).
+        Fused path (NCCL group, <= 8 ranks, peer access): ONE grouped GEMM launch whose epilogue stores this rank's
+        partial panels into slot `rank` of EVERY rank's staging buffer over NVLink (gtn_grouped_gemm_bcast on torch
+        symmetric memory: the stores overlap the DMMA work of the other resident CTAs), a device-side barrier, and
+        gtn_sum_slices adding the W slots in rank order -- deterministic and bit-identical on all ranks, which an
+        atomics-based reduction would not be.  Otherwise: local GEMM, then an NCCL all-reduce of the panels."""
+        ws, w, r = self.ws, self.w, rank()
+        if w > 1 and FUSED_ALLREDUCE and self._fused_ok is not False:
+            from . import parallel
+            span = ws.off(hc[-1]) + ws.items[hc[-1]][1] * ws.items[hc[-1]][2] - ws.off(hc[0])
+            nbytes = w * span * ws.buf.element_size()
+            if self._fused_ok is None:
+                err = None
+                try:
+                    ok_ = dist.get_backend() == "nccl" and w <= parallel.MAX_PEERS
+                    if ok_:
+                        parallel._symm_output(nbytes, ws.buf.device)
+                except Exception as exc:             # no peer access / symmetric memory on this system
+                    ok_, err = False, exc
+                flag = torch.tensor([1.0 if ok_ else 0.0], dtype=torch.float64, device=ws.buf.device)
+                all_reduce_(flag, op=2)              # all ranks take the same path
+                self._fused_ok = bool(flag.item() > 0)
+                if not self._fused_ok:
+                    parallel._symm.pop(nbytes, None)
+            if self._fused_ok:
+                t, hdl, ptrs = parallel._symm_output(nbytes, ws.buf.device)
+                groups = []
+                for a, b, c in zip(ha, hb, hc):
+                    _, m, k = ws.items[a]
+                    _, _, n = ws.items[b]
+                    groups.append(dict(a_off=ws.off(a), b_off=ws.off(b), c_off=r * span + ws.off(c) - ws.off(hc[0]),
+                                       lda=k, ldb=n, ldc=n, m=m, n=n, k=k))
+                key = ("shard_fused", str(ws.dtype), r, w, tuple(tuple(sorted(g.items())) for g in groups))
+                plan = _cached(key, lambda: E.GemmPlan(groups, ws.dtype, config=0))
+                hdl.barrier(channel=0)               # every peer has summed the previous contents of its buffer
+                with E.prof_region("grouped_gemm_bcast", 1, plan.bytes, plan.flops):
+                    check(lib.gtn_grouped_gemm_bcast(_ptr(ws.buf), _ptr(ws.buf), ptrs, w, dtype_code(ws.dtype),
+                                                     _ptr(plan.dev), plan.n, plan.tiles, _stream()),
+                          "gtn_grouped_gemm_bcast")
+                hdl.barrier(channel=1)               # every rank's partial panels have landed here
+                dst = ws.buf[ws.off(hc[0]): ws.off(hc[0]) + span]
+                with E.prof_region("sum_slices", 1, (w + 1) * span * ws.buf.element_size()):
+                    check(lib.gtn_sum_slices(_ptr(t), _ptr(dst), span, w, dtype_code(ws.dtype), _stream()),
+                          "gtn_sum_slices")
+                STATS["fused_allreduce_bytes"] = STATS.get("fused_allreduce_bytes", 0) + (w - 1) * span * ws.buf.element_size()
+                STATS["fused_allreduces"] = STATS.get("fused_allreduces", 0) + 1
+                return
+        E._ws_gemm(ws, list(zip(ha, hb, hc)))
+        self._reduce_handles(hc)
+
     def start(self, passes, robust=False):
-        E._ws_gemm(self.ws, list(zip(self.hG, self.hWh, self.hYh)))
-        self._reduce_handles(self.hYh)
+        self._gemm_allreduce(self.hG, self.hWh, self.hYh)
         self.orth(self.hYh, self.hQh, "p", passes, robust)
 
     def iterate(self, last, robust=False):
         ws = self.ws
         E._ws_gemm(ws, list(zip(self.hQh, self.hW, self.hZh)))
         self.orth(self.hZh, self.hPh, "q", 1, robust)
-        E._ws_gemm(ws, list(zip(self.hPh, self.hWh, self.hYh)))
-        self._reduce_handles(self.hYh)
+        self._gemm_allreduce(self.hPh, self.hWh, self.hYh)
         self.orth(self.hYh, self.hQh, "p", 2 if last else 1, robust)
 
     def _orth_robust(self, src, dst, side, passes):
@@ -411,9 +505,7 @@ class ShardedTruncPlan(E._TruncPlan):
                     Ub.view(-1).copy_(tmp)
         # ---- Ub, s, Vh from the owners
         if w > 1:
-            all_ok = self.jacobi_ok.clone()
-            dist.all_reduce(all_ok, op=dist.ReduceOp.MIN)
-            self.jacobi_ok.copy_(all_ok)
+            all_reduce_(self.jacobi_ok, op=2)
             for b in range(nb):
                 src = b % w
                 for t in (jws.view(self.jU[b]), jws.view(self.jV[b]), self.s_dev[self.soff[b]: self.soff[b] + self.L_[b]]):
@@ -426,8 +518,7 @@ class ShardedTruncPlan(E._TruncPlan):
         E._ws_ctranspose(ws, list(zip(self.hUb, self.hUbH)))
         E._ws_gemm(ws, list(zip(self.hUbH, self.hQh, self.hUh)))            # Uh = Ub^H Qh  (l x p), replicated
         # certificate rows  Eh_i = v_i^H W^H - s_i u_i^H  (l x p): partial sums over the local columns, then all-reduce
-        E._ws_gemm(ws, list(zip(self.hVk, self.hWh, self.hXh)))
-        self._reduce_handles(self.hXh)
+        self._gemm_allreduce(self.hVk, self.hWh, self.hXh)
         for b in range(nb):
             ws.view(self.hD[b]).diagonal().copy_(self.s_dev[self.soff[b]: self.soff[b] + self.L_[b]])
         E._ws_gemm(ws, list(zip(self.hD, self.hUh, self.hXh)), alpha=-1.0, beta=1.0)
@@ -443,7 +534,7 @@ class ShardedTruncPlan(E._TruncPlan):
         self.out_dev[2 * sL + nb].fill_(0.0)
         self.out_dev[2 * sL + nb + 1: 2 * sL + nb + 2].copy_(self.jacobi_ok)
         if w > 1:
-            dist.broadcast(self.out_dev, src=0)         # one decision for all ranks, whatever the last bits say
+            _broadcast(self.out_dev, 0)                 # one decision for all ranks, whatever the last bits say
         self.out_host.copy_(self.out_dev, non_blocking=True)
 
     def read(self):

@@ -344,6 +344,25 @@ int gtn_scale(void* x, int64_t n, int dtype, double s_re, double s_im, void* str
 int gtn_odd_checker(const void* x, int64_t rows, int64_t cols, int dtype, double* out_dev,
                     void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Collectives of the sharded coarse-graining step: thin wrappers of NCCL over NVLink /
+ * NVSwitch, bound at run time (dlopen of libnccl.so.2; gtn_comm_available() = 0 and GTN_ERR_UNSUPPORTED without it).
+ * The reference has no distributed mode; the sharded step (grassmanntn_b200/sharded.py) all-reduces l x p sketch
+ * panels and l x l Gram matrices, all-gathers the isometries, broadcasts the owners' small SVDs.
+ * One communicator per process (one process per GPU): rank 0 calls gtn_comm_unique_id, the 128-byte id reaches the
+ * other ranks by the host's own means, every rank calls gtn_comm_init.  Counts are ELEMENTS of `dtype` (GTN_C128 is
+ * sent as two doubles per element; only the sum is defined on it).  op: 0 sum, 1 max, 2 min.  All calls are enqueued on
+ * `stream`; buffers are device memory.  NCCL failures are returned as 1000 + ncclResult_t.
+ * ------------------------------------------------------------------------------------------ */
+#define GTN_COMM_ID_BYTES 128
+int gtn_comm_available(void);
+int gtn_comm_unique_id(void* id_out_128_bytes);
+int gtn_comm_init(const void* id_128_bytes, int rank, int world, void** comm_out);
+int gtn_comm_destroy(void* comm);
+int gtn_allreduce(void* comm, void* buf, int64_t count, int dtype, int op, void* stream);         /* in place */
+int gtn_allgather(void* comm, const void* send, void* recv, int64_t count_per_rank, int dtype, void* stream);
+int gtn_broadcast(void* comm, void* buf, int64_t count, int dtype, int root, void* stream);        /* in place */
+
 /* Library / device introspection (no device work). */
 int gtn_version(void);
 const char* gtn_build_arch(void);

@@ -89,6 +89,24 @@ def _worker(rank, world, port, q):
             rows.append((abs(Tn - aref[i, 0]) / aref[i, 0], abs(F - complex(aref[i, 1], aref[i, 2])) / abs(F)))
         out["atrg"] = rows
         out["stats"] = dict(sharded.STATS)
+        # ---- the C-ABI collectives (gtn_comm_*: what the chains above ran on) against torch.distributed
+        assert sharded.native_comm() is not None, "the NCCL wrappers of libgtn_b200.so were not used"
+        gen = torch.Generator(device="cpu"); gen.manual_seed(100 + rank)
+        x = torch.view_as_complex(torch.randn(1000, 2, generator=gen, dtype=torch.float64)).cuda()
+        a, b = x.clone(), x.clone()
+        sharded.all_reduce_(a)
+        dist.all_reduce(torch.view_as_real(b))
+        assert torch.equal(a, b)
+        ga = torch.empty(world * 1000, dtype=torch.complex128, device="cuda"); gb = torch.empty_like(ga)
+        sharded._all_gather(ga, x)
+        dist.all_gather_into_tensor(torch.view_as_real(gb), torch.view_as_real(x))
+        assert torch.equal(ga, gb)
+        c = x.clone(); sharded._broadcast(c, 1)
+        d = x.clone(); dist.broadcast(torch.view_as_real(d), src=1)
+        assert torch.equal(c, d)
+        m = torch.tensor([float(rank + 1)], dtype=torch.float64, device="cuda")
+        sharded.all_reduce_(m, op=2)
+        assert float(m.item()) == 1.0
         q.put((rank, out))
     finally:
         dist.destroy_process_group()
