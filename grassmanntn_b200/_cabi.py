@@ -76,6 +76,7 @@ def _load():
         "gtn_small_eigh_whiten": (i32, [vp, vp, i32, vp, vp, vp, i32, i32, dbl, vp, vp, vp, vp]),
         "gtn_chol_whiten": (i32, [vp, vp, i32, vp, vp, vp, i32, i32, i32, dbl, vp, vp, vp]),
         "gtn_chol_whiten_scratch_elems": (i64, [i32]),
+        "gtn_gram_shift": (i32, [vp, i32, vp, vp, i32, i32, dbl, vp]),
         "gtn_debug_phase_clocks": (i32, [vp]),
         "gtn_gram_rotate": (i32, [vp, vp, i32, vp, vp, vp, i32, i32, i32, dbl, dbl, i32, vp, vp]),
         "gtn_sumsq": (i32, [vp, i64, i32, vp, i32, vp]),
@@ -97,6 +98,7 @@ def _load():
         "gtn_allreduce": (i32, [vp, vp, i64, i32, i32, vp]),
         "gtn_allgather": (i32, [vp, vp, vp, i64, i32, vp]),
         "gtn_broadcast": (i32, [vp, vp, i64, i32, i32, vp]),
+        "gtn_peer_barrier": (i32, [vp, i32, i32, C.c_uint64, vp]),
         "gtn_version": (i32, []),
         "gtn_build_arch": (C.c_char_p, []),
     }

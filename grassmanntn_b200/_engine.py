@@ -985,21 +985,6 @@ def batched_svd(mats):
 batched_svd.last_sweeps = 0
 
 
-def orthonormal_rows_jacobi(mats):
-    """Orthonormal rows spanning the row spaces of `mats` (p x q, p <= q) from their one-sided Jacobi SVDs: the rows of
-    Vh.  Rows whose singular value is at or below 1e-14 s_0 come out of the kernel as normalised rounding noise that
-    was never orthogonalised against the others (dead rows are not rotated): they are set to zero -- like the
-    rows beyond the detected rank in the Cholesky whitening -- so that the result is orthonormal on its support."""
-    outs = []
-    for (U, sv, Vh) in batched_svd(mats):
-        n_good = int(np.sum(sv > 1e-14 * sv[0])) if len(sv) and sv[0] > 0 else 0
-        Vh = Vh.contiguous()
-        if n_good < Vh.shape[0]:
-            Vh[n_good:].zero_()
-        outs.append(Vh)
-    return outs
-
-
 # ------------------------------------------------------------------------------------------------
 #  truncated SVD: randomized subspace iteration (GEMM-bound) + small Jacobi + residual certificate
 # ------------------------------------------------------------------------------------------------
@@ -1209,6 +1194,7 @@ def subspace_rows(k):
 _trunc_fail = {}
 _trunc_rate = {}
 _trunc_robust = {}         # (batch shape, call site) -> True: the Gram-whitened iteration dropped directions here
+ROBUST_SHIFT = 1e-9        # relative diagonal shift (x trace) of the shifted Cholesky QR passes of the robust mode
 ROBUST_MIN_DIM = 1024      # sectors at least this large retry with Jacobi orthonormalisation before the full SVD
 SVD_SITE = [None]          # call site of the decomposition being run (set by _ops.decompose_many)
 FORCE_VERIFY_FAIL = [None]  # test hook: callable(SpeculativeSVD) -> True makes verify() report a failed certificate
@@ -1325,6 +1311,9 @@ class _TruncPlan:
                                           _ptr(self.chol_scratch) if self.chol_scratch is not None else None,
                                           _stream()), "gtn_chol_whiten")
 
+    def _gram_done(self, side):
+        """hook between the Gram GEMM and the whitening (column-sharded plans complete the q-side sums here)"""
+
     def _gram(self, cur, curH):
         """hT1_b = sum_s cur_b[:, Ks] cur_b[:, Ks]^H  as NS partial slices (one grouped launch).
         curH is None: the GEMM reads its B operand as the conjugate transpose of cur itself
@@ -1352,28 +1341,34 @@ class _TruncPlan:
 
     def orth(self, src, dst, side, passes, robust=False):
         ws = self.ws
-        if robust:
-            # orthonormal rows from the one-sided Jacobi SVD of the panels themselves: no Gram matrix, so directions
-            # down to eps * s_0 survive (a Gram matrix resolves sqrt(1e-13) = 3e-7 s_0).  Second pass: rows that died
-            # below the kernel's 2e-15 threshold in the first pass come out of it as unit noise vectors and are
-            # orthogonalised like any other row in the second.
-            mats_ = [ws.view(h) for h in src]
-            for _ in range(passes):
-                mats_ = orthonormal_rows_jacobi(mats_)
-            for b in range(self.nb):
-                ws.view(dst[b]).copy_(mats_[b])
-            return
         hC = self.hCp if side == "p" else self.hCq
         hS = self.hSp if side == "p" else self.hSq
-        cur = src
-        for ps in range(passes):
-            if GEMM_CONJ_TRANS:
+        # robust: SHIFTED Cholesky QR (sCholQR3 with two shifted passes).  A panel whose singular values span more than
+        # 3e-7 has a Gram matrix that plain pivoted Cholesky truncates (the directions below sqrt(1e-13) s_0 are
+        # dropped: the third decomposition of an ATRG step at chi >= 128 has s_k ~ 1e-8 s_0).  Adding 1e-9 trace(G) to
+        # the diagonal makes the factorisation exist for any range, T X then has condition <= 3e4 per pass with every
+        # direction kept (scaled, not cut), and two plain passes finish the job: 4 passes of 4 launches instead of the
+        # one-sided Jacobi SVD of the l x p panel (17 ms at l = 128, and an all-gather when the panel is sharded).
+        shifted = 2 if robust else 0
+        total = passes + shifted
+        tmp = self.hYh if side == "p" else self.hZh                 # second intermediate (the source panel's own storage
+        cur = src                                                   # is free once the first pass has consumed it)
+        for ps in range(total):
+            if GEMM_CONJ_TRANS and not robust:
                 self._gram(cur, None)                                # Gram  l x l  straight from cur
             else:
                 _ws_ctranspose(ws, list(zip(cur, hC)))
                 self._gram(cur, hC)
-            self._whiten(0 if ps == 0 else 1)
-            out = dst if ps == passes - 1 else hS
+            self._gram_done(side)
+            if ps < shifted:
+                check(lib.gtn_gram_shift(_ptr(ws.buf), dtype_code(self.dt), _ptr(self.g_off), _ptr(self.n_dev), self.nb,
+                                         self.NS, ROBUST_SHIFT, _stream()), "gtn_gram_shift")
+                count()
+            self._whiten(0 if ps == 0 else 1, rel_thr=1e-15 if ps < shifted else 1e-13)
+            if ps == total - 1:
+                out = dst
+            else:
+                out = hS if cur is not hS else tmp
             _ws_gemm(ws, list(zip(self.hT2, cur, out)))
             cur = out
 

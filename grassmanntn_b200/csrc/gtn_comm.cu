@@ -55,7 +55,36 @@ Api& api() {
 inline int64_t doubles_of(int64_t count, int dtype) { return dtype == GTN_C128 ? 2 * count : count; }
 inline int nccl_rc(int rc) { return rc == 0 ? GTN_OK : 1000 + rc; }      // NCCL errors are reported as 1000 + ncclResult_t
 
+// Device-side barrier between the GPUs of a box over peer-mapped memory: every rank writes `epoch` into slot `rank` of
+// EVERY rank's flag array and waits until all slots of its own array have reached `epoch`.  System-scope fences on both
+// sides order the peer stores of the kernels launched before the barrier (the GEMM epilogue's partial panels) before
+// the flag, and the consumer kernels after it.  One warp, ~5 us over NVSwitch.
+struct FlagPeers { unsigned long long* p[GTN_MAX_PEERS]; };
+
+__global__ void peer_barrier_kernel(FlagPeers flags, int rank, int npeers, unsigned long long epoch) {
+  const int t = threadIdx.x;
+  if (t < npeers) {
+    __threadfence_system();
+    volatile unsigned long long* dst = flags.p[t] + rank;
+    *dst = epoch;
+    volatile unsigned long long* src = flags.p[rank] + t;
+    const long long t0 = clock64();
+    while (*src < epoch) {
+      if (clock64() - t0 > 20000000000ll) break;       // ~10 s: a peer died; do not hang the GPU (the results are
+    }                                                  // then wrong and the step's certificate / norm checks fail)
+    __threadfence_system();
+  }
+}
+
 }  // namespace
+
+extern "C" int gtn_peer_barrier(void* const* flag_peers, int rank, int npeers, uint64_t epoch, void* stream) {
+  if (!flag_peers || npeers < 1 || npeers > GTN_MAX_PEERS || rank < 0 || rank >= npeers) return GTN_ERR_BAD_ARG;
+  FlagPeers f;
+  for (int i = 0; i < GTN_MAX_PEERS; ++i) f.p[i] = i < npeers ? (unsigned long long*)flag_peers[i] : nullptr;
+  peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(f, rank, npeers, (unsigned long long)epoch);
+  return (int)cudaGetLastError();
+}
 
 extern "C" int gtn_comm_available(void) { return api().ok ? 1 : 0; }
 

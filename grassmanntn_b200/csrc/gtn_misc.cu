@@ -292,6 +292,35 @@ extern "C" int gtn_sum_slices(const void* x, void* y, int64_t n, int nslices, in
   return (int)cudaGetLastError();
 }
 
+// G_b (sum of nsplit slices) gets rel * trace(G_b) added to its diagonal (slice 0): the shift of a shifted Cholesky QR.
+template <bool CPLX>
+__global__ void __launch_bounds__(RT) gram_shift_kernel(double* __restrict__ G, const int64_t* __restrict__ g_off,
+                                                        const int32_t* __restrict__ ns, int nsplit, double rel) {
+  const int n = ns[blockIdx.x];
+  const int64_t es = CPLX ? 2 : 1;
+  double* base = G + g_off[blockIdx.x] * es;
+  double tr = 0;
+  for (int i = threadIdx.x; i < n; i += RT)
+    for (int sp = 0; sp < nsplit; ++sp) tr += base[(int64_t(sp) * n * n + int64_t(i) * n + i) * es];
+  tr = block_sum(tr);
+  __shared__ double tot;
+  if (threadIdx.x == 0) tot = tr;
+  __syncthreads();
+  const double add = rel * tot;
+  for (int i = threadIdx.x; i < n; i += RT) base[(int64_t(i) * n + i) * es] += add;
+}
+
+extern "C" int gtn_gram_shift(void* G, int dtype, const int64_t* g_off_dev, const int32_t* n_dev, int nprob, int nsplit,
+                              double rel_shift, void* stream) {
+  if (nprob <= 0) return GTN_OK;
+  if (nsplit < 1) return GTN_ERR_BAD_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == GTN_C128) gram_shift_kernel<true><<<nprob, RT, 0, s>>>((double*)G, g_off_dev, n_dev, nsplit, rel_shift);
+  else if (dtype == GTN_F64) gram_shift_kernel<false><<<nprob, RT, 0, s>>>((double*)G, g_off_dev, n_dev, nsplit, rel_shift);
+  else return GTN_ERR_BAD_ARG;
+  return (int)cudaGetLastError();
+}
+
 extern "C" int gtn_row_sumsq(const void* x, double* y, int64_t rows, int64_t cols, int dtype, void* stream) {
   if (rows <= 0) return GTN_OK;
   if (rows > 2147483647LL) return GTN_ERR_BAD_ARG;

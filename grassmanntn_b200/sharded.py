@@ -39,7 +39,10 @@ from . import _cabi, _engine as E
 from ._cabi import check, count, lib
 from ._engine import BT, FERMI, PermutePlan, _cached, _ptr, _row_strides, _stream, build_job, dtype_code, lin_leg
 
-FUSED_ALLREDUCE = bool(int(__import__("os").environ.get("GTN_FUSED_ALLREDUCE", "1")))
+# fused GEMM + all-reduce over peer memory (ShardedTruncPlan._gemm_allreduce): measured equal to GEMM + NCCL all-reduce at
+# 2 GPUs (195.2 vs 194.9 ms per chi = 128 step) and slower at 8 (71.5 vs 64.7 ms: an all-reduce by peer stores of the
+# partial panels moves W - 1 copies per rank, 2.7 GB per step at W = 8, where NCCL reduces inside the NVSwitch) -> off
+FUSED_ALLREDUCE = bool(int(__import__("os").environ.get("GTN_FUSED_ALLREDUCE", "0")))
 BIG_PREROTATE = bool(int(__import__("os").environ.get("GTN_BIG_PREROTATE", "1")))
 BIG_PREROTATE_MIN_L = 80    # (gtn_gram_rotate serves l <= 80 on the single-GPU path)
 GATHER_MAX_DIM = 16384     # largest sector (smaller side) the owner-gathered fallback decomposes on one GPU
@@ -66,6 +69,7 @@ def _nbytes(t):
 #      stream when the process group runs on NCCL; torch.distributed otherwise (gloo: the CPU tests of the host logic)
 NATIVE_COMM = bool(int(__import__("os").environ.get("GTN_NATIVE_COMM", "1")))
 _native = {"comm": None, "tried": False}
+_peer_flags = {}           # symmetric buffer size -> [peer pointers of the barrier flags, epoch]
 
 
 def native_comm():
@@ -306,7 +310,8 @@ class ShardedTruncPlan(E._TruncPlan):
         if w > 1 and FUSED_ALLREDUCE and self._fused_ok is not False:
             from . import parallel
             span = ws.off(hc[-1]) + ws.items[hc[-1]][1] * ws.items[hc[-1]][2] - ws.off(hc[0])
-            nbytes = w * span * ws.buf.element_size()
+            data_bytes = w * span * ws.buf.element_size()
+            nbytes = data_bytes + 4096               # + the flag arrays of the device-side barrier
             if self._fused_ok is None:
                 err = None
                 try:
@@ -322,6 +327,17 @@ class ShardedTruncPlan(E._TruncPlan):
                     parallel._symm.pop(nbytes, None)
             if self._fused_ok:
                 t, hdl, ptrs = parallel._symm_output(nbytes, ws.buf.device)
+                bar = _peer_flags.get(nbytes)
+                if bar is None:
+                    import ctypes as C
+                    t[data_bytes:].zero_()
+                    hdl.barrier(channel=0)           # (once per buffer: the flags are zero everywhere)
+                    bar = _peer_flags[nbytes] = [(C.c_void_p * w)(*[int(p_) + data_bytes for p_ in hdl.buffer_ptrs]), 0]
+
+                def barrier():
+                    bar[1] += 1
+                    check(lib.gtn_peer_barrier(bar[0], r, w, bar[1], _stream()), "gtn_peer_barrier")
+                    count()
                 groups = []
                 for a, b, c in zip(ha, hb, hc):
                     _, m, k = ws.items[a]
@@ -330,12 +346,12 @@ class ShardedTruncPlan(E._TruncPlan):
                                        lda=k, ldb=n, ldc=n, m=m, n=n, k=k))
                 key = ("shard_fused", str(ws.dtype), r, w, tuple(tuple(sorted(g.items())) for g in groups))
                 plan = _cached(key, lambda: E.GemmPlan(groups, ws.dtype, config=0))
-                hdl.barrier(channel=0)               # every peer has summed the previous contents of its buffer
+                barrier()                            # every peer has summed the previous contents of its buffer
                 with E.prof_region("grouped_gemm_bcast", 1, plan.bytes, plan.flops):
                     check(lib.gtn_grouped_gemm_bcast(_ptr(ws.buf), _ptr(ws.buf), ptrs, w, dtype_code(ws.dtype),
                                                      _ptr(plan.dev), plan.n, plan.tiles, _stream()),
                           "gtn_grouped_gemm_bcast")
-                hdl.barrier(channel=1)               # every rank's partial panels have landed here
+                barrier()                            # every rank's partial panels have landed here
                 dst = ws.buf[ws.off(hc[0]): ws.off(hc[0]) + span]
                 with E.prof_region("sum_slices", 1, (w + 1) * span * ws.buf.element_size()):
                     check(lib.gtn_sum_slices(_ptr(t), _ptr(dst), span, w, dtype_code(ws.dtype), _stream()),
@@ -357,59 +373,9 @@ class ShardedTruncPlan(E._TruncPlan):
         self._gemm_allreduce(self.hPh, self.hWh, self.hYh)
         self.orth(self.hYh, self.hQh, "p", 2 if last else 1, robust)
 
-    def _orth_robust(self, src, dst, side, passes):
-        """orthonormal rows from the one-sided Jacobi SVD of the panels (no Gram matrix: full dynamic range).  The
-        replicated l x p panels are decomposed by their owner ranks (problem b on rank b % W); the column-sharded
-        l x q_r panels are first all-gathered (l x q numbers: isometry-sized).  The result is broadcast, every rank
-        keeps its columns (one owner per panel, so different panels are decomposed concurrently on different ranks)."""
-        ws, w, r = self.ws, self.w, rank()
-        dt, dev = self.dt, self.dev
-        full, shapes = {}, []
-        for b in range(self.nb):
-            loc = ws.view(src[b])
-            l, n = loc.shape
-            shapes.append((l, n))
-            owner = b % w
-            if side == "q" and w > 1:
-                g_ = torch.empty(w * l * n, dtype=dt, device=dev)
-                _all_gather(g_, loc.reshape(-1))
-                if r == owner:
-                    full[b] = g_.view(w, l, n).permute(1, 0, 2).reshape(l, w * n).contiguous()
-                del g_
-            elif r == owner:
-                full[b] = loc
-        outs = {}
-        if full:
-            order = sorted(full)
-            mats_ = [full[b] for b in order]
-            for _ in range(passes):
-                mats_ = E.orthonormal_rows_jacobi(mats_)
-            outs = dict(zip(order, mats_))
-        for b in range(self.nb):
-            l, n = shapes[b]
-            owner = b % w
-            ncols = n * w if (side == "q" and w > 1) else n
-            out = outs[b].contiguous() if r == owner else torch.empty(l, ncols, dtype=dt, device=dev)
-            if w > 1:
-                _broadcast(out, owner)
-            ws.view(dst[b]).copy_(out.view(l, w, n)[:, r, :] if (side == "q" and w > 1) else out)
-
-    def orth(self, src, dst, side, passes, robust=False):
-        if robust:
-            return self._orth_robust(src, dst, side, passes)
-        ws = self.ws
-        hC = self.hCp if side == "p" else self.hCq
-        hS = self.hSp if side == "p" else self.hSq
-        cur = src
-        for ps in range(passes):
-            E._ws_ctranspose(ws, list(zip(cur, hC)))
-            self._gram(cur, hC)
-            if side == "q":
-                self._reduce_handles(self.hT1)        # Gram matrix of column-sharded rows: sum over ranks
-            self._whiten(0 if ps == 0 else 1)
-            out = dst if ps == passes - 1 else hS
-            E._ws_gemm(ws, list(zip(self.hT2, cur, out)))
-            cur = out
+    def _gram_done(self, side):
+        if side == "q":
+            self._reduce_handles(self.hT1)            # Gram matrix of column-sharded rows: sum over ranks
 
     def check_enqueue(self, allow_host=True):
         ws, nb, dt, dev = self.ws, self.nb, self.dt, self.dev

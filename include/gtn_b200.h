@@ -237,6 +237,16 @@ int gtn_chol_whiten(const void* G, void* T, int dtype, const int64_t* g_off_dev,
                     const int64_t* t_off_dev, const int32_t* n_dev, int nprob, int max_n, int nsplit,
                     double rel_thr, int32_t* kept_dev, void* scratch, void* stream);
 
+/* G_b <- G_b + rel_shift * trace(G_b) * I for the Gram matrices handed to gtn_chol_whiten (same g_off / n / nsplit
+ * arguments; the trace is taken over the sum of the nsplit slices, the shift goes onto slice 0): the shift of a SHIFTED
+ * Cholesky QR.  A panel whose singular values span more than sqrt(1/eps) has a numerically indefinite Gram matrix --
+ * plain (pivoted) Cholesky drops every direction below 3e-7 s_0; with the shift the factorisation exists, T X has
+ * condition ~ 1/sqrt(rel_shift) and keeps all directions, and further (shifted, then plain) passes finish the
+ * orthonormalisation (shifted CholeskyQR3).  Used by the robust mode of the truncated sector SVD (spectra steeper than
+ * a Gram matrix resolves: the third decomposition of an ATRG step, reference gauge2d.py:1843). */
+int gtn_gram_shift(void* G, int dtype, const int64_t* g_off_dev, const int32_t* n_dev, int nprob, int nsplit,
+                   double rel_shift, void* stream);
+
 /* Pre-rotation for the one-sided Jacobi SVD of a short-and-wide matrix B (n_b <= 80 rows): from the
  * Gram matrix G_b = B B^H compute a UNITARY T_b (n_b x n_b) such that the rows of T_b B are orthogonal
  * up to the accuracy a Gram matrix allows (pivoted Cholesky G = P L L^H P^T, one-sided Jacobi on the
@@ -362,6 +372,11 @@ int gtn_comm_destroy(void* comm);
 int gtn_allreduce(void* comm, void* buf, int64_t count, int dtype, int op, void* stream);         /* in place */
 int gtn_allgather(void* comm, const void* send, void* recv, int64_t count_per_rank, int dtype, void* stream);
 int gtn_broadcast(void* comm, void* buf, int64_t count, int dtype, int root, void* stream);        /* in place */
+
+/* Device-side barrier over peer-mapped memory (the fused GEMM + all-reduce of the sharded step): flag_peers is a HOST
+ * array of npeers device pointers, entry q = rank q's flag array (>= npeers uint64, zero-initialised, mapped into this
+ * process).  Every rank passes the same monotonically increasing `epoch` (> 0).  Enqueued on `stream`. */
+int gtn_peer_barrier(void* const* flag_peers, int rank, int npeers, uint64_t epoch, void* stream);
 
 /* Library / device introspection (no device work). */
 int gtn_version(void);

@@ -234,6 +234,16 @@ class HostLibSVD(HostLib):
             kp[b] = r
         return 0
 
+    def gtn_gram_shift(self, G, code, g_off, n_dev, nprob, nsplit, rel_shift, stream):
+        dt = self._dt(code)
+        go, ns = _i64(g_off, nprob), _i32(n_dev, nprob)
+        for b in range(nprob):
+            n = int(ns[b])
+            sl = _arr(C.c_void_p(G.value + int(go[b]) * np.dtype(dt).itemsize), nsplit * n * n, dt).reshape(nsplit, n, n)
+            tr = float(np.real(np.trace(sl.sum(axis=0))))
+            sl[0][np.arange(n), np.arange(n)] += rel_shift * tr
+        return 0
+
     def gtn_gram_rotate(self, G, T, code, g_off, t_off, n_dev, nprob, max_n, nsplit, rel_thr, tol, max_sweeps,
                         sweeps, stream):
         dt = self._dt(code)
