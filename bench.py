@@ -375,6 +375,7 @@ def main_single(args, data, stats, label):
         if world > 1:
             dist.destroy_process_group()
         return
+    T_atrg = T if (not args.no_micro and chi >= 128) else None
     del T, h_in, box
     torch.cuda.empty_cache()
 
@@ -386,6 +387,22 @@ def main_single(args, data, stats, label):
              "whole_step_vs_fp64_yardstick": step_frac, "saturation_steps": sat_steps, "peak_mem_GiB": peak_mem,
              "jacobi_sweeps_last": E.batched_svd.last_sweeps, "svd_paths": dict(_ops.SVD_PATH_STATS),
              "trunc_refinements_last": E.truncated_svd_batch.last_iters}
+    if not args.no_micro and chi >= 128:
+        # the reference's default algorithm (ATRG, example.py:178-188) at the same size: alternating y / x steps from the
+        # same saturated tensor, time of the later steps (the first ones derive the iteration counts)
+        try:
+            X, ts = T_atrg, []
+            for i in range(5):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                X = (g.atrg2dy if i % 2 == 0 else g.atrg2dx)(X, X, chi)[0]
+                torch.cuda.synchronize()
+                ts.append((time.perf_counter() - t0) * 1e3)
+            extra["atrg_block_chi%d_ms_per_step" % chi] = {"steps": ts, "best": min(ts[2:])}
+            del X, T_atrg
+            torch.cuda.empty_cache()
+        except Exception as ex:
+            extra["atrg_block_chi%d_ms_per_step" % chi] = {"error": repr(ex)[:200]}
     if not args.no_micro:
         extra["microbench"] = mb = microbench(gtn, E, torch, dev, args, hbm_peak)
         extra["other_workloads"] = other_workloads(gtn, torch, data, stats, 32)
