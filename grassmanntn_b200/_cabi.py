@@ -44,7 +44,7 @@ class SvdOut(C.Structure):
 
 class SvdInfo(C.Structure):
     _fields_ = [("start_iters", C.c_int32), ("iters", C.c_int32), ("checks", C.c_int32), ("sweeps", C.c_int32),
-                ("launches", C.c_int32), ("reserved", C.c_int32), ("worst", C.c_double), ("rate", C.c_double)]
+                ("launches", C.c_int32), ("robust", C.c_int32), ("worst", C.c_double), ("rate", C.c_double)]
 
 
 GTN_OP_SECTOR_SVD_TRUNC, GTN_OP_SECTOR_EIGH_TRUNC = 0, 1

@@ -1724,7 +1724,7 @@ def _onecall_bytes(P_, Q_, ks, dt):
     return int(lib.gtn_workspace_bytes(_cabi.GTN_OP_SECTOR_SVD_TRUNC, dtype_code(dt), len(P_), m_, n_, k_))
 
 
-def _truncated_onecall(mats, ks, key, P_, Q_):
+def _truncated_onecall(mats, ks, key, P_, Q_, robust=False):
     """truncated_svd_batch through the one-call C ABI (include/gtn_b200.h: gtn_sector_svd_trunc): subspace iteration,
     certificate checks and rank certificate run inside the library; returns the same [(U, s, Vh)] or None."""
     dev, dt = mats[0].device, mats[0].dtype
@@ -1741,6 +1741,7 @@ def _truncated_onecall(mats, ks, key, P_, Q_):
     S = (C.c_double * sum(ks))()
     rank = (C.c_int32 * nb)()
     info = _cabi.SvdInfo()
+    info.robust = 1 if robust else 0
     info.start_iters = int(_trunc_iters_hint.get(key) or 0)
     info.rate = float(_trunc_rate.get(key, 0.0))
     ONE_CALL_STATS["calls"] += 1
@@ -1796,11 +1797,11 @@ def truncated_svd_batch(mats, ks, robust=False, speculative=False, resume=None):
     elif _trunc_robust.get(key) and not speculative and resume is None and not CAPTURING_STEP[0]:
         # this site's spectrum spans more than the Gram whitening resolves: straight to the Jacobi-orthonormalised run
         return truncated_svd_batch(mats, ks, robust=True)
-    if (ONE_CALL and not robust and resume is None and not CAPTURING_STEP[0] and not PROF.enabled
+    if (ONE_CALL and resume is None and not CAPTURING_STEP[0] and not PROF.enabled
             and _onecall_bytes(P_, Q_, ks, dt) > TRUNC_PLAN_CACHE_BYTES):
         # large sectors (chi >= 128: no cached workspace, no recorded graph): the whole driver loop runs behind
         # ONE C-ABI call (gtn_sector_svd_trunc, csrc/gtn_sector.cu); this host only keeps the iteration memory
-        return _truncated_onecall(mats, ks, key, P_, Q_)
+        return _truncated_onecall(mats, ks, key, P_, Q_, robust)
     fails = _trunc_fail.get(key, 0)
     if fails >= 2 and not robust:
         # this shape keeps failing the certificate (flat spectrum): go straight to the full SVD, but

@@ -346,23 +346,31 @@ struct Driver {
     gemm(g);
   }
 
-  void whiten(int slot) {
+  void whiten(int slot, double rel_thr = 1e-13) {
     if (err) return;
     ++launches;
     note(gtn_chol_whiten(ws, ws, lay.dtype, at<int64_t>(lay.o_goff), at<int64_t>(lay.o_toff), at<int32_t>(lay.o_ndev),
-                         lay.nb, lay.maxL, lay.NS, 1e-13, at<int32_t>(lay.o_kept) + slot * lay.nb,
+                         lay.nb, lay.maxL, lay.NS, rel_thr, at<int32_t>(lay.o_kept) + slot * lay.nb,
                          lay.chol_elems ? (void*)(ws + lay.o_chol) : nullptr, st));
   }
 
+  bool robust = false;      // shifted Cholesky QR: two passes with 1e-9 trace(G) on the diagonal before the plain ones
+
+  // src is Yh (side p) or Zh (side q): its storage serves as the second intermediate once the first pass has read it
   void orth(const std::vector<Mat>& src, const std::vector<Mat>& dst, bool side_p, int passes) {
     const std::vector<Mat>& C = side_p ? lay.Cp : lay.Cq;
     const std::vector<Mat>& S = side_p ? lay.Sp : lay.Sq;
     const std::vector<Mat>* cur = &src;
-    for (int ps = 0; ps < passes; ++ps) {
+    const int shifted = robust ? 2 : 0, total = passes + shifted;
+    for (int ps = 0; ps < total; ++ps) {
       ctranspose_all(*cur, C);
       gram(*cur, C);
-      whiten(ps == 0 ? 0 : 1);
-      const std::vector<Mat>& out = (ps == passes - 1) ? dst : S;
+      if (ps < shifted && !err) {
+        ++launches;
+        note(gtn_gram_shift(ws, lay.dtype, at<int64_t>(lay.o_goff), at<int32_t>(lay.o_ndev), lay.nb, lay.NS, 1e-9, st));
+      }
+      whiten(ps == 0 ? 0 : 1, ps < shifted ? 1e-15 : 1e-13);
+      const std::vector<Mat>& out = (ps == total - 1) ? dst : ((cur == &S) ? src : S);
       gemm_all(lay.T2, *cur, out);
       cur = &out;
     }
@@ -542,7 +550,7 @@ Verdict certificate(Driver& d, std::vector<double>& out, const void* const* M, d
     for (int i = 0; i < l; ++i) nnz += fabs(s[i] / (fabs(s0) + numer_cutoff)) > numer_cutoff;
     int kk = std::min(lay.K[b], nnz);
     const bool band = kk > 0 && s[kk - 1] <= kRankNoise * s0;
-    const bool dropped = nnz < lay.K[b] && kept < l && nnz >= kept;
+    const bool dropped = !d.robust && nnz < lay.K[b] && kept < l && nnz >= kept;
     if (band || dropped) {
       int nD = 0;
       for (int i = 0; i < l; ++i) nD += s[i] > kRankNoise * s0;
@@ -601,6 +609,7 @@ extern "C" int gtn_sector_svd_trunc(const void* const* M, const int64_t* m, cons
   d.ws = (char*)workspace;
   d.st = (cudaStream_t)stream;
   const Layout& lay = d.lay;
+  d.robust = info && info->robust != 0;
   d.init_tables();
   d.load(M);
   const int start_it = info ? std::max(0, std::min(info->start_iters, kMaxIters)) : 0;

@@ -288,7 +288,8 @@ typedef struct {
   int32_t checks;
   int32_t sweeps;
   int32_t launches; /* out: kernels launched by the call */
-  int32_t reserved;
+  int32_t robust;   /* in: 1 = shifted Cholesky QR orthonormalisations (gtn_gram_shift): spectra that span more than 3e-7
+                       inside the cut, where the plain run returns GTN_ERR_NOT_CONVERGED */
   double worst;
   double rate;
 } gtn_svd_info;

@@ -25,7 +25,7 @@ def _decaying(m, n, cplx, seed, rate=0.8, rank=None):
     return (Qa * s) @ Qb.conj().T
 
 
-def _onecall(torch, mats, ks, eig=False):
+def _onecall(torch, mats, ks, eig=False, robust=False):
     from grassmanntn_b200 import _cabi, _engine as E
     lib = _cabi.lib
     dev = torch.device("cuda")
@@ -47,6 +47,7 @@ def _onecall(torch, mats, ks, eig=False):
     lam = (C.c_double * (2 * sum(ks)))()
     rank = (C.c_int32 * nb)()
     info = _cabi.SvdInfo()
+    info.robust = 1 if robust else 0
     if eig:
         rc = lib.gtn_sector_eigh_trunc(ptrs(src), m_, n_, nb, code, k_, 1e-14, ptrs(U), S, ptrs(Vh), lam, rank,
                                        E._ptr(ws), nbytes, C.byref(info), None)
@@ -92,6 +93,22 @@ def test_onecall_flat_spectrum_is_reported(gtn):
     rc, outs, info = _onecall(torch, [M], [16])
     from grassmanntn_b200 import _cabi
     assert rc == _cabi.GTN_ERR_NOT_CONVERGED
+
+
+def test_onecall_steep_spectrum_needs_the_robust_mode(gtn):
+    """singular values falling by 0.6 per index: s_40 = 2e-9 s_0 lies below what a Gram matrix resolves (3e-7), the plain
+    run must refuse (its whitening dropped directions), the shifted-Cholesky-QR run must deliver all 40 to 1e-10 s_0"""
+    import torch
+    from grassmanntn_b200 import _cabi
+    M = _decaying(512, 512, True, 21, rate=0.6)
+    rc, outs, info = _onecall(torch, [M], [40])
+    assert rc == _cabi.GTN_ERR_NOT_CONVERGED
+    rc, outs, info = _onecall(torch, [M], [40], robust=True)
+    assert rc == 0
+    U, s, Vh, rank, _ = outs[0]
+    ref = np.linalg.svd(M, compute_uv=False)
+    assert rank == 40 and np.abs(s - ref[:40]).max() <= 1e-10 * ref[0]
+    assert np.abs(s[24:] / ref[24:40] - 1).max() <= 1e-4            # the tail (7e-6 ... 2e-9 s_0) also in relative terms
 
 
 def test_onecall_eigh_vs_numpy(gtn):
