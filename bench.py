@@ -391,6 +391,18 @@ def main_single(args, data, stats, label):
         # the reference's default algorithm (ATRG, example.py:178-188) at the same size: alternating y / x steps from the
         # same saturated tensor, time of the later steps (the first ones derive the iteration counts)
         try:
+            # a MOVING chain with adaptation on (the headline repeats one tensor): four consecutive TRG steps
+            X, ts = T_atrg, []
+            for i in range(4):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                X = g.trg(X, chi)[0]
+                torch.cuda.synchronize()
+                ts.append((time.perf_counter() - t0) * 1e3)
+            extra["trg_block_moving_chain_chi%d_ms" % chi] = ts
+        except Exception as ex:
+            extra["trg_block_moving_chain_chi%d_ms" % chi] = {"error": repr(ex)[:200]}
+        try:
             X, ts = T_atrg, []
             for i in range(5):
                 torch.cuda.synchronize()
