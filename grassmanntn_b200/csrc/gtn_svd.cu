@@ -1004,38 +1004,32 @@ __global__ void __launch_bounds__(NT)
 // the full G + L pair of the kernel above (2 n (n+1) elements) does not fit any more and the global-scratch variant
 // pays an L2 round trip per element and pivot (1.3 ms per launch at n = 128: 13 ms of a chi = 128 TRG step, and the
 // largest piece of work that is REPLICATED when the step is sharded over several GPUs).  Here the Hermitian matrix is
-// kept as its packed lower triangle (n (n+1) / 2 elements, 129 KB at n = 128) and factorised IN PLACE without moving
-// data for the pivoting: the column of pivot k is frozen where it stands -- rows and columns of earlier pivots are
-// never touched again -- so that  L_k[i] = G_k[i][p_k] / sqrt(pivot_k)  is read back from the triangle when the
-// inverse is built.  Per pivot: stage the pivot column into a double-buffered vector (coalesced, conflict-free reads
-// for everybody), rank-1 update of the remaining lower triangle (half the work of the full-matrix update), two block
-// barriers.  The inverse is built one column per warp (32 columns in flight) in a per-warp shared column buffer and
-// scattered into T.
+// kept as its packed lower triangle (n (n+1) / 2 elements, 129 KB at n = 128) and factorised IN PLACE with physical
+// diagonal pivoting (symmetric row / column swaps inside the triangle), so the factor ends up in pivot order and the
+// trailing update only touches the trailing triangle.  Per pivot: swap + scale + stage the pivot column into a
+// contiguous vector (coalesced, conflict-free reads for everybody), rank-1 update of the trailing lower triangle, two
+// block barriers.  The inverse is built row by row in place and scattered into T.
 constexpr int PK_MAXN = 128;
 constexpr int PK_T = 1024;
-static_assert(PK_T / 32 == 32 && PK_MAXN == 128, "the packed Cholesky kernel unrolls over 4 groups of 32 rows / columns");
+static_assert(PK_T / 8 >= PK_MAXN, "the in-place inverse of the packed Cholesky kernel runs 8 lanes per column");
 __device__ __forceinline__ int tri(int i) { return (i * (i + 1)) >> 1; }
-// G[i][j] of the Hermitian matrix held as packed lower triangle
-__device__ __forceinline__ c128 herm_get(const c128* Gp, int i, int j) {
-  if (i >= j) return Gp[tri(i) + j];
-  c128 v = Gp[tri(j) + i];
-  v.im = -v.im;
-  return v;
-}
-
 template <bool CPLX>
-__global__ void __launch_bounds__(PK_T)
+__global__ void __launch_bounds__(PK_T, 1)
     chol_whiten_packed_kernel(const typename Elem<CPLX>::T* __restrict__ Gb, typename Elem<CPLX>::T* __restrict__ Tb,
                               const int64_t* __restrict__ g_off, const int64_t* __restrict__ t_off,
                               const int32_t* __restrict__ ns, int nsplit, double rel_thr, int32_t* __restrict__ kept) {
+  // Round-2 rewrite (after `ncu --set full` of the first version: 4.0 M warp instructions per matrix, issue slots 67 %
+  // busy, 13 % FP64 -- bound by index arithmetic: pivoting by masks made every pivot walk the WHOLE triangle, and the
+  // inverse chased the pivot order through two indirections per element).  Now the pivoting is PHYSICAL: pivot k swaps
+  // row / column k with the pivot's in the packed triangle (n element swaps), so the trailing update runs over the
+  // clean trailing triangle only ((n - k)^2 / 2 elements: n^3 / 6 in total instead of n^3 / 2) and the factor ends up
+  // in pivot order in place, where the row-wise in-place inverse reads it without any indirection.
   using T = typename Elem<CPLX>::T;
   extern __shared__ __align__(16) unsigned char sm_raw[];
   const int n = ns[blockIdx.x];
   c128* Gp = reinterpret_cast<c128*>(sm_raw);
-  c128* colbuf = Gp + tri(n);                       // (PK_T / 32) columns of n + 1 elements
   __shared__ c128 vb[2][PK_MAXN];
   __shared__ int perm[PK_MAXN];
-  __shared__ double invs[PK_MAXN];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool stamp = tid == 0 && blockIdx.x == 0;
   if (stamp) gtn_phase_clk[0] = clock64();
@@ -1054,25 +1048,17 @@ __global__ void __launch_bounds__(PK_T)
     }
     if constexpr (CPLX) { T z; z.re = 0.0; z.im = 0.0; Elem<CPLX>::st(Tout + e, z); } else Elem<CPLX>::st(Tout + e, 0.0);
   }
+  if (tid < n) perm[tid] = tid;
   __syncthreads();
-  // ---- pivoted Cholesky, in place
-  constexpr int NW = PK_MAXN / 32;
-  unsigned done[NW];
-  double dreg[NW];
-#pragma unroll
-  for (int t = 0; t < NW; ++t) {
-    done[t] = 0u;
-    const int i = lane + 32 * t;
-    dreg[t] = i < n ? Gp[tri(i) + i].re : -1.0;
-  }
+  // ---- diagonally pivoted Cholesky with physical symmetric swaps, in place: L_r[a][b] ends up at tri(a) + b
   double first = 0.0;
   int rank = n;
   for (int k = 0; k < n; ++k) {
-    double best = -1.0; int bidx = 0;
-#pragma unroll
-    for (int t = 0; t < NW; ++t) {
-      const bool free_ = !((done[t] >> lane) & 1u);
-      if (free_ && dreg[t] > best) { best = dreg[t]; bidx = lane + 32 * t; }
+    // pivot search on the remaining diagonal, redundantly by every warp (same data, same result: no broadcast)
+    double best = -1.0; int bidx = k;
+    for (int i = k + lane; i < n; i += 32) {
+      const double d = Gp[tri(i) + i].re;
+      if (d > best) { best = d; bidx = i; }
     }
     const unsigned key = best > 0.0 ? (unsigned)(__double_as_longlong(best) >> 32) : 0u;
     const unsigned top = __reduce_max_sync(0xffffffffu, key);
@@ -1081,85 +1067,66 @@ __global__ void __launch_bounds__(PK_T)
     bidx = __shfl_sync(0xffffffffu, bidx, src);
     if (k == 0) first = best;
     if (!(best > rel_thr * first && best > 0.0)) { rank = k; break; }
-    const int pk = bidx;
+    const int p = bidx;
     const double inv = rsqrt(best);
-    const double inv2 = inv * inv;
     c128* v = vb[k & 1];
-    if (tid < n) v[tid] = herm_get(Gp, tid, pk);                 // column p_k as it stands (frozen from now on)
-    if (tid == 0) { perm[k] = pk; invs[k] = inv; }
-#pragma unroll
-    for (int t = 0; t < NW; ++t)
-      if ((pk >> 5) == t) done[t] |= 1u << (pk & 31);
-    __syncthreads();
-#pragma unroll
-    for (int t = 0; t < NW; ++t) {
-      const int i = lane + 32 * t;
-      if (i < n && !((done[t] >> lane) & 1u)) {
-        const c128 g = v[i];
-        dreg[t] -= (g.re * g.re + g.im * g.im) * inv2;
-      }
-    }
-    // G[i][j] -= v[i] conj(v[j]) / pivot over the free rows i >= j: one warp per row, lanes along the row
-    // (both loops unrolled over the NW = 4 groups of 32 indices: the done masks are then addressed statically -- the
-    //  kernel is instruction-issue bound, ncu: 4.0 M warp instructions per matrix at l = 128, 13 % of them FP64 --
-    //  and the pivot column entries of this lane are loaded once per pivot instead of once per row)
-    c128 vj[NW];
-    bool fj[NW];
-#pragma unroll
-    for (int t = 0; t < NW; ++t) {
-      const int j = lane + 32 * t;
-      fj[t] = j < n && !((done[t] >> lane) & 1u);
-      if (fj[t]) vj[t] = v[j];
-    }
-#pragma unroll
-    for (int u = 0; u < NW; ++u) {
-      const int i = warp + 32 * u;                               // PK_T / 32 == 32 warps: rows warp, warp + 32, ...
-      if (i >= n || ((done[u] >> warp) & 1u)) continue;
-      c128 a = v[i];
-      a.re *= inv2; a.im *= inv2;
-      c128* row = Gp + tri(i);
-#pragma unroll
-      for (int t = 0; t < NW; ++t) {
-        const int j = lane + 32 * t;
-        if (t <= u && j <= i && fj[t]) {
-          c128 g = row[j];
-          g.re -= a.re * vj[t].re + a.im * vj[t].im;
-          g.im -= a.im * vj[t].re - a.re * vj[t].im;
-          row[j] = g;
+    // swap k <-> p (thread x owns index x), scale column k by 1 / sqrt(pivot), stage it contiguously in v
+    if (tid < n) {
+      const int x = tid;
+      if (p != k) {
+        if (x < k) {
+          const c128 a = Gp[tri(k) + x]; Gp[tri(k) + x] = Gp[tri(p) + x]; Gp[tri(p) + x] = a;
+        } else if (x > k && x < p) {
+          c128 a = Gp[tri(x) + k], b = Gp[tri(p) + x];
+          a.im = -a.im; b.im = -b.im;
+          Gp[tri(x) + k] = b; Gp[tri(p) + x] = a;
+        } else if (x > p) {
+          const c128 a = Gp[tri(x) + k]; Gp[tri(x) + k] = Gp[tri(x) + p]; Gp[tri(x) + p] = a;
+        } else if (x == p) {
+          c128 a = Gp[tri(p) + k]; a.im = -a.im; Gp[tri(p) + k] = a;
+        } else {                                                    // x == k: the two diagonal entries
+          const c128 a = Gp[tri(k) + k]; Gp[tri(k) + k] = Gp[tri(p) + p]; Gp[tri(p) + p] = a;
+          const int t = perm[k]; perm[k] = perm[p]; perm[p] = t;
         }
       }
+      if (x > k) {
+        c128 a = Gp[tri(x) + k];
+        a.re *= inv; a.im *= inv;
+        Gp[tri(x) + k] = a;
+        v[x] = a;
+      } else if (x == k) {
+        c128 d; d.re = best * inv; d.im = 0.0;                      // sqrt(pivot)
+        Gp[tri(k) + k] = d;
+      }
+    }
+    __syncthreads();
+    // trailing update G[i][j] -= L[i][k] conj(L[j][k]) for k < j <= i: one warp per row, lanes along the row
+    for (int i = k + 1 + warp; i < n; i += PK_T / 32) {
+      const c128 a = v[i];
+      c128* row = Gp + tri(i);
+      for (int j = k + 1 + lane; j <= i; j += 32) {
+        const c128 b = v[j];
+        c128 g = row[j];
+        g.re -= a.re * b.re + a.im * b.im;
+        g.im -= a.im * b.re - a.re * b.im;
+        row[j] = g;
+      }
     }
     __syncthreads();
   }
-  if (tid == 0 && rank < n) {
-    int k = rank;
-    for (int i = 0; i < n; ++i)
-      if (!((done[i >> 5] >> (i & 31)) & 1u)) perm[k++] = i;
-  }
-  __syncthreads();
   const int r = rank;
   if (stamp) gtn_phase_clk[1] = clock64();
-  // ---- X = L_r^{-1} IN PLACE, row by row: L_r[a][b] = G_b[perm[a]][perm[b]] * invs[b] (a >= b) sits at the packed slot
-  // of (perm[a], perm[b]); row a of X only needs row a of L_r and the rows of X above it,
-  //     X[a][b] = -invs[a] * sum_{j = b .. a-1} L_r[a][j] X[j][b]   (b < a),   X[a][a] = invs[a],
-  // so X[a][b] overwrites L_r[a][b] once every column has read row a (one barrier before, one after the stores).  All
-  // 128 columns advance together, 8 lanes per column splitting the sum: 128 sequential steps of ~n/16 multiply-adds
-  // per lane, instead of the 320 steps of one-column-per-warp forward substitution (4 blocks of 32 columns) this
-  // replaces (l = 128: 641 k cycles of the kernel's 1.48 M; profiles/r2d_whiten_probe_before.txt).
-  // X is stored so that herm_get(Gp, perm[a], perm[b]) returns it (conjugated when perm[a] < perm[b]).
+  // ---- X = L_r^{-1} in place, row by row:  X[a][b] = -(1 / L[a][a]) sum_{j = b .. a-1} L[a][j] X[j][b],  X[a][a] = 1 / L[a][a].
+  // All columns advance together (8 lanes per column); row a of L is read by everybody before it is overwritten.
   {
     const int b = tid >> 3, sub = tid & 7;
     for (int a = 0; a < r; ++a) {
-      const int pa = perm[a];
+      const c128* La = Gp + tri(a);
       double sr = 0.0, si = 0.0;
       if (b < a) {
-        const int pb = perm[b];
         for (int jj = b + sub; jj < a; jj += 8) {
-          const int pj = perm[jj];
-          c128 l = herm_get(Gp, pa, pj);
-          const double s_ = invs[jj];
-          l.re *= s_; l.im *= s_;
-          const c128 x = herm_get(Gp, pj, pb);
+          const c128 l = La[jj];
+          const c128 x = Gp[tri(jj) + b];
           sr += l.re * x.re - l.im * x.im;
           si += l.re * x.im + l.im * x.re;
         }
@@ -1169,15 +1136,13 @@ __global__ void __launch_bounds__(PK_T)
         sr += __shfl_xor_sync(0xffffffffu, sr, o);
         si += __shfl_xor_sync(0xffffffffu, si, o);
       }
+      const double d = 1.0 / La[a].re;
       __syncthreads();
-      if (sub == 0 && b <= a && b < r) {
-        const double d = invs[a];
+      if (sub == 0 && b <= a) {
         c128 o;
         if (b == a) { o.re = d; o.im = 0.0; }
         else { o.re = -sr * d; o.im = -si * d; }
-        const int pb = perm[b];
-        if (pa >= pb) Gp[tri(pa) + pb] = o;
-        else { o.im = -o.im; Gp[tri(pb) + pa] = o; }
+        Gp[tri(a) + b] = o;
       }
       __syncthreads();
     }
@@ -1185,9 +1150,9 @@ __global__ void __launch_bounds__(PK_T)
     for (int e = tid; e < r * r; e += PK_T) {
       const int a = e / r, bb = e - a * r;
       if (bb <= a) {
-        const c128 v = herm_get(Gp, perm[a], perm[bb]);
+        const c128 x = Gp[tri(a) + bb];
         T* dst = Tout + int64_t(a) * n + perm[bb];
-        if constexpr (CPLX) { T t; t.re = v.re; t.im = v.im; Elem<CPLX>::st(dst, t); } else Elem<CPLX>::st(dst, v.re);
+        if constexpr (CPLX) { T t; t.re = x.re; t.im = x.im; Elem<CPLX>::st(dst, t); } else Elem<CPLX>::st(dst, x.re);
       }
     }
   }
@@ -1353,7 +1318,7 @@ extern "C" int gtn_chol_whiten(const void* G, void* T, int dtype, const int64_t*
 #undef GTN_CHOL_LAUNCH
   } else if (max_n <= PK_MAXN) {
     // packed lower triangle + 32 column buffers in shared memory (199 KB at n = 128)
-    const size_t smem = (size_t(max_n) * (max_n + 1) / 2 + size_t(PK_T / 32) * (max_n + 1)) * 16;
+    const size_t smem = (size_t(max_n) * (max_n + 1) / 2) * 16;        // the packed lower triangle
     static size_t attr = 0;
     if (smem > attr) {
       int e = set_smem(chol_whiten_packed_kernel<true>, smem);
