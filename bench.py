@@ -17,9 +17,8 @@ matrices); --chi 32 / 64 run the smaller configurations (chi = 32 = example_bloc
              pass over the same steps) against its bound: FP64 tensor pipe (yard-stick: cuBLAS ZGEMM timed in this
              run; nominal 40 TFLOP/s stated beside it) or HBM (MEASURED_PEAKS.json)
   cpu_baseline  the numpy oracle port (oracle/gtn_oracle.py trg_block) on the host cores, one bounded sample
-             (rank 0, N=1): a full step for chi <= 64; for chi = 128 one full step at D = chi = 64 (the same chain one
-             level earlier) scaled by (chi/64)^6 -- every O(D^6) term of the step (the four sector SVDs of
-             (D^2/2)^2 matrices, the eight sector GEMMs of the contraction) scales that way
+             (rank 0, N=1): full steps for chi <= 64; for chi = 128 the same estimator as --impl reference (a quarter
+             sample of the D = chi = 64 step, below), two samples
 
 --impl reference runs ONLY the CPU oracle port (the reference is Python and does not travel to the GPU box; see
 DESIGN.md) with all host threads on the same config/metric; at chi = 128 every "step" is a bounded quarter sample
@@ -179,12 +178,7 @@ def cpu_reference_run(args, data, stats, quick=False):
             dt = (time.perf_counter() - t0) / steps
             return dt, "%d full TRG steps at chi=%d (oracle/gtn_oracle.py trg_block; numpy/LAPACK)" % (steps, level)
         if quick:
-            t0 = time.perf_counter()
-            O.trg_block(B, level)
-            dt = time.perf_counter() - t0
-            return dt * scale, ("one full TRG step of the oracle port at D=chi=%d (%.1f s; same chain one level earlier) "
-                                "x (chi/%d)^6 = %g: the four (D^2/2)^2 sector SVDs and the eight sector GEMMs of a step "
-                                "are O(D^6)" % (level, dt, level, scale))
+            steps, warm = 2, 1          # the same estimator as the reference arm (below), two samples
         M = cpu_quarter_setup(O, B)
         for _ in range(min(warm, 1)):
             np.linalg.svd(M, full_matrices=False)
