@@ -1068,6 +1068,10 @@ def deflated_norm_bound(W, UhD, U, ldu, nD, thr, allreduce=None):
     f = math.sqrt(max(float(f2.item()), 0.0))
     if f <= thr or min(p, q) < 2:
         return f
+    if f > thr * math.sqrt(min(p, q) * (1 if allreduce is None else 64)):
+        # ||N||_2 >= ||N||_F / sqrt(rank): no bound can come below thr -- skip the min(p, q)^2 max(p, q) GEMM
+        # (8192^3: 122 ms at chi = 128).  (Sharded: the number of ranks is not known here; 64 covers a box.)
+        return f
     Nh = torch.empty(p * q, dtype=dt, device=dev)
     _ctranspose_t(N, p, q, q, Nh)                        # q x p
     if p <= q:
@@ -1794,8 +1798,10 @@ def truncated_svd_batch(mats, ks, robust=False, speculative=False, resume=None):
     key = (pkey, SVD_SITE[0])               # iteration hints / failure memory are per call site
     if robust:
         key = key + ("robust",)
-    elif _trunc_robust.get(key) and not speculative and resume is None and not CAPTURING_STEP[0]:
-        # this site's spectrum spans more than the Gram whitening resolves: straight to the Jacobi-orthonormalised run
+    elif _trunc_robust.get(key) and resume is None and not CAPTURING_STEP[0]:
+        # this site's spectrum spans more than the Gram whitening resolves: straight to the shifted-Cholesky-QR run
+        # (also for speculative callers: they accept a verified, non-speculative result; measured on the chi = 128
+        # ATRG chain: the plain attempt + its rank certificate cost 135 ms of every 620 ms step before being rejected)
         return truncated_svd_batch(mats, ks, robust=True)
     if (ONE_CALL and resume is None and not CAPTURING_STEP[0] and not PROF.enabled
             and _onecall_bytes(P_, Q_, ks, dt) > TRUNC_PLAN_CACHE_BYTES):

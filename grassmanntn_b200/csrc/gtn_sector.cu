@@ -524,6 +524,7 @@ struct Driver {
     }
     const double f = sqrt(std::max(sumsq(elem(W), p * q), 0.0));
     if (err || f <= thr || std::min(p, q) < 2) return f;
+    if (f > thr * sqrt((double)std::min(p, q))) return f;      // ||N||_2 >= ||N||_F / sqrt(rank): no bound can reach thr
     ctranspose(elem(W), q, elem(lay.Wh[b]), p, p, q);                           // N^H (q x p)
     Mat Gm{lay.scratchG, std::min(p, q), std::min(p, q)};
     std::vector<gtn_gemm_group> g3{p <= q ? group(W, lay.Wh[b], Gm) : group(lay.Wh[b], W, Gm)};
