@@ -235,6 +235,42 @@ def test_truncated_eig_vs_oracle_D16(gtn):
     assert np.abs(_np(R) - r.data).max() <= 1e-9 * np.abs(r.data).max()
 
 
+def test_rank_certificate_bounds_and_null_band_refinement(gtn):
+    """_engine.deflated_norm_bound (the norm bound of M - U_D U_D^H M that decides the reference's rank rule for
+    numerically rank-deficient sectors) against numpy: ||N||_2 <= bound <= ||N||_F, the Schatten-4 branch taken when the
+    Frobenius norm alone is not conclusive; and refine_null_band lowering noise-level values of a full-SVD result."""
+    import torch
+    from grassmanntn_b200 import _engine as E
+    rng = np.random.RandomState(23)
+    p, q, r = 384, 512, 12
+    A = rng.randn(p, r) + 1j * rng.randn(p, r)
+    B = rng.randn(r, q) + 1j * rng.randn(r, q)
+    noise = 1e-9 * (rng.randn(p, q) + 1j * rng.randn(p, q))
+    M = A @ B + noise
+    Ur, sr, Vr = np.linalg.svd(M, full_matrices=False)
+    Nn = M - Ur[:, :r] @ (Ur[:, :r].conj().T @ M)
+    two, fro = np.linalg.norm(Nn, 2), np.linalg.norm(Nn)
+    Md = torch.from_numpy(M).cuda()
+    U = torch.from_numpy(np.ascontiguousarray(Ur)).cuda()
+    UhD = torch.from_numpy(np.ascontiguousarray(Ur[:, :r].conj().T)).cuda()
+    thr = 0.5 * (two * 1.3 + fro)                      # Frobenius norm above, Schatten-4 bound below
+    b1 = E.deflated_norm_bound(Md, UhD, U, U.shape[1], r, thr=fro * 2)        # conclusive at once: the Frobenius norm
+    assert abs(b1 - fro) <= 1e-6 * fro
+    b2 = E.deflated_norm_bound(Md, UhD, U, U.shape[1], r, thr=thr)
+    assert two * (1 - 1e-9) <= b2 < fro, (two, b2, fro)
+    assert b2 <= thr, (b2, thr, "the Schatten-4 bound of a flat noise spectrum is ~ n^(1/4) x the 2-norm, far below n^(1/2)")
+    # full-SVD result with two noise values lifted above the rank rule's threshold: refinement certifies rank r
+    M0 = torch.from_numpy(A @ B).cuda()
+    (Uf, sf, Vf), = E.batched_svd([M0.clone()])
+    s_fake = sf.copy()
+    s_fake[r: r + 2] = 3e-14 * sf[0]
+    calls = dict(E.RANK_CHECK_STATS)
+    _, s_ref, _ = E.refine_null_band(M0, (Uf, s_fake, Vf))
+    assert E.RANK_CHECK_STATS["certified"] == calls["certified"] + 1
+    assert int(np.sum(s_ref / (s_ref[0] + 1e-14) > 1e-14)) == r
+    assert np.array_equal(s_ref[:r], sf[:r])
+
+
 def test_chain_is_bitwise_reproducible(gtn):
     """Two executions of the same chain from the same engine state give the same BITS (round-1 review: the Jacobi
     rotation order depended on atomics timing and the norm on the order of atomicAdds).  Now: the dead-row threshold of
