@@ -1107,9 +1107,27 @@ def refine_null_band(M, usv):
     Mc = M.contiguous()
     p, q = Mc.shape
     Uc = U.contiguous()
-    UhD = torch.empty(max(nD * p, 1), dtype=Mc.dtype, device=Mc.device)
+    dt, dev = Mc.dtype, Mc.device
+    UhD = torch.empty(max(nD * p, 1), dtype=dt, device=dev)
     _ctranspose_t(Uc, p, nD, Uc.shape[1], UhD)
-    bound = deflated_norm_bound(Mc, UhD, Uc, Uc.shape[1], nD, thr)
+    # The Jacobi kernel's dominant left vectors carry its backward error (thousands of rotations: the subspace is off
+    # by ~1e-13, measured: the deflated matrix then has norm 2e-13 s_0 and nothing can be certified).  One step of
+    # subspace iteration on the dominant subspace, Yh = (Uh_D M) M^H re-orthonormalised (the small nD x p panel through
+    # the Jacobi kernels themselves), removes the leak to second order before the deflation.
+    Z = torch.empty(nD * q, dtype=dt, device=dev)
+    _gemm_t(UhD, p, Mc, q, Z, q, nD, q, p)
+    Mh = torch.empty(p * q, dtype=dt, device=dev)
+    _ctranspose_t(Mc, p, q, q, Mh)
+    Yh = torch.empty(nD * p, dtype=dt, device=dev)
+    _gemm_t(Z, q, Mh, p, Yh, p, nD, p, q)
+    del Z, Mh
+    (_, sy, Qh), = batched_svd([Yh.view(nD, p)])
+    if len(sy) < nD or not sy[nD - 1] > 0:
+        return usv
+    Qh = Qh.contiguous()
+    Qm = torch.empty(p * nD, dtype=dt, device=dev)
+    _ctranspose_t(Qh, nD, p, p, Qm)                              # p x nD: the refined dominant left vectors
+    bound = deflated_norm_bound(Mc, Qh, Qm, nD, nD, thr)
     if bound <= thr:
         RANK_CHECK_STATS["certified"] += 1
         sv = sv.copy()

@@ -264,6 +264,9 @@ def test_rank_certificate_bounds_and_null_band_refinement(gtn):
     (Uf, sf, Vf), = E.batched_svd([M0.clone()])
     s_fake = sf.copy()
     s_fake[r: r + 2] = 3e-14 * sf[0]
+    # (left vectors additionally polluted at the 1e-12 level, ten times the Jacobi kernel's backward error)
+    gen = torch.Generator(device="cpu"); gen.manual_seed(5)
+    Uf = Uf + 1e-12 * torch.view_as_complex(torch.randn(tuple(Uf.shape) + (2,), generator=gen, dtype=torch.float64)).to(Uf.device)
     calls = dict(E.RANK_CHECK_STATS)
     _, s_ref, _ = E.refine_null_band(M0, (Uf, s_fake, Vf))
     assert E.RANK_CHECK_STATS["certified"] == calls["certified"] + 1
