@@ -697,7 +697,7 @@ __device__ long long gtn_phase_clk[8];
 
 constexpr int CHOL_MAXN = 512;       // global-scratch variant
 constexpr int CHOL_T_SMALL = 256;
-constexpr int CHOL_T_LARGE = 1024;
+
 
 // Diagonally pivoted Cholesky of the Hermitian n x n matrix G (row stride ld), ONE block barrier per
 // pivot and no data movement for the pivoting.  Every warp runs the pivot search redundantly on
@@ -1013,11 +1013,16 @@ constexpr int PK_MAXN = 128;
 constexpr int PK_T = 1024;
 static_assert(PK_T / 8 >= PK_MAXN, "the in-place inverse of the packed Cholesky kernel runs 8 lanes per column");
 __device__ __forceinline__ int tri(int i) { return (i * (i + 1)) >> 1; }
-template <bool CPLX>
+// GLOB = false: the triangle lives in shared memory (n <= PK_MAXN).  GLOB = true (PK_MAXN < n <= CHOL_MAXN: chi = 192
+// ... 256 subspaces): the same algorithm on a triangle in the caller's global scratch (L2-resident: 0.5 MB at n = 256);
+// __syncthreads() orders the block's global accesses.  It replaces the mask-pivoted full-matrix kernel for these
+// sizes (n^3 element updates through L2: 2.9 ms per launch at n = 160).
+template <bool CPLX, bool GLOB>
 __global__ void __launch_bounds__(PK_T, 1)
     chol_whiten_packed_kernel(const typename Elem<CPLX>::T* __restrict__ Gb, typename Elem<CPLX>::T* __restrict__ Tb,
                               const int64_t* __restrict__ g_off, const int64_t* __restrict__ t_off,
-                              const int32_t* __restrict__ ns, int nsplit, double rel_thr, int32_t* __restrict__ kept) {
+                              const int32_t* __restrict__ ns, int nsplit, double rel_thr, int32_t* __restrict__ kept,
+                              c128* __restrict__ scratch, int64_t scratch_stride) {
   // Round-2 rewrite (after `ncu --set full` of the first version: 4.0 M warp instructions per matrix, issue slots 67 %
   // busy, 13 % FP64 -- bound by index arithmetic: pivoting by masks made every pivot walk the WHOLE triangle, and the
   // inverse chased the pivot order through two indirections per element).  Now the pivoting is PHYSICAL: pivot k swaps
@@ -1027,9 +1032,12 @@ __global__ void __launch_bounds__(PK_T, 1)
   using T = typename Elem<CPLX>::T;
   extern __shared__ __align__(16) unsigned char sm_raw[];
   const int n = ns[blockIdx.x];
-  c128* Gp = reinterpret_cast<c128*>(sm_raw);
-  __shared__ c128 vb[2][PK_MAXN];
-  __shared__ int perm[PK_MAXN];
+  constexpr int NMAX = GLOB ? CHOL_MAXN : PK_MAXN;
+  c128* Gp;
+  if constexpr (GLOB) Gp = scratch + int64_t(blockIdx.x) * scratch_stride;
+  else Gp = reinterpret_cast<c128*>(sm_raw);
+  __shared__ c128 vb[2][NMAX];
+  __shared__ int perm[NMAX];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool stamp = tid == 0 && blockIdx.x == 0;
   if (stamp) gtn_phase_clk[0] = clock64();
@@ -1119,30 +1127,42 @@ __global__ void __launch_bounds__(PK_T, 1)
   // ---- X = L_r^{-1} in place, row by row:  X[a][b] = -(1 / L[a][a]) sum_{j = b .. a-1} L[a][j] X[j][b],  X[a][a] = 1 / L[a][a].
   // All columns advance together (8 lanes per column); row a of L is read by everybody before it is overwritten.
   {
-    const int b = tid >> 3, sub = tid & 7;
+    constexpr int NCH = NMAX / (PK_T / 8);          // column chunks of 128 (one in shared memory, up to 4 in global)
+    const int b0 = tid >> 3, sub = tid & 7;
     for (int a = 0; a < r; ++a) {
       const c128* La = Gp + tri(a);
-      double sr = 0.0, si = 0.0;
-      if (b < a) {
-        for (int jj = b + sub; jj < a; jj += 8) {
-          const c128 l = La[jj];
-          const c128 x = Gp[tri(jj) + b];
-          sr += l.re * x.re - l.im * x.im;
-          si += l.re * x.im + l.im * x.re;
-        }
-      }
+      double sr[NCH], si[NCH];
 #pragma unroll
-      for (int o = 4; o > 0; o >>= 1) {
-        sr += __shfl_xor_sync(0xffffffffu, sr, o);
-        si += __shfl_xor_sync(0xffffffffu, si, o);
+      for (int ch = 0; ch < NCH; ++ch) {
+        const int b = b0 + ch * (PK_T / 8);
+        sr[ch] = 0.0; si[ch] = 0.0;
+        if (b < a) {
+          for (int jj = b + sub; jj < a; jj += 8) {
+            const c128 l = La[jj];
+            const c128 x = Gp[tri(jj) + b];
+            sr[ch] += l.re * x.re - l.im * x.im;
+            si[ch] += l.re * x.im + l.im * x.re;
+          }
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+          sr[ch] += __shfl_xor_sync(0xffffffffu, sr[ch], o);
+          si[ch] += __shfl_xor_sync(0xffffffffu, si[ch], o);
+        }
       }
       const double d = 1.0 / La[a].re;
       __syncthreads();
-      if (sub == 0 && b <= a) {
-        c128 o;
-        if (b == a) { o.re = d; o.im = 0.0; }
-        else { o.re = -sr * d; o.im = -si * d; }
-        Gp[tri(a) + b] = o;
+      if (sub == 0) {
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+          const int b = b0 + ch * (PK_T / 8);
+          if (b <= a) {
+            c128 o;
+            if (b == a) { o.re = d; o.im = 0.0; }
+            else { o.re = -sr[ch] * d; o.im = -si[ch] * d; }
+            Gp[tri(a) + b] = o;
+          }
+        }
       }
       __syncthreads();
     }
@@ -1321,26 +1341,29 @@ extern "C" int gtn_chol_whiten(const void* G, void* T, int dtype, const int64_t*
     const size_t smem = (size_t(max_n) * (max_n + 1) / 2) * 16;        // the packed lower triangle
     static size_t attr = 0;
     if (smem > attr) {
-      int e = set_smem(chol_whiten_packed_kernel<true>, smem);
-      if (!e) e = set_smem(chol_whiten_packed_kernel<false>, smem);
+      int e = set_smem(chol_whiten_packed_kernel<true, false>, smem);
+      if (!e) e = set_smem(chol_whiten_packed_kernel<false, false>, smem);
       if (e) return e;
       attr = smem;
     }
     if (dtype == GTN_C128)
-      chol_whiten_packed_kernel<true><<<nprob, PK_T, smem, s>>>((const c128*)G, (c128*)T, g_off_dev, t_off_dev, n_dev,
-                                                                 nsplit, rel_thr, kept_dev);
+      chol_whiten_packed_kernel<true, false><<<nprob, PK_T, smem, s>>>((const c128*)G, (c128*)T, g_off_dev, t_off_dev,
+                                                                        n_dev, nsplit, rel_thr, kept_dev, nullptr, 0);
     else
-      chol_whiten_packed_kernel<false><<<nprob, PK_T, smem, s>>>((const double*)G, (double*)T, g_off_dev, t_off_dev,
-                                                                  n_dev, nsplit, rel_thr, kept_dev);
+      chol_whiten_packed_kernel<false, false><<<nprob, PK_T, smem, s>>>((const double*)G, (double*)T, g_off_dev,
+                                                                         t_off_dev, n_dev, nsplit, rel_thr, kept_dev,
+                                                                         nullptr, 0);
   } else {
+    // PK_MAXN < n <= CHOL_MAXN: the packed physical-pivot kernel on a triangle in the global scratch
     if (!scratch) return GTN_ERR_BAD_ARG;
     const int64_t stride = gtn_chol_whiten_scratch_elems(max_n);
     if (dtype == GTN_C128)
-      chol_whiten_kernel<true, CHOL_T_LARGE, true, 0><<<nprob, CHOL_T_LARGE, 0, s>>>(
-          (const c128*)G, (c128*)T, g_off_dev, t_off_dev, n_dev, nsplit, rel_thr, kept_dev, (c128*)scratch, stride);
+      chol_whiten_packed_kernel<true, true><<<nprob, PK_T, 0, s>>>((const c128*)G, (c128*)T, g_off_dev, t_off_dev, n_dev,
+                                                                    nsplit, rel_thr, kept_dev, (c128*)scratch, stride);
     else
-      chol_whiten_kernel<false, CHOL_T_LARGE, true, 0><<<nprob, CHOL_T_LARGE, 0, s>>>(
-          (const double*)G, (double*)T, g_off_dev, t_off_dev, n_dev, nsplit, rel_thr, kept_dev, (c128*)scratch, stride);
+      chol_whiten_packed_kernel<false, true><<<nprob, PK_T, 0, s>>>((const double*)G, (double*)T, g_off_dev, t_off_dev,
+                                                                     n_dev, nsplit, rel_thr, kept_dev, (c128*)scratch,
+                                                                     stride);
   }
   return (int)cudaGetLastError();
 }

@@ -61,7 +61,7 @@ def _gram(n, rank, cplx, seed, cond=1e6):
 
 
 @pytest.mark.parametrize("cplx", [True, False])
-@pytest.mark.parametrize("n", [24, 48, 80, 96, 128, 160])
+@pytest.mark.parametrize("n", [24, 48, 80, 96, 128, 160, 256])
 def test_chol_whiten_variants(gtn, n, cplx):
     import torch
     for rank, nsplit in ((n, 1), (n, 4), (max(n - 7, 1), 1)):
