@@ -479,6 +479,7 @@ class block:
     @property
     def data(self):
         bt = self._bt
+        _ops.settle(bt)                 # the views are writable: tensors that still read this storage are written first
         nf = len(bt.faxes)
         arr = np.empty((2,) * nf, dtype=object)
         for p in bt.patterns():

@@ -313,6 +313,13 @@ def sigma_bits(pi, n):
     return v
 
 
+def _register_dependent(src, bt):
+    """src remembers (weakly) the unwritten permutations that read it: _ops.settle(src) writes them before src's
+    storage is handed out for modification"""
+    import weakref
+    src.__dict__.setdefault("_deps", weakref.WeakSet()).add(bt)
+
+
 class BT:
     """Parity-blocked Grassmann tensor on the device."""
 
@@ -325,7 +332,29 @@ class BT:
         self.faxes = tuple(a for a, s in enumerate(self.stats) if s in FERMI)
         self.off = {}        # pattern -> element offset (stored blocks only)
         self.zero = set()    # stored blocks known to be identically zero
-        self.buf = None
+        self._lazy = None    # a pending permutation of another tensor (_ops.LazyPermute): `off` describes the buffer
+        self._buf = None     # it WILL have; consumers that pack anyway read the source and skip this pass
+
+    # ---- storage
+    @property
+    def buf(self):
+        b = self._buf
+        if b is None and self._lazy is not None:
+            lz, self._lazy = self._lazy, None
+            self.__dict__.pop("_key", None)
+            b = self._buf = lz.materialise()
+        return b
+
+    @buf.setter
+    def buf(self, value):
+        self._buf = value
+        if self._lazy is not None:
+            self._lazy = None
+            self.__dict__.pop("_key", None)
+
+    def pending(self):
+        """the unwritten permutation this tensor stands for, or None"""
+        return self._lazy if self._buf is None else None
 
     # ---- geometry
     @property
@@ -344,12 +373,17 @@ class BT:
     def block_size(self, pat):
         return math.prod(self.block_shape(pat)) if self.ndim else 1
 
-    def alloc(self, pats=None, zero=False):
+    def plan_blocks(self, pats=None):
+        """lay the blocks `pats` out back to back (offsets only); returns the number of elements"""
         pats = list(self.patterns()) if pats is None else list(pats)
         total = 0
         for p in pats:
             self.off[p] = total
             total += self.block_size(p)
+        return total
+
+    def alloc(self, pats=None, zero=False):
+        total = self.plan_blocks(pats)
         dev = require_cuda()
         self.buf = (torch.zeros if zero else torch.empty)(max(total, 1), dtype=self.dtype, device=dev)
         return self
@@ -372,12 +406,23 @@ class BT:
         """hashable description of the layout (cached: a BT's layout is not changed after it has
         been handed to an op)"""
         k = self.__dict__.get("_key")
-        if k is None or k[0] != (len(self.off), len(self.zero), self.fmt):
-            k = ((len(self.off), len(self.zero), self.fmt),
+        lz = self.pending()
+        if k is None or k[0] != (len(self.off), len(self.zero), self.fmt, lz is None):
+            k = ((len(self.off), len(self.zero), self.fmt, lz is None),
                  (self.stats, self.e, self.o, str(self.dtype), self.fmt,
-                  tuple(sorted((p, o) for p, o in self.off.items())), tuple(sorted(self.zero))))
+                  tuple(sorted((p, o) for p, o in self.off.items())), tuple(sorted(self.zero)))
+                 + (() if lz is None else (lz.sig,)))
             self._key = k
         return k[1]
+
+    def stored_elems(self):
+        """elements of the stored blocks (known without the buffer)"""
+        return sum(self.block_size(p) for p in self.off)
+
+    def layout_key(self):
+        """key() of the written tensor (the same whether or not it is still an unwritten permutation)"""
+        k = self.key()
+        return k[:-1] if self.pending() is not None else k
 
     def leg(self, a):
         return (self.stats[a], self.e[a], self.o[a])
@@ -386,10 +431,18 @@ class BT:
         r = BT(self.stats, self.e, self.o, self.dtype, self.fmt)
         r.off = dict(self.off)
         r.zero = set(self.zero)
-        r.buf = self.buf.clone()
+        lz = self.pending()
+        if lz is not None:
+            r._lazy = lz                 # the copy of an unwritten permutation is the same unwritten permutation
+            _register_dependent(lz.src, r)
+        else:
+            r.buf = self.buf.clone()
         return r
 
     def sumsq(self, pats=None):
+        lz = self.pending()
+        if lz is not None and pats is None:
+            return lz.src.sumsq()        # a signed permutation has the norm of its source
         acc = torch.zeros(1, dtype=torch.float64, device=self.buf.device)
         code = dtype_code(self.dtype)
         covered = sum(self.block_size(p) for p in self.off)
@@ -421,6 +474,12 @@ class BT:
 
     def scale_(self, s):
         s = complex(s)
+        lz = self.pending()
+        if lz is not None:               # written once, scaled on the way
+            self._lazy = None
+            self.__dict__.pop("_key", None)
+            self._buf = lz.materialise(s.real if s.imag == 0.0 else s)
+            return self
         check(lib.gtn_scale(_ptr(self.buf), self.buf.numel(), dtype_code(self.dtype), s.real, s.imag, _stream()),
               "gtn_scale")
         count()

@@ -40,6 +40,78 @@ def _err(msg):
 
 
 # ------------------------------------------------------------------------------------------------
+#  unwritten permutations (no permuted copy between two ops that both move the data)
+# ------------------------------------------------------------------------------------------------
+LAZY_PERMUTE = bool(int(os.environ.get("GTN_LAZY_PERMUTE", "1")))
+LAZY_STATS = {"created": 0, "fused": 0, "materialised": 0}
+
+
+class LazyPermute:
+    """A tensor that is a signed leg permutation (optionally conjugated) of a stored tensor `src` and has not been
+    written: leg p of the tensor is leg perm[p] of src, the value carries (-1)^e with e the GF(2) form
+    sum_{a in alpha} p_a + sum_{a in beta} sigma_a + sum_{{a,b} in Q} p_a p_b over the legs of src.
+    The reference writes every such intermediate (T1 = einsum('ijkl->jkli', T) at gauge2d.py:1673, the leg order of
+    VV / UU at :1727-1732, the conjugates at :1974 / :1985) and the consumer then moves the data once more to build
+    its matrix; Grassmann reorderings compose (the exponents add), so a consumer that packs anyway (PackPlan,
+    the matricisation of a decomposition) reads src through the composed tables: one pass and one launch less per
+    pair.  Any other access (`BT.buf`) writes the tensor first, with the launch plan it was created with."""
+    __slots__ = ("src", "perm", "alpha", "beta", "Q", "conj", "sig", "_mat", "__weakref__")
+
+    def __init__(self, src, perm, alpha, beta, Q, conj, mat):
+        assert src.pending() is None
+        self.src, self.perm = src, tuple(perm)
+        self.alpha, self.beta, self.Q = frozenset(alpha), frozenset(beta), frozenset(Q)
+        self.conj = bool(conj)
+        self.sig = ("lazy", src.key(), self.perm, tuple(sorted(self.alpha)), tuple(sorted(self.beta)),
+                    tuple(sorted(tuple(sorted(pr)) for pr in self.Q)), self.conj)
+        self._mat = mat                      # (source buffer, scale) -> the tensor's buffer
+
+    def materialise(self, scale=1.0):
+        LAZY_STATS["materialised"] += 1
+        return self._mat(self.src.buf, scale)
+
+
+def _attach_lazy(res, lz):
+    """make the (buffer-less) BT `res` stand for lz; src remembers it so that handing out writable views of src
+    (block.data) can write its dependents first"""
+    res._buf, res._lazy = None, lz
+    res.__dict__.pop("_key", None)
+    _engine_mod._register_dependent(lz.src, res)
+    LAZY_STATS["created"] += 1
+    return res
+
+
+def settle(bt):
+    """write every unwritten permutation of bt (call before bt's storage is modified in place)"""
+    for d in list(bt.__dict__.get("_deps", ())):
+        d.buf
+    bt.__dict__.pop("_deps", None)
+
+
+def _through_lazy(bt, labels, assigned):
+    """the same pack expressed on the source of an unwritten permutation: (src, labels of src's legs, total sign
+    assignment, conj)"""
+    lz = bt.pending()
+    inv = [0] * len(lz.perm)
+    for p_, a in enumerate(lz.perm):
+        inv[a] = p_
+    src_labels = [labels[inv[a]] for a in range(len(lz.perm))]
+    alpha, beta, Q = set(assigned[0]), set(assigned[1]), set(assigned[2])
+    for a in lz.alpha:
+        alpha ^= {src_labels[a]}
+    for a in lz.beta:
+        beta ^= {src_labels[a]}
+    for pr in lz.Q:
+        a, b = tuple(pr)
+        x, y = src_labels[a], src_labels[b]
+        if x == y:
+            alpha ^= {x}                 # both legs on the diagonal of a trace: p * p = p
+        else:
+            Q ^= {frozenset((x, y))}
+    return lz.src, src_labels, (alpha, beta, Q), lz.conj
+
+
+# ------------------------------------------------------------------------------------------------
 #  packing an operand into [batch][rows][cols][t]
 # ------------------------------------------------------------------------------------------------
 def _label_legs(bt, labels):
@@ -62,7 +134,7 @@ def _compact_sizes(layR, layC):
     return re_ * ce + ro * co, re_ * ce
 
 
-def _pack_jobs(bt, labels, info, groups, lays, assigned, out_elems_mult=None, compact=False):
+def _pack_jobs(bt, labels, info, groups, lays, assigned, out_elems_mult=None, compact=False, conj=False):
     """Jobs that copy every live block of `bt` into the packed buffer.
     groups: dict name -> list of labels for 'B' (batch), 'R', 'C', 'T'; lays: GroupLayout per name.
     assigned: (alpha labels, beta labels, Q pairs) evaluated by this operand.
@@ -120,7 +192,7 @@ def _pack_jobs(bt, labels, info, groups, lays, assigned, out_elems_mult=None, co
         for pr in q_pairs:
             x, y = tuple(pr)
             const ^= par[x] & par[y]
-        jobs.append(build_job(legs, beta=beta, const=const, in_base=bt.off[pat], out_base=out_base))
+        jobs.append(build_job(legs, beta=beta, const=const, conj=conj, in_base=bt.off[pat], out_base=out_base))
     return jobs, used
 
 
@@ -142,7 +214,14 @@ class PackPlan:
     def __init__(self, bt, labels, info, groups, assigned, restrict_even=None, compact=False):
         self.lays = lays = {g: group_layout([info[ch] for ch in groups[g]]) for g in ("B", "R", "C", "T")}
         self.compact = bool(compact and restrict_even and COMPACT_PACK and not groups["T"] and bt.is_even())
-        jobs, used = _pack_jobs(bt, labels, info, groups, lays, assigned, compact=self.compact)
+        self.fused = bt.pending() is not None
+        conj = False
+        if self.fused:
+            # the operand is an unwritten permutation: pack straight from its source through the composed tables
+            bt, labels, assigned, conj = _through_lazy(bt, labels, assigned)
+            LAZY_STATS["fused"] += 1
+        self.src_labels, self.assigned, self.conj = list(labels), assigned, conj
+        jobs, used = _pack_jobs(bt, labels, info, groups, lays, assigned, compact=self.compact, conj=conj)
         self.plan = PermutePlan(jobs)
         self.total = lays["B"].total * lays["R"].total * lays["C"].total * lays["T"].total
         if self.compact:
@@ -163,12 +242,15 @@ class PackPlan:
         self.tcols = lays["T"].total
 
     def run(self, bt):
-        dev = bt.buf.device
-        buf = _alloc(torch.empty if self.full else torch.zeros, max(self.total, 1), bt.dtype, dev)
-        self.plan.run(bt.buf, buf)
+        return self.run_src(bt.pending().src.buf if self.fused else bt.buf)
+
+    def run_src(self, src, scale=1.0):
+        dev = src.device
+        buf = _alloc(torch.empty if self.full else torch.zeros, max(self.total, 1), src.dtype, dev)
+        self.plan.run(src, buf, scale)
         if self.reduce:
-            red = torch.empty(max(self.rows, 1), dtype=bt.dtype, device=dev)
-            check(lib.gtn_rowsum(_ptr(buf), _ptr(red), self.rows, self.tcols, dtype_code(bt.dtype), _stream()),
+            red = torch.empty(max(self.rows, 1), dtype=src.dtype, device=dev)
+            check(lib.gtn_rowsum(_ptr(buf), _ptr(red), self.rows, self.tcols, dtype_code(src.dtype), _stream()),
                   "gtn_rowsum")
             count()
             buf = red
@@ -273,8 +355,26 @@ def _bt_from_layout(info, labels, dtype, lay, even, buf):
         if lay.size[p] > 0:
             res.off[p] = lay.offset[p]
     # the layout is parity-sorted: for an even tensor the (never written) odd part is the tail
-    res.buf = buf[: max(lay.even_total, 1)] if even else buf
+    if buf is not None:
+        res.buf = buf[: max(lay.even_total, 1)] if even else buf
     return res
+
+
+def _lazy_result(pp, info, out, x):
+    """the result of a pure permutation whose pack plan is pp, unwritten (LazyPermute); a permutation of an unwritten
+    permutation refers to the stored tensor underneath (chains collapse)"""
+    lay, even = pp.lays["R"], pp.even
+    res = _bt_from_layout(info, out, x.dtype, lay, even, None)
+    root = x.pending().src if pp.fused else x
+    ax = {ch: a for a, ch in enumerate(pp.src_labels)}
+    al, be, Q = pp.assigned
+
+    def mat(src_buf, scale):
+        buf = pp.run_src(src_buf, scale)
+        return buf[: max(lay.even_total, 1)] if even else buf
+    lz = LazyPermute(root, [ax[ch] for ch in out], {ax[c] for c in al}, {ax[c] for c in be},
+                     {frozenset(ax[c] for c in pr) for pr in Q}, pp.conj, mat)
+    return _attach_lazy(res, lz)
 
 
 def _plan_single(labels, output, bt, prog):
@@ -286,8 +386,12 @@ def _plan_single(labels, output, bt, prog):
             raise NotImplementedError("einsum: a repeated index that is kept in the output is not supported")
     groups = {"B": [], "R": list(out), "C": [], "T": t_labels}
     pp = PackPlan(bt, labels, info, groups, (prog.alpha, prog.beta, prog.Q))
+    pure = (output is not None and not t_labels and len(set(labels)) == len(labels)
+            and len(out) == len(labels) and len(labels) > 0)
 
     def run(ops):
+        if pure and LAZY_PERMUTE:
+            return _lazy_result(pp, info, out, ops[0])
         buf = pp.run(ops[0])
         if output is None:
             return _scalar(buf)
@@ -420,14 +524,15 @@ def _plan_pair(inputs, output, ops, prog):
         bufL, bufR = ppL.run(Lop), ppR.run(Rop)
         r = BT(res_meta[0], res_meta[1], res_meta[2], A_.dtype)
         r.off = dict(res_off)
-        r.buf = _alloc(torch.empty, max(acc, 1), A_.dtype, A_.buf.device)
+        dev_ = bufL.device
+        r.buf = _alloc(torch.empty, max(acc, 1), A_.dtype, dev_)
         if Ktot == 0:
             r.buf.zero_()
         elif Mtot == 1 and Ntot == 1 and Btot == 1 and len(groups) == 1:
             # full contraction to a scalar: 1 x K x 1 is a dot product, not a GEMM
             g0 = groups[0]
             nparts = 1184
-            part = torch.empty(2 * nparts, dtype=torch.float64, device=A_.buf.device)
+            part = torch.empty(2 * nparts, dtype=torch.float64, device=dev_)
             with prof_region("dot", 2, 2 * g0["k"] * bufL.element_size()):
                 check(lib.gtn_dot(_ptr(bufL[g0["a_off"]:]), _ptr(bufR[g0["b_off"]:]), g0["k"], dtype_code(A_.dtype),
                                   _ptr(r.buf), _ptr(part), nparts, _stream()), "gtn_dot")
@@ -462,6 +567,8 @@ def _plan_permute(bt, labels, out_labels):
     pp = PackPlan(bt, labels, info, groups, (set(), set(), set()))
 
     def run(x):
+        if LAZY_PERMUTE and len(labels) > 0:
+            return _lazy_result(pp, info, out_labels, x)
         return _bt_from_layout(info, out_labels, x.dtype, pp.lays["R"], pp.even, pp.run(x))
     return run
 
@@ -497,8 +604,13 @@ def _join_sign_terms(legs_idx, stats, fermionic):
     return alpha, beta, Q
 
 
-def _block_jobs(bt, live, alpha, beta, Q, place):
-    """jobs over blocks with leg-level sign terms; place(pat, bshape) -> (out_base, out_strides) or None"""
+def _block_jobs(bt, live, alpha, beta, Q, place, through=False):
+    """jobs over blocks with leg-level sign terms; place(pat, bshape) -> (out_base, out_strides) or None.
+    through: when bt is an unwritten permutation (LazyPermute) the jobs read its SOURCE through the composed sign
+    program -- the caller then runs the plan on _src_buf(bt) and takes its live blocks from _live_of(bt)."""
+    lz = bt.pending() if through else None
+    if lz is not None:
+        return _block_jobs_through(bt, lz, live, alpha, beta, Q, place)
     jobs = []
     for pat in live:
         pis = dict(zip(bt.faxes, pat))
@@ -521,6 +633,64 @@ def _block_jobs(bt, live, alpha, beta, Q, place):
             const ^= pis[x] & pis[y]
         jobs.append(build_job(legs, beta=bflags, const=const, conj=conj, in_base=bt.off[pat], out_base=out_base))
     return jobs
+
+
+def _block_jobs_through(bt, lz, live, alpha, beta, Q, place):
+    """_block_jobs of the tensor bt = (signed permutation lz of lz.src), reading lz.src: leg p of bt is leg lz.perm[p]
+    of the source; the sign exponents add (alpha / beta / Q are over bt's legs, lz's over the source's)"""
+    src, perm = lz.src, lz.perm
+    n = bt.ndim
+    A_ = set(perm[a] for a in alpha) ^ set(lz.alpha)
+    B_ = set(perm[a] for a in beta) ^ set(lz.beta)
+    Q_ = {frozenset((perm[x], perm[y])) for x, y in (tuple(pr) for pr in Q)} ^ set(lz.Q)
+    live = set(live)
+    jobs = []
+    LAZY_STATS["fused"] += 1
+    for spat in src.live():
+        spis = dict(zip(src.faxes, spat))
+        pat = tuple(spis[perm[p]] for p in bt.faxes)
+        if pat not in live:
+            continue
+        bshape = bt.block_shape(pat)
+        pl = place(pat, bshape)
+        if pl is None:
+            continue
+        out_base, ostr, conj = pl
+        sshape = src.block_shape(spat)
+        sstr = _row_strides(sshape)
+        legs, bflags = [None] * n, [0] * n
+        for p in range(n):
+            a = perm[p]
+            q = sigma_bits(spis[a], sshape[a]) if a in B_ else None
+            legs[a] = lin_leg(sshape[a], sstr[a], ostr[p], q=q)
+            bflags[a] = 1 if a in B_ else 0
+        const = 0
+        for a in A_:
+            const ^= spis[a]
+        for pr in Q_:
+            x, y = tuple(pr)
+            const ^= spis[x] & spis[y]
+        jobs.append(build_job(legs, beta=bflags, const=const, conj=bool(conj) != lz.conj, in_base=src.off[spat],
+                              out_base=out_base))
+    return jobs
+
+
+def _src_buf(bt):
+    """the buffer a plan built by _block_jobs(..., through=True) on bt reads"""
+    lz = bt.pending()
+    return bt.buf if lz is None else lz.src.buf
+
+
+def _live_of(bt):
+    """live blocks of bt; for an unwritten permutation those its source actually holds"""
+    lz = bt.pending()
+    if lz is None:
+        return bt.live()
+    have = set()
+    for spat in lz.src.live():
+        spis = dict(zip(lz.src.faxes, spat))
+        have.add(tuple(spis[lz.perm[p]] for p in bt.faxes))
+    return [p for p in bt.live() if p in have]
 
 
 def _decompose_prepare(bt, nl, kind):
@@ -554,7 +724,7 @@ def _decompose_prepare(bt, nl, kind):
         # one side purely bosonic: an even tensor lives entirely in the parity-0 rows / columns
         rows = {0: layR.sector(0)}
         cols = {0: layC.sector(0)}
-    live = bt.live()
+    live = _live_of(bt)
     dev = require_cuda()
     fpos_R = [a for a in Rl if ferm[a]]
     fpos_C = [a for a in Cl if ferm[a]]
@@ -579,10 +749,10 @@ def _decompose_prepare(bt, nl, kind):
             base = offs[s] + (layR.offset[pr] - rows[s][0]) * ld + (layC.offset[pc] - cols[s][0])
             sr, sc = layR.strides(pr), layC.strides(pc)
             return base, [x * ld for x in sr] + list(sc), False
-        return PermutePlan(_block_jobs(bt, live, alpha, beta, Q, place))
+        return PermutePlan(_block_jobs(bt, live, alpha, beta, Q, place, through=True))
     plan = _cached(("svdpack", bt.key(), nl), build_pack)
     Mbuf = (torch.empty if len(live) >= nlive_needed else torch.zeros)(max(acc, 1), dtype=bt.dtype, device=dev)
-    plan.run(bt.buf, Mbuf)
+    plan.run(_src_buf(bt), Mbuf)
     mats = [Mbuf[offs[s]: offs[s] + sizes[s][0] * sizes[s][1]].view(sizes[s][0], sizes[s][1]) for s in sectors]
     if kind == "eig":
         for Mx in mats:
@@ -909,9 +1079,9 @@ def hconjugate_bt(bt, nl):
     fl = {a: flip(bt.stats[a]) for a in range(n)}
     a2, b2, q2 = _join_sign_terms(Cl, fl, ferm)
     alpha, beta, Q = a1 ^ a2, b1 ^ b2, q1 ^ q2
-    live = bt.live()
+    live = _live_of(bt)
     npat = lambda pat: tuple(dict(zip(bt.faxes, pat))[a] for a in new_order if ferm[a])
-    res.alloc([npat(p) for p in live])
+    total = res.plan_blocks([npat(p) for p in live])
 
     def build():
         def place(pat, bshape):
@@ -921,9 +1091,28 @@ def hconjugate_bt(bt, nl):
             for newpos, a in enumerate(new_order):
                 ostr[a] = ostr_new[newpos]
             return res.off[op], ostr, True
-        return PermutePlan(_block_jobs(bt, live, alpha, beta, Q, place))
-    _cached(("hconj", bt.key(), nl), build).run(bt.buf, res.buf)
+        return PermutePlan(_block_jobs(bt, live, alpha, beta, Q, place, through=True))
+    plan = _cached(("hconj", bt.key(), nl), build)
+
+    def mat(src_buf, scale):
+        out = _alloc(torch.empty, max(total, 1), src_buf.dtype, src_buf.device)
+        plan.run(src_buf, out, scale)
+        return out
     res.zero = set()
+    if LAZY_PERMUTE and this_fmt != "matrix" and n > 0:
+        # the conjugate is a signed, conjugated permutation: left unwritten for the contraction that packs it
+        # (hotrg3dz: cA = AA.hconjugate(...) feeds the Gram contraction only, reference gauge2d.py:1974-1992)
+        lz0 = bt.pending()
+        if lz0 is None:
+            root, pm, conj0 = bt, list(range(n)), False
+            A0, B0, Q0 = set(), set(), set()
+        else:
+            root, pm, conj0 = lz0.src, lz0.perm, lz0.conj
+            A0, B0, Q0 = set(lz0.alpha), set(lz0.beta), set(lz0.Q)
+        lz = LazyPermute(root, [pm[a] for a in new_order], {pm[a] for a in alpha} ^ A0, {pm[a] for a in beta} ^ B0,
+                         {frozenset(pm[a] for a in pr) for pr in Q} ^ Q0, not conj0, mat)
+        return _attach_lazy(res, lz)
+    res._buf = mat(_src_buf(bt), 1.0)
     if this_fmt == "matrix":
         res = bt_switch_format(res)
     return res

@@ -162,7 +162,8 @@ def stream_steps(host_inputs, step, prepare=None, n_out=2):
         if prepare is not None:
             prepare(X)
         Y, val = step(X)
-        done = torch.cuda.Event()
+        _bt_of(Y)[0].buf                                     # (a result that is an unwritten permutation is written here,
+        done = torch.cuda.Event()                            #  on the compute stream, while its source is still valid)
         done.record(cur)
         in_free[i % 2] = done
         k = i % n_out

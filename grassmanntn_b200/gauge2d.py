@@ -45,8 +45,13 @@ SPEC_STATS = {"speculated": 0, "failed": 0}       # decompositions run speculati
 
 
 def _normalised(T):
+    """(T / |T|, |T|) for a step's own un-normalised result: scaled in place (T is not used again by the callers);
+    a result that is still an unwritten permutation (_ops.LazyPermute) is written once, scaled on the way"""
     Tnorm = T.norm
-    return T * (1.0 / Tnorm), Tnorm
+    if getattr(T, "_bt", None) is None or getattr(T, "_data", None) is not None:
+        return T * (1.0 / Tnorm), Tnorm
+    T._bt.scale_(1.0 / Tnorm)
+    return T, Tnorm
 
 
 def zcap(T):
@@ -126,7 +131,7 @@ def _wrap_bt(bt, like):
 
 
 def _step_key(name, T, *params):
-    return (name, type(T).__name__, getattr(T, "encoder", None), _bt_of(T).key()) + params
+    return (name, type(T).__name__, getattr(T, "encoder", None), _bt_of(T).layout_key()) + params
 
 
 class _StepGraph:
@@ -141,7 +146,9 @@ class _StepGraph:
     def __init__(self, T, body):
         import torch
         from . import _cabi, _engine as E
-        self.static = _bt_of(T).clone()
+        _bt_of(T).buf                                 # (an unwritten permutation is written: the graph needs an input
+        self.static = _bt_of(T).clone()               #  buffer of its own, not a view of this particular tensor)
+        assert self.static.pending() is None
         self.key = self.static.key()
         Tin = _wrap_bt(self.static, T)
         self.norm_host = torch.zeros(1, dtype=torch.float64).pin_memory()
@@ -188,7 +195,7 @@ class _StepGraph:
     def replay(self, T):
         from . import _cabi
         bt = _bt_of(T)
-        if bt.key() != self.key or bt.buf.numel() != self.static.buf.numel():
+        if bt.layout_key() != self.key or bt.buf.numel() != self.static.buf.numel():
             return None
         self.static.buf.copy_(bt.buf)
         self.g.replay()
@@ -223,7 +230,7 @@ def _graph_step(key, T, body):
     if sg is None:
         n, _ = _steady.get(key, (0, None))
         bt = _bt_of(T)
-        if n < 2 or bt.buf.numel() * bt.buf.element_size() > STEP_GRAPH_MAX_BYTES:
+        if n < 2 or bt.stored_elems() * (16 if bt.dtype.is_complex else 8) > STEP_GRAPH_MAX_BYTES:
             return None
         import time as _time
         t0 = _time.perf_counter()

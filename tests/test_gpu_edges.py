@@ -512,3 +512,83 @@ def test_dense_data_inplace_edit_is_seen(gtn):
     view = X.data                      # a result keeps its block form until .data is asked for
     view *= 2.0
     assert abs(gtn.einsum('ii', X) - 2 * gtn.einsum('ii', gtn.einsum('ij->ji', A))) <= 1e-12 * max(abs(ref), 1.0)
+
+
+# ---------------------------------------------------------------- unwritten permutations (_ops.LazyPermute)
+def _bits(gtn, x):
+    """every stored element of a result, as numpy (forces an unwritten permutation to be written)"""
+    if isinstance(x, (tuple, list)):
+        return [_bits(gtn, y) for y in x]
+    bt = x._bt if getattr(x, "_bt", None) is not None else x._get_bt()
+    return (dict(bt.off), bt.buf.cpu().numpy().copy())
+
+
+def _same(a, b):
+    if isinstance(a, list):
+        return len(a) == len(b) and all(_same(x, y) for x, y in zip(a, b))
+    return a[0] == b[0] and a[1].shape == b[1].shape and np.array_equal(a[1], b[1])
+
+
+def _lazy_chain(gtn, T, fmt):
+    X = T.toblock() if fmt == "block" else T
+    P1 = gtn.einsum('ijkl->jkli', X)                       # signed permutation
+    P2 = gtn.einsum('abcd->dcab', P1)                      # of an unwritten one: refers to X
+    H = P2.hconjugate('ab|cd')                             # conjugated + signed + permuted, still unwritten
+    R1 = gtn.einsum('abcd,abef->cdef', H, P1)              # both operands packed from X
+    R2 = gtn.einsum('abcd,dbef->feac', P2, X)              # GEMM result left in its natural leg order ...
+    R3 = gtn.einsum('feac,face', R2, P1)                   # ... and packed from there (scalar)
+    tr = gtn.einsum('ijij', P1)                            # trace over legs of an unwritten permutation
+    U, S, V = P1.svd('ab|cd')                              # matricised from X
+    U2, S2, V2 = H.svd('ab|cd', 5)
+    HH = H.hconjugate('ab|cd')                             # conjugate of an unwritten conjugate
+    n1 = P2.norm
+    Sc = P2 * 0.5
+    return [P1, P2, H, R1, R2, U, S, V, U2, S2, V2, HH, Sc], [R3, tr, n1]
+
+
+@pytest.mark.parametrize("fmt", ["dense", "block"])
+@pytest.mark.parametrize("cplx", [True, False])
+def test_unwritten_permutations_equal_written_ones(gtn, fmt, cplx):
+    """a chain of leg permutations, conjugates, contractions, traces and decompositions with the intermediates left
+    unwritten (consumers read the stored source through composed sign tables) against the same chain with every
+    intermediate written: identical bits everywhere (signs are exact and each element is moved, never recomputed);
+    only norms may differ in the last place (summation order)."""
+    from grassmanntn_b200 import _ops
+    rng = np.random.RandomState(91)
+    _, T = _mk(gtn, (4, 8, 4, 8), (1, 1, -1, -1), rng, cplx=cplx)
+    saved = _ops.LAZY_PERMUTE
+    try:
+        _ops.LAZY_PERMUTE = False
+        ten0, sc0 = _lazy_chain(gtn, T, fmt)
+        ten0 = _bits(gtn, ten0)
+        _ops.LAZY_PERMUTE = True
+        for k in _ops.LAZY_STATS:
+            _ops.LAZY_STATS[k] = 0
+        ten1, sc1 = _lazy_chain(gtn, T, fmt)
+        st = dict(_ops.LAZY_STATS)
+        unwritten = [getattr(x, "_bt", None) is not None and x._bt.pending() is not None for x in ten1]
+        ten1 = _bits(gtn, ten1)
+    finally:
+        _ops.LAZY_PERMUTE = saved
+    assert st["created"] >= 4 and st["materialised"] <= 1, st     # (the scaled copy Sc is written when it is scaled)
+    assert unwritten[:3] == [True, True, True] and unwritten[11], unwritten
+    for k, (a, b) in enumerate(zip(ten0, ten1)):
+        assert _same(a, b), k
+    for a, b in zip(sc0, sc1):
+        assert abs(a - b) <= 4e-16 * max(abs(a), 1.0)
+
+
+def test_unwritten_permutation_is_not_an_alias(gtn):
+    """einsum returns a new tensor in the reference: writing into the source's blocks afterwards (`.data` views) must
+    not change a permutation of it that has not been written yet"""
+    rng = np.random.RandomState(92)
+    _, T = _mk(gtn, (4, 4, 4, 4), (1, 1, -1, -1), rng)
+    B = T.toblock()
+    P = gtn.einsum('ijkl->lkji', B)
+    C = gtn.einsum('ijkl->lkji', B.copy())
+    want = _bits(gtn, C)
+    views = B.data
+    for idx in np.ndindex(views.shape):
+        views[idx] *= 0.0
+    assert float(B.norm) == 0.0
+    assert _same(_bits(gtn, P), want)

@@ -215,6 +215,16 @@ def test_dense_data_inplace_edit_is_seen(gtn_host):
     GE.test_dense_data_inplace_edit_is_seen(gtn_host)
 
 
+@pytest.mark.parametrize("fmt", ["dense", "block"])
+@pytest.mark.parametrize("cplx", [True, False])
+def test_unwritten_permutations_equal_written_ones(gtn_host, fmt, cplx):
+    GE.test_unwritten_permutations_equal_written_ones(gtn_host, fmt, cplx)
+
+
+def test_unwritten_permutation_is_not_an_alias(gtn_host):
+    GE.test_unwritten_permutation_is_not_an_alias(gtn_host)
+
+
 def test_perturbed_z2_chain_truncated_vs_reference(gtn_host_trunc):
     """the 12-step dcut-16 TRG chain of tests/test_chains.py (real-reference golden) with the subspace-iteration SVD
     and its certificate running on the host double: Tnorm and F to 1e-10 at every step (no graphs here; the GPU test
