@@ -592,3 +592,42 @@ def test_unwritten_permutation_is_not_an_alias(gtn):
         views[idx] *= 0.0
     assert float(B.norm) == 0.0
     assert _same(_bits(gtn, P), want)
+
+
+@pytest.mark.parametrize("algo", ["trg", "atrg", "hotrg3dz"])
+def test_steps_with_unwritten_permutations_equal_written_ones(gtn, algo):
+    """whole coarse-graining steps on the Z2 tensor with and without the unwritten-permutation path: same Tnorm and
+    the same tensor to rounding of the norm (the data path is bit-identical; the norm of an unwritten result is summed
+    over its source, i.e. in another order)"""
+    from grassmanntn_b200 import _ops, gauge2d as g
+    old_graph, old_spec = g.STEP_GRAPH, g.SPECULATE
+    g.STEP_GRAPH = False
+
+    def run():
+        if algo == "hotrg3dz":
+            T6 = g.load_initial_tensor()
+            T, n = g.hotrg3dz(T6, T6, 8)
+            return [n], T
+        T = g.zcap(g.load_initial_tensor()).toblock()
+        ns = []
+        for i in range(3):
+            if algo == "trg":
+                T, n = g.trg(T, 8)
+            else:
+                T, n = (g.atrg2dy if i % 2 == 0 else g.atrg2dx)(T, T, 8)
+            ns.append(n)
+        return ns, T
+    saved = _ops.LAZY_PERMUTE
+    try:
+        _ops.LAZY_PERMUTE = False
+        n0, T0 = run()
+        _ops.LAZY_PERMUTE = True
+        n1, T1 = run()
+    finally:
+        _ops.LAZY_PERMUTE = saved
+        g.STEP_GRAPH, g.SPECULATE = old_graph, old_spec
+    for a, b in zip(n0, n1):
+        assert abs(a - b) <= 1e-15 * abs(a), (n0, n1)
+    (off0, b0), (off1, b1) = _bits(gtn, T0), _bits(gtn, T1)
+    assert off0 == off1
+    assert np.abs(b0 - b1).max() <= 1e-14 * np.abs(b0).max()

@@ -221,6 +221,11 @@ def test_unwritten_permutations_equal_written_ones(gtn_host, fmt, cplx):
     GE.test_unwritten_permutations_equal_written_ones(gtn_host, fmt, cplx)
 
 
+@pytest.mark.parametrize("algo", ["trg", "atrg", "hotrg3dz"])
+def test_steps_with_unwritten_permutations_equal_written_ones(gtn_host, algo):
+    GE.test_steps_with_unwritten_permutations_equal_written_ones(gtn_host, algo)
+
+
 def test_unwritten_permutation_is_not_an_alias(gtn_host):
     GE.test_unwritten_permutation_is_not_an_alias(gtn_host)
 
