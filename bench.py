@@ -720,6 +720,17 @@ def other_workloads(gtn, torch, data, stats, chi):
     return out
 
 
+def _written(r):
+    """a timed einsum must have written its result: a pure permutation is otherwise returned unwritten
+    (grassmanntn_b200._ops.LazyPermute) and would be timed as zero work"""
+    bt = getattr(r, "_bt", None)
+    if bt is not None:
+        bt.buf
+    elif hasattr(r, "buf"):
+        r.buf
+    return r
+
+
 def einsum_sweep(gtn, torch, O):
     """BASELINE.json configs[4]: synthetic Grassmann einsums, 4-8 leg complex128 tensors (seeded,
     uniform [0,1) + i uniform [0,1), Grassmann-odd entries zeroed), sign-only and sign+contract.
@@ -755,13 +766,13 @@ def einsum_sweep(gtn, torch, O):
             d = O.random_dense(shape, st, dtype=complex, rng=rng)
             objs.append(gtn.dense(d.data, statistics=st).toblock())
         for _ in range(2):
-            r = gtn.einsum(sub, *objs)
+            r = _written(gtn.einsum(sub, *objs))
         torch.cuda.synchronize()
         E.PROF.start()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         for _ in range(5):
-            r = gtn.einsum(sub, *objs)
+            r = _written(gtn.einsum(sub, *objs))
         e.record()
         torch.cuda.synchronize()
         pr = E.PROF.stop()
@@ -844,13 +855,13 @@ def microbench(gtn, E, torch, dev, args, hbm_peak):
         bt = A._get_bt()
         from grassmanntn_b200 import _ops
         for _ in range(3):
-            r = _ops.einsum_bt('ijkl->jkli', [bt])
+            r = _written(_ops.einsum_bt('ijkl->jkli', [bt]))
         torch.cuda.synchronize()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         reps = 10 if D == 64 else 3
         s.record()
         for _ in range(reps):
-            r = _ops.einsum_bt('ijkl->jkli', [bt])
+            r = _written(_ops.einsum_bt('ijkl->jkli', [bt]))
         e.record()
         torch.cuda.synchronize()
         ms = s.elapsed_time(e) / reps
@@ -879,14 +890,14 @@ def microbench(gtn, E, torch, dev, args, hbm_peak):
             VV = even_block((1, 1, -1, 1))
             UU = even_block((-1, 1, -1, 1))
             for _ in range(2):
-                r = gtn.einsum('lxzk,jzxi->ijkl', VV, UU)
+                r = _written(gtn.einsum('lxzk,jzxi->ijkl', VV, UU))
             torch.cuda.synchronize()
             E.PROF.start()
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             reps = 3
             s.record()
             for _ in range(reps):
-                r = gtn.einsum('lxzk,jzxi->ijkl', VV, UU)
+                r = _written(gtn.einsum('lxzk,jzxi->ijkl', VV, UU))
             e.record()
             torch.cuda.synchronize()
             pr = E.PROF.stop()

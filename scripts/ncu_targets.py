@@ -13,7 +13,7 @@ if which in ("all", "permute"):
     x = torch.rand(D ** 4, dtype=torch.float64, device=dev).to(torch.complex128).view(D, D, D, D)
     bt = gtn.dense(x, statistics=(1, 1, -1, -1))._get_bt()
     for _ in range(3):
-        r = _ops.einsum_bt('ijkl->jkli', [bt])
+        r = _ops.einsum_bt('ijkl->jkli', [bt]); r.buf        # (.buf: a pure permutation is written on demand)
     torch.cuda.synchronize()
 if which in ("all", "gemm"):
     N = 4096
