@@ -226,6 +226,60 @@ def test_steps_with_unwritten_permutations_equal_written_ones(gtn_host, algo):
     GE.test_steps_with_unwritten_permutations_equal_written_ones(gtn_host, algo)
 
 
+@pytest.mark.parametrize("seed", range(12))
+def test_random_chains_of_unwritten_permutations(gtn_host, seed):
+    """random chains of signed permutations and conjugates (2-4 links) ending in a consumer that packs from the
+    stored source -- a contraction with a partner, a trace, a decomposition -- against the same chain with every link
+    written: identical bits (the composed GF(2) sign programs, incl. the p*p = p folding of traced pairs)"""
+    import itertools
+    import gtn_oracle as O
+    from grassmanntn_b200 import _ops
+    gtn = gtn_host
+    rng = np.random.RandomState(1000 + seed)
+    nleg = int(rng.choice([4, 4, 6]))
+    dims = [int(rng.choice([2, 4])) for _ in range(nleg // 2)]
+    shape = tuple(dims + dims)                       # legs a and a + nleg/2 have the same dimension ...
+    stats = tuple([1] * (nleg // 2) + [-1] * (nleg // 2))       # ... and opposite statistics (traceable pairs)
+    o = O.random_dense(shape, stats, dtype=complex, rng=rng)
+    letters = "abcdef"[:nleg]
+    links = []
+    for _ in range(int(rng.randint(2, 5))):
+        if rng.rand() < 0.3:
+            links.append(("h", int(rng.randint(1, nleg))))
+        else:
+            links.append(("p", "".join(rng.permutation(list(letters)))))
+    consumer = int(rng.randint(0, 3))
+
+    def run(fmt):
+        X = gtn.dense(o.data, statistics=stats)
+        X = X.toblock() if fmt else X
+        Y = X
+        for kind, arg in links:
+            if kind == "h":
+                Y = Y.hconjugate(letters[:arg] + "|" + letters[arg:])
+            else:
+                Y = gtn.einsum(letters + "->" + arg, Y)
+        outs = [Y]
+        if consumer == 0:                            # contraction with its own conjugate over all but one leg
+            Z = Y.hconjugate(letters[:1] + "|" + letters[1:])
+            outs.append(gtn.einsum(letters + "," + letters[1:] + "z->" + letters[0] + "z", Y, Z))
+        elif consumer == 1:                          # decomposition
+            outs.extend(Y.svd(letters[:nleg // 2] + "|" + letters[nleg // 2:]))
+        else:                                        # norm and scaled copy
+            outs.append(Y * 0.25)
+        return GE._bits(gtn, outs)
+    saved = _ops.LAZY_PERMUTE
+    try:
+        for fmt in (False, True):
+            _ops.LAZY_PERMUTE = False
+            a = run(fmt)
+            _ops.LAZY_PERMUTE = True
+            b = run(fmt)
+            assert GE._same(a, b), (links, consumer, fmt)
+    finally:
+        _ops.LAZY_PERMUTE = saved
+
+
 def test_unwritten_permutation_is_not_an_alias(gtn_host):
     GE.test_unwritten_permutation_is_not_an_alias(gtn_host)
 
